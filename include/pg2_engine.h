@@ -1,0 +1,88 @@
+/* procgen2-b200 — C ABI of the batched, GPU-resident environment engine.
+ *
+ * Plain C: pointers and sizes only, no torch / CUDA types in the signatures. The per-game
+ * drop-in libraries (libCoinRun.so, libMaze.so, ... — same file names as the reference's CMake
+ * targets, games/<g>/CMakeLists.txt `add_library(<Game> SHARED ...)`) implement the reference's
+ * cenv ABI (include/cenv.h) on top of these entry points; Python front-ends bind them with
+ * ctypes (procgen2_b200/engine.py).
+ *
+ * What each call replaces in the reference (one environment per process there, N here):
+ *   pg2_create  <- cenv_make   games/coinrun/coinrun.cpp:127-306 (maze.cpp:85, bossfight.cpp:…)
+ *   pg2_reset   <- cenv_reset  games/coinrun/coinrun.cpp:308-339
+ *   pg2_step*   <- cenv_step   games/coinrun/coinrun.cpp:341-391 (+ caller-side
+ *                  "if terminated: reset" of game_test.py:38-40, done on device as auto-reset)
+ *   pg2_fetch   <- the observation / reward / terminated read-out of cenv/cenv.py:289-309
+ *   pg2_destroy <- cenv_close  games/coinrun/coinrun.cpp:413-441
+ *
+ * Environment i of an engine created with (seed, first_env) is seeded `seed + first_env + i`
+ * and reproduces, bit for bit, a reference process created with that seed
+ * (cenv_make(seed) -> cenv_reset() -> cenv_step()* with reset-on-terminate).
+ *
+ * All functions return 0 on success, non-zero on error (pg2_last_error() gives the text) —
+ * the same convention as the cenv entry points (cenv/cenv.py:208-209).
+ */
+#ifndef PG2_ENGINE_H
+#define PG2_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG2_API __attribute__((__visibility__("default")))
+
+typedef struct pg2_engine pg2_engine;
+
+typedef struct {
+    const char* game;            /* "maze" | "coinrun" | "bossfight" | "chaser" | "climber" | "caveflyer" | "jumper" */
+    int32_t num_envs;            /* environments owned by this engine (this GPU's shard) */
+    int32_t seed;                /* base seed; env i gets seed + first_env + i (uint32 wrap) */
+    int32_t first_env;           /* global index of this shard's first environment */
+    int32_t device;              /* CUDA device ordinal */
+    int32_t max_episode_steps;   /* extension: >0 truncates episodes; 0 = reference behaviour */
+    const char* assets_path;     /* packed asset blob; NULL -> $PG2_ASSETS or <lib dir>/../data/assets.bin */
+} pg2_config;
+
+PG2_API int32_t pg2_create(const pg2_config* cfg, pg2_engine** out);
+PG2_API void pg2_destroy(pg2_engine* e);
+
+/* cenv_reset for every environment. seeds: NULL (continue the RNG streams) or num_envs host
+ * int32 (option "seed" of cenv_reset: reseed env i with seeds[i]). Renders the reset frame. */
+PG2_API int32_t pg2_reset(pg2_engine* e, const int32_t* seeds);
+
+/* One cenv_step for every environment. `actions` = num_envs int32 in HOST memory (copied to
+ * the device inside the call) / DEVICE memory. Asynchronous: results stay in HBM. */
+PG2_API int32_t pg2_step(pg2_engine* e, const int32_t* actions_host);
+PG2_API int32_t pg2_step_device(pg2_engine* e, const int32_t* actions_device);
+
+/* Copy results of the last step/reset to host buffers (any pointer may be NULL) and wait.
+ * obs: num_envs*12288 uint8 (64x64x3 RGB, row-major), reward: num_envs float,
+ * terminated / truncated: num_envs uint8. */
+PG2_API int32_t pg2_fetch(pg2_engine* e, uint8_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated);
+
+/* Device-resident results (valid until the next step on the engine's stream). */
+PG2_API uint8_t* pg2_obs_device(pg2_engine* e);
+PG2_API float* pg2_reward_device(pg2_engine* e);
+PG2_API uint8_t* pg2_terminated_device(pg2_engine* e);
+PG2_API uint8_t* pg2_truncated_device(pg2_engine* e);
+
+PG2_API int32_t pg2_sync(pg2_engine* e);
+PG2_API void* pg2_stream(pg2_engine* e);            /* cudaStream_t the engine launches on */
+PG2_API int32_t pg2_num_envs(pg2_engine* e);
+PG2_API int64_t pg2_kernel_launches(pg2_engine* e); /* kernels launched so far (bench.py gpu_launches) */
+PG2_API int64_t pg2_state_bytes_per_env(pg2_engine* e);
+
+/* Test / checkpoint access to the structure-of-arrays state: copies field `name` of the game
+ * (or common) state to host memory. Returns bytes written, or <0 if the field is unknown or
+ * `capacity` is too small. per_env receives the element count per environment. */
+PG2_API int64_t pg2_read_field(pg2_engine* e, const char* name, void* out, int64_t capacity, int32_t* elem_size, int32_t* per_env);
+PG2_API int64_t pg2_write_field(pg2_engine* e, const char* name, const void* in, int64_t bytes);
+
+PG2_API const char* pg2_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,349 @@
+// Host side of the batched engine + kernel entry points (sm_100a).
+//
+// Per step, per game G, three kernels run back to back on one stream:
+//   k_step<G>    thread-per-env: action decode, sub-step loop (entity update, physics, tile /
+//                entity collision), reward / terminated, append finished envs to the reset list
+//                (warp ballot + one atomic per warp)                 <- cenv_step  (<g>.cpp)
+//   k_reset<G>   warp-per-finished-env: reset() with on-device procedural level generation,
+//                continuing the env's MT19937 stream                <- reset()     (<g>.cpp)
+//   k_render<G>  CTA-per-env: 64x64x3 observation, TMA bulk store    <- render_game (<g>.cpp) + SDL
+// No CPU fallback exists: every entry point fails loudly when CUDA is unavailable.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pg2_engine.h"
+#include "assets.h"
+#include "games/all_games.cuh"
+#include "pg2_kernels.cuh"
+
+namespace pg2 {
+
+static thread_local std::string g_error;
+static int fail(const std::string& msg) { g_error = msg; return 1; }
+
+#define PG2_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t err__ = (call);                                                             \
+        if (err__ != cudaSuccess) {                                                             \
+            g_error = std::string(#call) + ": " + cudaGetErrorString(err__);                    \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+
+// rng.seed(seed) for envs [0, N) (or the listed ones): seeds[i] given, else base + first + i.
+__global__ void k_seed(CommonState c, int N, uint32_t base_seed, const int32_t* __restrict__ seeds, int init_persistent) {
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= N) return;
+    seed_body(c, env, seeds ? (uint32_t)seeds[env] : base_seed + (uint32_t)env, init_persistent != 0);
+}
+
+template <class G>
+__global__ void __launch_bounds__(128) k_step(typename G::State s, CommonState c, const int32_t* __restrict__ actions,
+                                              float* __restrict__ reward, uint8_t* __restrict__ terminated,
+                                              uint8_t* __restrict__ truncated, int* __restrict__ reset_list,
+                                              int* __restrict__ reset_count, int N, int max_episode_steps) {
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    bool done = false;
+    if (env < N) done = step_body<G>(s, c, env, actions[env], reward, terminated, truncated, max_episode_steps);
+    // reset-list compaction: one atomic per warp
+    unsigned m = __ballot_sync(0xffffffffu, done);
+    if (m) {
+        int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(reset_count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (done) reset_list[base + __popc(m & ((1u << lane) - 1u))] = env;
+    }
+}
+
+// reset_list == nullptr: every env resets (cenv_make / cenv_reset).
+template <class G>
+__global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::State s, CommonState c,
+                                                                    const int* __restrict__ reset_list,
+                                                                    const int* __restrict__ reset_count, int N) {
+    extern __shared__ __align__(16) char smem[];
+    const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* mt = (uint32_t*)smem + warp_in_cta * MT_N;
+    char* arena = smem + RESET_WARPS_PER_CTA * MT_N * 4 + warp_in_cta * RESET_ARENA_BYTES;
+    const int count = reset_list ? *reset_count : N;
+    const int total_warps = gridDim.x * RESET_WARPS_PER_CTA;
+    for (int w = blockIdx.x * RESET_WARPS_PER_CTA + warp_in_cta; w < count; w += total_warps) {
+        int env = reset_list ? reset_list[w] : w;
+        reset_body<G>(s, c, env, mt, arena, lane);
+    }
+}
+
+template <class G>
+__global__ void __launch_bounds__(RENDER_THREADS) k_render(typename G::State s, CommonState c, const TexInfo* __restrict__ tex,
+                                                           const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs,
+                                                           int* __restrict__ reset_count, int N) {
+    __shared__ Frame f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reset_count = 0;   // consumed by k_reset earlier on this stream
+    for (int env = blockIdx.x; env < N; env += gridDim.x) render_body<G>(s, c, env, f, tex, atlas, obs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host engine
+
+struct EngineBase {
+    virtual ~EngineBase() {}
+    virtual int reset(const int32_t* seeds) = 0;
+    virtual int step_device(const int32_t* actions_dev) = 0;
+    virtual bool find_field(const char* name, void** ptr, int* esz, int* pe) = 0;
+    virtual size_t state_bytes_per_env() = 0;
+
+    int device = 0, N = 0, max_episode_steps = 0;
+    uint32_t base_seed = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    int num_sms = 148;
+    // device buffers
+    void* state_mem = nullptr;
+    void* common_mem = nullptr;
+    CommonState common;
+    uint8_t* obs = nullptr;
+    float* reward = nullptr;
+    uint8_t* terminated = nullptr;
+    uint8_t* truncated = nullptr;
+    int32_t* actions = nullptr;
+    int32_t* seeds_dev = nullptr;
+    int* reset_list = nullptr;
+    int* reset_count = nullptr;
+    TexInfo* texinfo = nullptr;
+    uint32_t* atlas = nullptr;
+    int32_t* actions_pinned = nullptr;
+
+    int free_all() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        cudaFree(state_mem); cudaFree(common_mem); cudaFree(obs); cudaFree(reward); cudaFree(terminated);
+        cudaFree(truncated); cudaFree(actions); cudaFree(seeds_dev); cudaFree(reset_list); cudaFree(reset_count);
+        cudaFree(texinfo); cudaFree(atlas);
+        if (actions_pinned) cudaFreeHost(actions_pinned);
+        if (stream) cudaStreamDestroy(stream);
+        return 0;
+    }
+};
+
+template <class G>
+struct Engine : EngineBase {
+    typename G::State st;
+
+    int init(const pg2_config* cfg) {
+        device = cfg->device; N = cfg->num_envs; max_episode_steps = cfg->max_episode_steps;
+        base_seed = (uint32_t)cfg->seed + (uint32_t)cfg->first_env;
+        PG2_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        PG2_CUDA(cudaGetDeviceProperties(&prop, device));
+        num_sms = prop.multiProcessorCount;
+        PG2_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        PG2_CUDA(cudaMalloc(&state_mem, G::State::bytes(N)));
+        PG2_CUDA(cudaMemsetAsync(state_mem, 0, G::State::bytes(N), stream));
+        st = G::State::bind(state_mem, N);
+        PG2_CUDA(cudaMalloc(&common_mem, CommonState::bytes(N)));
+        PG2_CUDA(cudaMemsetAsync(common_mem, 0, CommonState::bytes(N), stream));
+        common = CommonState::bind(common_mem, N);
+        PG2_CUDA(cudaMalloc(&obs, (size_t)N * OBS_BYTES));
+        PG2_CUDA(cudaMemsetAsync(obs, 0, (size_t)N * OBS_BYTES, stream));
+        PG2_CUDA(cudaMalloc(&reward, sizeof(float) * N));
+        PG2_CUDA(cudaMalloc(&terminated, N));
+        PG2_CUDA(cudaMalloc(&truncated, N));
+        PG2_CUDA(cudaMemsetAsync(reward, 0, sizeof(float) * N, stream));
+        PG2_CUDA(cudaMemsetAsync(terminated, 0, N, stream));
+        PG2_CUDA(cudaMemsetAsync(truncated, 0, N, stream));
+        PG2_CUDA(cudaMalloc(&actions, sizeof(int32_t) * N));
+        PG2_CUDA(cudaMalloc(&seeds_dev, sizeof(int32_t) * N));
+        PG2_CUDA(cudaMalloc(&reset_list, sizeof(int) * N));
+        PG2_CUDA(cudaMalloc(&reset_count, sizeof(int)));
+        PG2_CUDA(cudaMemsetAsync(reset_count, 0, sizeof(int), stream));
+        PG2_CUDA(cudaMallocHost(&actions_pinned, sizeof(int32_t) * N));
+        // texture atlas: decode the game's textures from the packed blob, upload once
+        int ntex = 0;
+        const char* const* names = G::texture_names(&ntex);
+        std::vector<TexInfo> infos(ntex);
+        std::vector<uint32_t> texels;
+        std::string err;
+        if (!load_textures(cfg->assets_path, names, ntex, &infos, &texels, &err)) return fail(err);
+        PG2_CUDA(cudaMalloc(&texinfo, sizeof(TexInfo) * ntex));
+        PG2_CUDA(cudaMalloc(&atlas, sizeof(uint32_t) * texels.size()));
+        PG2_CUDA(cudaMemcpyAsync(texinfo, infos.data(), sizeof(TexInfo) * ntex, cudaMemcpyHostToDevice, stream));
+        PG2_CUDA(cudaMemcpyAsync(atlas, texels.data(), sizeof(uint32_t) * texels.size(), cudaMemcpyHostToDevice, stream));
+        PG2_CUDA(cudaStreamSynchronize(stream));
+        PG2_CUDA(cudaFuncSetAttribute(k_reset<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, reset_smem()));
+        // cenv_make: seed, then reset() once (level #1 is generated and never rendered, Q29)
+        k_seed<<<(N + 127) / 128, 128, 0, stream>>>(common, N, base_seed, nullptr, 1);
+        launches++;
+        launch_reset_all();
+        PG2_CUDA(cudaGetLastError());
+        PG2_CUDA(cudaStreamSynchronize(stream));
+        return 0;
+    }
+
+    static int reset_smem() { return RESET_WARPS_PER_CTA * (MT_N * 4 + RESET_ARENA_BYTES); }
+    int reset_grid(int count) const {
+        int ctas = (count + RESET_WARPS_PER_CTA - 1) / RESET_WARPS_PER_CTA;
+        return ctas < num_sms * 4 ? (ctas < 1 ? 1 : ctas) : num_sms * 4;
+    }
+    void launch_reset_all() {
+        k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, nullptr, nullptr, N);
+        launches++;
+    }
+    void launch_render() {
+        int grid = N < num_sms * 8 ? N : num_sms * 8;
+        k_render<G><<<grid, RENDER_THREADS, 0, stream>>>(st, common, texinfo, atlas, obs, reset_count, N);
+        launches++;
+    }
+
+    int reset(const int32_t* seeds) override {
+        PG2_CUDA(cudaSetDevice(device));
+        if (seeds) {
+            memcpy(actions_pinned, seeds, sizeof(int32_t) * N);
+            PG2_CUDA(cudaMemcpyAsync(seeds_dev, actions_pinned, sizeof(int32_t) * N, cudaMemcpyHostToDevice, stream));
+            k_seed<<<(N + 127) / 128, 128, 0, stream>>>(common, N, 0u, seeds_dev, 0);
+            launches++;
+        }
+        launch_reset_all();
+        launch_render();
+        PG2_CUDA(cudaMemsetAsync(reward, 0, sizeof(float) * N, stream));
+        PG2_CUDA(cudaMemsetAsync(terminated, 0, N, stream));
+        PG2_CUDA(cudaMemsetAsync(truncated, 0, N, stream));
+        PG2_CUDA(cudaGetLastError());
+        return 0;
+    }
+
+    int step_device(const int32_t* actions_dev) override {
+        k_step<G><<<(N + 127) / 128, 128, 0, stream>>>(st, common, actions_dev, reward, terminated, truncated, reset_list,
+                                                     reset_count, N, max_episode_steps);
+        k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count, N);
+        launches += 2;
+        launch_render();
+        PG2_CUDA(cudaGetLastError());
+        return 0;
+    }
+
+    bool find_field(const char* name, void** ptr, int* esz, int* pe) override {
+        return st.find(name, ptr, esz, pe) || common.find(name, ptr, esz, pe);
+    }
+    size_t state_bytes_per_env() override { return (G::State::bytes(1024) + CommonState::bytes(1024)) / 1024; }
+};
+
+}  // namespace pg2
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+
+using namespace pg2;
+
+struct pg2_engine { std::unique_ptr<EngineBase> impl; };
+
+extern "C" {
+
+const char* pg2_last_error(void) { return g_error.c_str(); }
+
+int32_t pg2_create(const pg2_config* cfg, pg2_engine** out) {
+    if (!cfg || !out || !cfg->game) return fail("pg2_create: null argument");
+    if (cfg->num_envs <= 0) return fail("pg2_create: num_envs must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("pg2_create: no CUDA device available — this engine has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("pg2_create: invalid device ordinal");
+    std::string g = cfg->game;
+    for (auto& ch : g) ch = (char)tolower(ch);
+    std::unique_ptr<EngineBase> impl;
+    int rc = 1;
+#define PG2_TRY_GAME(NAME, TYPE) \
+    if (!impl && g == NAME) { auto* e = new Engine<TYPE>(); impl.reset(e); rc = e->init(cfg); }
+    PG2_FOR_EACH_GAME(PG2_TRY_GAME)
+#undef PG2_TRY_GAME
+    if (!impl) return fail("pg2_create: unknown game '" + g + "'");
+    if (rc) { impl->free_all(); return rc; }
+    *out = new pg2_engine{ std::move(impl) };
+    return 0;
+}
+
+void pg2_destroy(pg2_engine* e) {
+    if (!e) return;
+    e->impl->free_all();
+    delete e;
+}
+
+int32_t pg2_reset(pg2_engine* e, const int32_t* seeds) { return e->impl->reset(seeds); }
+
+int32_t pg2_step(pg2_engine* e, const int32_t* actions_host) {
+    EngineBase* b = e->impl.get();
+    PG2_CUDA(cudaSetDevice(b->device));
+    // the pinned staging buffer is reused every step: wait for the previous copy to have left it
+    PG2_CUDA(cudaStreamSynchronize(b->stream));
+    memcpy(b->actions_pinned, actions_host, sizeof(int32_t) * b->N);
+    PG2_CUDA(cudaMemcpyAsync(b->actions, b->actions_pinned, sizeof(int32_t) * b->N, cudaMemcpyHostToDevice, b->stream));
+    return b->step_device(b->actions);
+}
+
+int32_t pg2_step_device(pg2_engine* e, const int32_t* actions_device) {
+    PG2_CUDA(cudaSetDevice(e->impl->device));
+    return e->impl->step_device(actions_device);
+}
+
+int32_t pg2_fetch(pg2_engine* e, uint8_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated) {
+    EngineBase* b = e->impl.get();
+    PG2_CUDA(cudaSetDevice(b->device));
+    if (obs) PG2_CUDA(cudaMemcpyAsync(obs, b->obs, (size_t)b->N * OBS_BYTES, cudaMemcpyDeviceToHost, b->stream));
+    if (reward) PG2_CUDA(cudaMemcpyAsync(reward, b->reward, sizeof(float) * b->N, cudaMemcpyDeviceToHost, b->stream));
+    if (terminated) PG2_CUDA(cudaMemcpyAsync(terminated, b->terminated, b->N, cudaMemcpyDeviceToHost, b->stream));
+    if (truncated) PG2_CUDA(cudaMemcpyAsync(truncated, b->truncated, b->N, cudaMemcpyDeviceToHost, b->stream));
+    PG2_CUDA(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+uint8_t* pg2_obs_device(pg2_engine* e) { return e->impl->obs; }
+float* pg2_reward_device(pg2_engine* e) { return e->impl->reward; }
+uint8_t* pg2_terminated_device(pg2_engine* e) { return e->impl->terminated; }
+uint8_t* pg2_truncated_device(pg2_engine* e) { return e->impl->truncated; }
+
+int32_t pg2_sync(pg2_engine* e) {
+    PG2_CUDA(cudaSetDevice(e->impl->device));
+    PG2_CUDA(cudaStreamSynchronize(e->impl->stream));
+    return 0;
+}
+void* pg2_stream(pg2_engine* e) { return (void*)e->impl->stream; }
+int32_t pg2_num_envs(pg2_engine* e) { return e->impl->N; }
+int64_t pg2_kernel_launches(pg2_engine* e) { return e->impl->launches; }
+int64_t pg2_state_bytes_per_env(pg2_engine* e) { return (int64_t)e->impl->state_bytes_per_env(); }
+
+int64_t pg2_read_field(pg2_engine* e, const char* name, void* out, int64_t capacity, int32_t* elem_size, int32_t* per_env) {
+    EngineBase* b = e->impl.get();
+    void* ptr; int esz, pe;
+    if (!b->find_field(name, &ptr, &esz, &pe)) { g_error = std::string("unknown field ") + name; return -1; }
+    if (elem_size) *elem_size = esz;
+    if (per_env) *per_env = pe;
+    int64_t bytes = (int64_t)esz * pe * b->N;
+    if (!out) return bytes;
+    if (capacity < bytes) { g_error = "pg2_read_field: buffer too small"; return -2; }
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    if (cudaMemcpy(out, ptr, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { g_error = "pg2_read_field: copy failed"; return -3; }
+    return bytes;
+}
+
+int64_t pg2_write_field(pg2_engine* e, const char* name, const void* in, int64_t bytes_in) {
+    EngineBase* b = e->impl.get();
+    void* ptr; int esz, pe;
+    if (!b->find_field(name, &ptr, &esz, &pe)) { g_error = std::string("unknown field ") + name; return -1; }
+    int64_t bytes = (int64_t)esz * pe * b->N;
+    if (bytes_in != bytes) { g_error = "pg2_write_field: size mismatch"; return -2; }
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    if (cudaMemcpy(ptr, in, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { g_error = "pg2_write_field: copy failed"; return -3; }
+    return bytes;
+}
+
+}  // extern "C"

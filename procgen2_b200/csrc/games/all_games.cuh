@@ -1,0 +1,6 @@
+// Registry of the games compiled into the engine. PG2_FOR_EACH_GAME(X) expands X(name, Type).
+#pragma once
+#include "maze.cuh"
+
+#define PG2_FOR_EACH_GAME(X) \
+    X("maze", pg2::Maze)

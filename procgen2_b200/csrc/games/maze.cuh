@@ -1,0 +1,262 @@
+// Maze — device restatement of /root/reference/games/maze/:
+//   step logic   System_Agent::update          common_systems.cpp:69-136, cenv_step maze.cpp:279-326
+//   level gen    System_Tilemap::regenerate    tilemap.cpp:31-109, Maze_Generator maze_generator.cpp:47-195,
+//                reset()                       maze.cpp:416-438
+//   frame        render_game                   maze.cpp:386-414, tilemap.cpp:111-131,
+//                sprite / agent render         common_systems.cpp:41-63, 138-151
+// hard_mode only (compile-time default of the reference): 25x25 world, all visible.
+#pragma once
+#include "../pg2_common.cuh"
+#include "../pg2_render.cuh"
+#include "../pg2_state.cuh"
+#include "../pg2_warp.cuh"
+
+namespace pg2 {
+
+#define PG2_MAZE_FIELDS(F)                                              \
+    F(uint8_t, tiles, 640)   /* env-major, [y + x*25], 0 empty 1 wall */ \
+    F(float, agent_x, 1)                                                \
+    F(float, agent_y, 1)                                                \
+    F(uint8_t, face_forward, 1)                                         \
+    F(float, goal_x, 1)                                                 \
+    F(float, goal_y, 1)                                                 \
+    F(int32_t, bg_index, 1)                                             \
+    F(float, bg_offset, 1)                                              \
+    F(int32_t, curr_step, 1)
+
+PG2_DEFINE_STATE(MazeState, PG2_MAZE_FIELDS)
+
+struct Maze {
+    using State = MazeState;
+    static constexpr int WORLD = 25;          // world_dim (tilemap.cpp:36)
+    static constexpr int TIMEOUT = 500;       // maze.cpp:49
+    static constexpr int TILE_CLASSES = 1;
+    static constexpr int TILE_STRIDE = 640;
+    enum Tex { T_WALL = 0, T_CHEESE = 1, T_MOUSE = 2, T_BG0 = 3, NUM_BG = 9, NUM_TEX = 12 };
+
+    static const char* const* texture_names(int* count) {
+        static const char* const names[NUM_TEX] = {
+            "assets/kenney/Ground/Sand/sandCenter.png",
+            "assets/misc_assets/cheese.png",
+            "assets/kenney/Enemies/mouse_move.png",
+            "assets/topdown_backgrounds/floortiles.png",
+            "assets/topdown_backgrounds/backgrounddetailed1.png",
+            "assets/topdown_backgrounds/backgrounddetailed2.png",
+            "assets/topdown_backgrounds/backgrounddetailed3.png",
+            "assets/topdown_backgrounds/backgrounddetailed4.png",
+            "assets/topdown_backgrounds/backgrounddetailed5.png",
+            "assets/topdown_backgrounds/backgrounddetailed6.png",
+            "assets/topdown_backgrounds/backgrounddetailed7.png",
+            "assets/topdown_backgrounds/backgrounddetailed8.png",
+        };
+        *count = NUM_TEX;
+        return names;
+    }
+
+    // System_Tilemap::get (tilemap.h:79-84): out of bounds is a wall. (x, y) in map space.
+    static PG2_DEV int get(const uint8_t* tiles, int x, int y) {
+        if (x < 0 || y < 0 || x >= WORLD || y >= WORLD) return 1;
+        return tiles[y + x * WORLD];
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // cenv_step body for one environment (thread-per-env). Returns terminated.
+    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward) {
+        const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
+        float px = s.agent_x[env], py = s.agent_y[env];
+        int movement_x = action / 3 - 1;
+        int movement_y = movement_x ? 0 : -(action % 3 - 1);
+        if (movement_x) {
+            int nx = f2i(__fadd_rn(px, (float)movement_x));
+            if (get(tiles, nx, WORLD - 1 - f2i(py)) == 0) px = __fadd_rn((float)nx, 0.5f);
+        } else if (movement_y) {
+            int ny = f2i(__fadd_rn(py, (float)movement_y));
+            if (get(tiles, f2i(px), WORLD - 1 - ny) == 0) py = __fadd_rn((float)ny, 0.5f);
+        }
+        Rect me{ __fadd_rn(px, -0.5f), __fadd_rn(py, -0.5f), 1.0f, 1.0f };
+        Rect goal{ __fadd_rn(s.goal_x[env], -0.5f), __fadd_rn(s.goal_y[env], -0.5f), 1.0f, 1.0f };
+        bool reached = check_collision(me, goal);
+        if (movement_x > 0) s.face_forward[env] = 1;
+        else if (movement_x < 0) s.face_forward[env] = 0;
+        s.agent_x[env] = px; s.agent_y[env] = py;
+        c.sprites_valid[env] = 1;                 // sprite_render->update(dt)
+        *reward = reached ? 10.0f : 0.0f;
+        bool terminated = reached;
+        int cs = s.curr_step[env] + 1;
+        s.curr_step[env] = cs;
+        if (cs >= TIMEOUT) terminated = true;     // maze.cpp:308-310
+        return terminated;
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // reset(): one warp, redundant-uniform execution (pg2_warp.cuh).
+    static PG2_DEV_NOINLINE void regenerate(const State& s, const CommonState& c, int env, WarpCtx& w) {
+        const int lane = w.lane;
+        uint8_t* tiles = w.alloc<uint8_t>(TILE_STRIDE);
+        w.fill<uint8_t>(tiles, TILE_STRIDE, 1);                       // std::fill(..., wall)
+
+        const int maze_dim = w.rng.uniform_int(0, (WORLD - 1) / 2 - 1) * 2 + 3;
+        const int margin = (WORLD - maze_dim) / 2;
+
+        // ---- Maze_Generator::generate_maze(maze_dim, maze_dim) (maze_generator.cpp:55-139)
+        const int mw = maze_dim, mh = maze_dim;
+        const int aw = mw + 2, ah = mh + 2;                            // padded array
+        uint8_t* grid = w.alloc<uint8_t>(27 * 27);
+        int16_t* set_idx = w.alloc<int16_t>(27 * 27);
+        uint8_t* set_rank = w.alloc<uint8_t>(27 * 27);
+        int16_t* free_cells = w.alloc<int16_t>(27 * 27);
+        uint8_t* is_free = w.alloc<uint8_t>(25 * 25);
+        uint32_t* walls = w.alloc<uint32_t>(320);                       // x1 | y1<<8 | x2<<16 | y2<<24
+        w.fill<uint8_t>(grid, aw * ah, 1);
+        w.fill<uint8_t>(is_free, 25 * 25, 0);
+        for (int i = lane; i < mw * mh; i += WARP_LANES) { set_idx[i] = (int16_t)i; set_rank[i] = 0; }
+        __syncwarp();
+        grid[1 + ah * 1] = 0;                                          // corner
+        int num_free = 0;
+        int nwalls = 0;
+        for (int i = 1; i < mw; i += 2)
+            for (int j = 0; j < mh; j += 2)
+                if (i > 0 && i < mw - 1) { walls[nwalls] = (uint32_t)(i - 1) | (uint32_t)j << 8 | (uint32_t)(i + 1) << 16 | (uint32_t)j << 24; nwalls++; }
+        for (int i = 0; i < mw; i += 2)
+            for (int j = 1; j < mh; j += 2)
+                if (j > 0 && j < mh - 1) { walls[nwalls] = (uint32_t)i | (uint32_t)(j - 1) << 8 | (uint32_t)i << 16 | (uint32_t)(j + 1) << 24; nwalls++; }
+        __syncwarp();
+
+        auto find = [&](int cell) {                                    // path halving
+            int cur = cell;
+            while (set_idx[cur] != cur) { int gp = set_idx[set_idx[cur]]; set_idx[cur] = (int16_t)gp; cur = gp; }
+            return cur;
+        };
+        auto set_free_cell = [&](int x, int y) {
+            grid[(y + 1) + ah * (x + 1)] = 0;
+            int cell = y + mh * x;
+            if (!is_free[cell]) { free_cells[num_free] = (int16_t)cell; is_free[cell] = 1; num_free++; }
+        };
+
+        while (nwalls > 0) {
+            int n = w.rng.uniform_int(0, nwalls - 1);
+            uint32_t wl = walls[n];
+            int x1 = wl & 255, y1 = (wl >> 8) & 255, x2 = (wl >> 16) & 255, y2 = wl >> 24;
+            int s0 = find(y1 + mh * x1);
+            int s1 = find(y2 + mh * x2);
+            int x0 = (x1 + x2) / 2, y0 = (y1 + y2) / 2;
+            int center = y0 + mh * x0;
+            bool can_remove = (grid[(y0 + 1) + ah * (x0 + 1)] == 1) && (s0 != s1);
+            __syncwarp();
+            if (can_remove) {
+                set_free_cell(x1, y1);
+                set_free_cell(x0, y0);
+                set_free_cell(x2, y2);
+                if (set_rank[s0] > set_rank[s1]) {
+                    set_idx[s1] = (int16_t)s0; set_idx[center] = (int16_t)s0;
+                } else {
+                    set_idx[s0] = (int16_t)s1; set_idx[center] = (int16_t)s1;
+                    if (set_rank[s0] == set_rank[s1]) set_rank[s1]++;
+                }
+            }
+            __syncwarp();
+            // walls.erase(walls.begin() + n): order-preserving shift, 32 elements at a time
+            for (int base = n; base < nwalls - 1; base += WARP_LANES) {
+                int k = base + lane;
+                uint32_t v = (k < nwalls - 1) ? walls[k + 1] : 0u;
+                __syncwarp();
+                if (k < nwalls - 1) walls[k] = v;
+                __syncwarp();
+            }
+            nwalls--;
+        }
+
+        // ---- place_object(GOAL) (maze_generator.cpp:183-195): cell index 10 (START_CELL) and
+        // consumed cells are rejected and redrawn
+        int fidx = w.rng.uniform_int(0, num_free - 1);
+        while (free_cells[fidx] == -1 || free_cells[fidx] == 10) fidx = w.rng.uniform_int(0, num_free - 1);
+        int obj_cell = free_cells[fidx];
+        __syncwarp();
+        grid[(obj_cell % mh + 1) + ah * (obj_cell / mh + 1)] = 2;
+        __syncwarp();
+
+        // ---- copy the maze into the world (tilemap.cpp:77-88)
+        int goal_x = 0, goal_y = 0;
+        for (int i = 0; i < maze_dim; ++i)
+            for (int j = lane; j < maze_dim; j += WARP_LANES) {
+                int t = grid[(j + 1) + ah * (i + 1)];
+                tiles[(j + margin) + (i + margin) * WORLD] = (t == 1) ? 1 : 0;
+            }
+        goal_x = obj_cell / mh + margin;
+        goal_y = obj_cell % mh + margin;
+        __syncwarp();
+
+        // ---- reset() tail (maze.cpp:421-437)
+        int bg_index = w.rng.uniform_int(0, NUM_BG - 1);
+        float bg_offset = w.rng.uniform_real(0.0f, 1.0f);
+
+        uint8_t* gt = s.tiles + (size_t)env * TILE_STRIDE;
+        for (int i = lane; i < TILE_STRIDE / 4; i += WARP_LANES) ((uint32_t*)gt)[i] = ((const uint32_t*)tiles)[i];
+        if (lane == 0) {
+            s.goal_x[env] = __fadd_rn((float)goal_x, 0.5f);
+            s.goal_y[env] = __fadd_rn((float)(WORLD - 1 - goal_y), 0.5f);
+            s.agent_x[env] = __fadd_rn((float)margin, 0.5f);
+            s.agent_y[env] = __fadd_rn((float)(WORLD - 1 - margin), 0.5f);
+            s.face_forward[env] = 1;
+            s.bg_index[env] = bg_index;
+            s.bg_offset[env] = bg_offset;
+            s.curr_step[env] = 0;
+            c.cam_x[env] = __fmul_rn(__fmul_rn((float)WORLD, 0.5f), UNIT_TO_PIXELS);
+            c.cam_y[env] = __fmul_rn(__fmul_rn((float)WORLD, 0.5f), UNIT_TO_PIXELS);
+            c.sprites_valid[env] = 0;
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // render_game(true): fill the frame description (whole CTA cooperates).
+    static PG2_DEV int tile_class(uint32_t) { return 0; }
+
+    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, Frame& f, const TexInfo* tex) {
+        const int tid = threadIdx.x;
+        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(64.0f, __fmul_rn(UNIT_TO_PIXELS, (float)WORLD)) };
+        int lx, ly, ux, uy;
+        tile_window(cam, &lx, &ly, &ux, &uy);
+        int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);
+        if (is_role(0)) {
+            f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = 1;
+            // background (maze.cpp:402-408)
+            int bg = T_BG0 + s.bg_index[env];
+            TexInfo bt = tex[bg];
+            float aspect = __fdiv_rn((float)bt.w, (float)bt.h);
+            float extra = __fsub_rn(aspect, 1.0f);
+            f.pre[0] = make_blit(tex, bg, __fmul_rn(-s.bg_offset[env], extra), 0.0f, cam,
+                                 __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h));
+            f.npre = 1;
+        }
+        if (is_role(1)) {
+            int n = 0;
+            if (c.sprites_valid[env]) {   // cheese (tilemap.cpp:95-98, common_systems.cpp:41-63)
+                float gx = __fmul_rn(__fadd_rn(s.goal_x[env], -0.48f), UNIT_TO_PIXELS);
+                float gy = __fmul_rn(__fadd_rn(s.goal_y[env], -0.5f), UNIT_TO_PIXELS);
+                float sc = __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 0.95f), UNIT_TO_PIXELS), (float)tex[T_CHEESE].w);
+                f.post[n++] = make_blit(tex, T_CHEESE, gx, gy, cam, sc);
+            }
+            // agent (common_systems.cpp:138-151)
+            float ax = __fmul_rn(__fadd_rn(s.agent_x[env], -0.5f), UNIT_TO_PIXELS);
+            float ay = __fmul_rn(__fadd_rn(s.agent_y[env], -0.5f), UNIT_TO_PIXELS);
+            float sc = __fmul_rn(__fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_MOUSE].w), 1.0f);
+            f.post[n++] = make_blit(tex, T_MOUSE, ax, ay, cam, sc, 1.0f, s.face_forward[env] != 0);
+            f.npost = n;
+        }
+        // tile layer (tilemap.cpp:111-131)
+        const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_WALL].w);
+        for (int t = tid; t < ncol + nrow; t += blockDim.x) {
+            if (t < ncol) f.col[0][t] = make_axis(__fmul_rn((float)(lx + t), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tex[T_WALL].w, tscale, false, false);
+            else f.row[0][t - ncol] = make_axis(__fmul_rn((float)(ly + t - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, tex[T_WALL].h, tscale, false, true);
+        }
+        const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
+        for (int t = tid; t < ncol * nrow; t += blockDim.x) {
+            int cx = t % ncol, ry = t / ncol;
+            int id = get(tiles, lx + cx, WORLD - 1 - (ly + ry));
+            f.tile_tex[ry * MAX_WIN + cx] = id ? (uint16_t)T_WALL : NO_TILE;
+        }
+        __syncthreads();
+    }
+};
+
+}  // namespace pg2

@@ -1,0 +1,65 @@
+// Bodies of the three per-step kernels, shared between the __global__ entry points in
+// engine.cu and the single-threaded test harness tests/hostsim/ (see pg2_platform.cuh).
+#pragma once
+#include "pg2_render.cuh"
+#include "pg2_state.cuh"
+#include "pg2_warp.cuh"
+
+namespace pg2 {
+
+// rng.seed(seed) + process-lifetime defaults (cenv_make)
+PG2_DEV_NOINLINE void seed_body(const CommonState& c, int env, uint32_t seed, bool init_persistent) {
+    mt_seed(c.mt + (size_t)env * MT_N, seed);
+    c.mti[env] = MT_N;
+    if (init_persistent) {
+        c.cam_x[env] = 0.0f; c.cam_y[env] = 0.0f;   // Renderer::camera_position{0} (renderer.h:18)
+        c.sprites_valid[env] = 0; c.ep_steps[env] = 0; c.fault[env] = 0;
+    }
+}
+
+// cenv_step for one env (without the render): returns "episode over" (terminated or truncated)
+template <class G>
+PG2_DEV bool step_body(const typename G::State& s, const CommonState& c, int env, int action, float* reward,
+                       uint8_t* terminated, uint8_t* truncated, int max_episode_steps) {
+    float r = 0.0f;
+    bool term = G::step(s, c, env, action, &r);
+    bool trunc = false;
+    int ep = c.ep_steps[env] + 1;
+    if (max_episode_steps > 0 && ep >= max_episode_steps && !term) trunc = true;
+    c.ep_steps[env] = ep;
+    reward[env] = r;
+    terminated[env] = term ? 1 : 0;
+    truncated[env] = trunc ? 1 : 0;
+    return term || trunc;
+}
+
+// reset() for one env by one warp; `mt` = 624 words of per-warp scratch, `arena` = RESET_ARENA_BYTES
+template <class G>
+PG2_DEV void reset_body(const typename G::State& s, const CommonState& c, int env, uint32_t* mt, char* arena, int lane) {
+    uint32_t* gmt = c.mt + (size_t)env * MT_N;
+    for (int i = lane; i < MT_N; i += WARP_LANES) mt[i] = gmt[i];
+    __syncwarp();
+    WarpCtx ctx;
+    ctx.rng.mt = mt; ctx.rng.idx = c.mti[env]; ctx.rng.lane = lane;
+    ctx.lane = lane; ctx.arena = arena; ctx.arena_off = 0;
+    G::regenerate(s, c, env, ctx);
+    __syncwarp();
+    for (int i = lane; i < MT_N; i += WARP_LANES) gmt[i] = mt[i];
+    if (lane == 0) { c.mti[env] = ctx.rng.idx; c.ep_steps[env] = 0; }
+    __syncwarp();
+}
+
+// render_game(true) + RGBA->RGB pack for one env by one CTA
+template <class G>
+PG2_DEV void render_body(const typename G::State& s, const CommonState& c, int env, Frame& f, const TexInfo* __restrict__ tex,
+                         const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs) {
+    if (threadIdx.x == 0) { f.npre = 0; f.npost = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1; }
+    __syncthreads();
+    G::build_frame(s, c, env, f, tex);
+    __syncthreads();
+    frame_finalize(f);
+    frame_rasterise<G>(f, tex, atlas);
+    frame_store(f, obs + (size_t)env * OBS_BYTES);
+}
+
+}  // namespace pg2

@@ -1,0 +1,46 @@
+// Platform shim. The product is CUDA (sm_100a) only. The PG2_HOSTSIM branch exists solely so
+// that tests/hostsim/ can compile these same headers with g++ and single-step the generators
+// and the rasteriser against the oracle on the GPU-less build container (fast iteration on
+// parity); it is never part of any shipped library and is not a fallback — the engine
+// (engine.cu) refuses to start without a CUDA device.
+#pragma once
+#include <stdint.h>
+
+#ifndef PG2_HOSTSIM
+#include <cuda_runtime.h>
+#define PG2_DEV __device__ __forceinline__
+#define PG2_DEV_NOINLINE __device__
+namespace pg2 {
+constexpr int WARP_LANES = 32;
+}
+#else
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#define PG2_DEV inline
+#define PG2_DEV_NOINLINE inline
+#define __restrict__
+namespace pg2 {
+constexpr int WARP_LANES = 1;
+struct Dim3Sim { int x; };
+static const Dim3Sim threadIdx{ 0 }, blockDim{ 1 }, blockIdx{ 0 }, gridDim{ 1 };
+inline void __syncthreads() {}
+inline void __syncwarp() {}
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fsqrt_rn(float a) { return sqrtf(a); }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline float __uint2float_rn(uint32_t u) { return (float)u; }
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline int __ffs(uint32_t m) { return __builtin_ffs((int)m); }
+inline int __popc(uint32_t m) { return __builtin_popcount(m); }
+inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+using std::max;
+using std::min;
+}
+#endif

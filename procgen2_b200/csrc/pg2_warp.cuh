@@ -1,0 +1,35 @@
+// Execution context of the level-generation ("reset") kernel: ONE WARP per resetting
+// environment. Level generators are long, sequential, data-dependent programs (Kruskal mazes,
+// cellular automata, BFS; SURVEY §7 hard part (c)); running them one-thread-per-env would
+// serialise 32 different control flows per warp. Instead the 32 lanes of a warp execute the
+// same generator for the same environment *redundantly* (identical registers, identical RNG
+// position, shared-memory reads are broadcasts) and split only the bulk work — MT19937
+// twists, tile-map fills, cellular-automaton passes, copies to HBM — by lane id.
+#pragma once
+#include "pg2_rng.cuh"
+
+namespace pg2 {
+
+constexpr int RESET_WARPS_PER_CTA = 2;
+constexpr int RESET_ARENA_BYTES = 24 * 1024;   // per-warp scratch
+
+struct WarpCtx {
+    WarpMt rng;
+    int lane;
+    char* arena;       // per-warp shared-memory scratch
+    int arena_off;
+
+    template <class T>
+    PG2_DEV_NOINLINE T* alloc(int count) {
+        int off = (arena_off + 15) & ~15;
+        arena_off = off + (int)sizeof(T) * count;
+        return (T*)(arena + off);
+    }
+    template <class T>
+    PG2_DEV_NOINLINE void fill(T* p, int count, T v) {
+        for (int i = lane; i < count; i += WARP_LANES) p[i] = v;
+        __syncwarp();
+    }
+};
+
+}  // namespace pg2
