@@ -43,6 +43,8 @@ typedef struct {
     int32_t device;              /* CUDA device ordinal */
     int32_t max_episode_steps;   /* extension: >0 truncates episodes; 0 = reference behaviour */
     const char* assets_path;     /* packed asset blob; NULL -> $PG2_ASSETS or <lib dir>/../data/assets.bin */
+    int32_t auto_reset;          /* 1: finished envs run reset() on device inside the same step (observation =
+                                    reset frame); 0: reference behaviour, the caller calls pg2_reset */
 } pg2_config;
 
 PG2_API int32_t pg2_create(const pg2_config* cfg, pg2_engine** out);

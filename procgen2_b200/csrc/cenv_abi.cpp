@@ -1,0 +1,217 @@
+// cenv drop-in: one shared library per game (libMaze.so, libCoinRun.so, ...) exporting exactly
+// the symbols of include/cenv.h, implemented on the batched GPU engine (include/pg2_engine.h).
+// Compiled once per game with -DPG2_GAME="<game>".
+//
+// Mirrors the reference glue games/<g>/<g>.cpp:
+//   cenv_make   option parsing "seed" | "width" | "height", space/obs buffers (coinrun.cpp:127-203)
+//   cenv_reset  optional "seed" option, reset(), render, copy observation   (coinrun.cpp:308-339)
+//   cenv_step   key "action" INT, step, render, copy observation            (coinrun.cpp:341-391)
+//   cenv_close  frees the library-owned buffers                             (coinrun.cpp:413-441)
+// Extension (documented in include/cenv.h): "num_envs", "device", "max_episode_steps",
+// "auto_reset" make-options; batched "action"/"screen" buffers; per-env results as step infos.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <string>
+#include <vector>
+
+#include "cenv.h"
+#include "pg2_engine.h"
+
+#ifndef PG2_GAME
+#error "compile with -DPG2_GAME=\"<game>\""
+#endif
+
+static_assert(sizeof(cenv_key_value) == 24 && offsetof(cenv_key_value, value_buffer) == 16, "cenv_key_value layout");
+static_assert(sizeof(cenv_option) == 24 && offsetof(cenv_option, value) == 16, "cenv_option layout");
+static_assert(sizeof(cenv_step_data) == 40 && offsetof(cenv_step_data, terminated) == 24 && offsetof(cenv_step_data, truncated) == 25 &&
+              offsetof(cenv_step_data, infos_size) == 28 && offsetof(cenv_step_data, infos) == 32, "cenv_step_data layout");
+
+extern "C" {
+CENV_API cenv_make_data make_data;
+CENV_API cenv_reset_data reset_data;
+CENV_API cenv_step_data step_data;
+CENV_API cenv_render_data render_data;
+}
+
+namespace {
+
+const int kVersion = 100;        // coinrun.cpp:9
+const int kObsBytes = 64 * 64 * 3;
+const int kNumActions = 15;      // coinrun.cpp:27
+
+pg2_engine* g_engine = nullptr;
+int g_num_envs = 1;
+int g_window_w = 512, g_window_h = 512;
+
+cenv_key_value g_observation;    // shared by reset_data and step_data, like the reference
+cenv_key_value g_obs_space, g_act_space;
+cenv_key_value g_infos[3];
+float g_box[2] = { 0.0f, 255.0f };
+int32_t g_nvec[1] = { kNumActions };
+std::vector<uint8_t> g_obs, g_term, g_trunc, g_frame;
+std::vector<float> g_reward;
+std::vector<int32_t> g_actions, g_seeds;
+
+int fetch() {
+    if (pg2_fetch(g_engine, g_obs.data(), g_reward.data(), g_term.data(), g_trunc.data())) {
+        fprintf(stderr, "[procgen2_b200] %s\n", pg2_last_error());
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t cenv_get_env_version() { return kVersion; }
+
+int32_t cenv_make(const char* /*render_mode*/, cenv_option* options, int32_t options_size) {
+    if (g_engine) { pg2_destroy(g_engine); g_engine = nullptr; }
+    unsigned int seed = (unsigned int)time(nullptr);     // coinrun.cpp:130
+    int device = 0, max_episode_steps = 0, auto_reset = -1;
+    g_num_envs = 1;
+    for (int i = 0; i < options_size; i++) {
+        std::string name(options[i].name);
+        if (options[i].value_type != CENV_VALUE_TYPE_INT) continue;
+        int v = options[i].value.i;
+        if (name == "seed") seed = (unsigned int)v;
+        else if (name == "width") g_window_w = v;
+        else if (name == "height") g_window_h = v;
+        else if (name == "num_envs") g_num_envs = v;
+        else if (name == "device") device = v;
+        else if (name == "max_episode_steps") max_episode_steps = v;
+        else if (name == "auto_reset") auto_reset = v;
+    }
+    if (g_num_envs < 1 || (long long)g_num_envs * kObsBytes > 2147483647LL) {
+        fprintf(stderr, "[procgen2_b200] num_envs out of range for an int32 cenv buffer size\n");
+        return 1;
+    }
+    if (auto_reset < 0) auto_reset = g_num_envs > 1 ? 1 : 0;
+
+    pg2_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.game = PG2_GAME;
+    cfg.num_envs = g_num_envs;
+    cfg.seed = (int32_t)seed;
+    cfg.first_env = 0;
+    cfg.device = device;
+    cfg.max_episode_steps = max_episode_steps;
+    cfg.assets_path = nullptr;
+    cfg.auto_reset = auto_reset;
+    if (pg2_create(&cfg, &g_engine)) {
+        fprintf(stderr, "[procgen2_b200] cenv_make failed: %s\n", pg2_last_error());
+        return 1;
+    }
+
+    g_obs.assign((size_t)g_num_envs * kObsBytes, 0);
+    g_reward.assign(g_num_envs, 0.0f);
+    g_term.assign(g_num_envs, 0);
+    g_trunc.assign(g_num_envs, 0);
+    g_actions.assign(g_num_envs, 0);
+    g_seeds.assign(g_num_envs, 0);
+    g_frame.assign((size_t)g_window_w * g_window_h * 3, 0);
+
+    g_obs_space = { "screen", CENV_SPACE_TYPE_BOX, 2, {} };
+    g_obs_space.value_buffer.f = g_box;
+    g_act_space = { "action", CENV_SPACE_TYPE_MULTI_DISCRETE, 1, {} };
+    g_act_space.value_buffer.i = g_nvec;
+    make_data.observation_spaces_size = 1;
+    make_data.observation_spaces = &g_obs_space;
+    make_data.action_spaces_size = 1;
+    make_data.action_spaces = &g_act_space;
+
+    g_observation = { "screen", CENV_VALUE_TYPE_BYTE, g_num_envs * kObsBytes, {} };
+    g_observation.value_buffer.b = g_obs.data();
+
+    reset_data.observations_size = 1;
+    reset_data.observations = &g_observation;
+    reset_data.infos_size = 0;
+    reset_data.infos = nullptr;
+
+    step_data.observations_size = 1;
+    step_data.observations = &g_observation;
+    step_data.reward.f = 0.0f;
+    step_data.terminated = false;
+    step_data.truncated = false;
+    g_infos[0] = { "reward", CENV_VALUE_TYPE_FLOAT, g_num_envs, {} };
+    g_infos[0].value_buffer.f = g_reward.data();
+    g_infos[1] = { "terminated", CENV_VALUE_TYPE_BYTE, g_num_envs, {} };
+    g_infos[1].value_buffer.b = g_term.data();
+    g_infos[2] = { "truncated", CENV_VALUE_TYPE_BYTE, g_num_envs, {} };
+    g_infos[2].value_buffer.b = g_trunc.data();
+    step_data.infos_size = g_num_envs > 1 ? 3 : 0;
+    step_data.infos = g_num_envs > 1 ? g_infos : nullptr;
+
+    render_data.value_type = CENV_VALUE_TYPE_BYTE;
+    render_data.value_buffer_width = g_window_w;
+    render_data.value_buffer_height = g_window_h;
+    render_data.value_buffer_channels = 3;
+    render_data.value_buffer.b = g_frame.data();
+    return 0;
+}
+
+int32_t cenv_reset(cenv_option* options, int32_t options_size) {
+    if (!g_engine) return 1;
+    bool reseed = false;
+    for (int i = 0; i < options_size; i++) {
+        std::string name(options[i].name);
+        if (name == "seed" && options[i].value_type == CENV_VALUE_TYPE_INT) {
+            // env i restarts its stream from seed + i (i = 0: exactly rng.seed(seed), coinrun.cpp:313-317)
+            for (int e = 0; e < g_num_envs; e++) g_seeds[e] = (int32_t)((unsigned int)options[i].value.i + (unsigned int)e);
+            reseed = true;
+        }
+    }
+    if (pg2_reset(g_engine, reseed ? g_seeds.data() : nullptr)) {
+        fprintf(stderr, "[procgen2_b200] cenv_reset failed: %s\n", pg2_last_error());
+        return 1;
+    }
+    return fetch();
+}
+
+int32_t cenv_step(cenv_key_value* actions, int32_t actions_size) {
+    if (!g_engine) return 1;
+    std::fill(g_actions.begin(), g_actions.end(), 0);
+    for (int i = 0; i < actions_size; i++) {
+        std::string key(actions[i].key);
+        if (key == "action") {
+            if (actions[i].value_type != CENV_VALUE_TYPE_INT || actions[i].value_buffer_size != g_num_envs) {
+                fprintf(stderr, "[procgen2_b200] cenv_step: \"action\" must be INT[%d]\n", g_num_envs);
+                return 1;
+            }
+            memcpy(g_actions.data(), actions[i].value_buffer.i, sizeof(int32_t) * g_num_envs);
+        }
+    }
+    if (pg2_step(g_engine, g_actions.data())) {
+        fprintf(stderr, "[procgen2_b200] cenv_step failed: %s\n", pg2_last_error());
+        return 1;
+    }
+    if (fetch()) return 1;
+    step_data.reward.f = g_reward[0];
+    step_data.terminated = g_term[0] != 0;
+    step_data.truncated = g_trunc[0] != 0;
+    return 0;
+}
+
+// Human-mode frame. The reference re-renders the scene at window resolution
+// (coinrun.cpp:393-411); that cold path is a "next" row: until then the
+// frame is env 0's observation, nearest-neighbour enlarged to width x height.
+int32_t cenv_render() {
+    if (!g_engine) return 1;
+    for (int y = 0; y < g_window_h; y++)
+        for (int x = 0; x < g_window_w; x++) {
+            int sx = x * 64 / g_window_w, sy = y * 64 / g_window_h;
+            memcpy(&g_frame[3 * ((size_t)x + (size_t)g_window_w * y)], &g_obs[3 * (sx + 64 * sy)], 3);
+        }
+    return 0;
+}
+
+void cenv_close() {
+    if (g_engine) { pg2_destroy(g_engine); g_engine = nullptr; }
+    g_obs.clear(); g_frame.clear();
+}
+
+}  // extern "C"

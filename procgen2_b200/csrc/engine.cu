@@ -19,6 +19,7 @@
 
 #include "../../include/pg2_engine.h"
 #include "assets.h"
+#include "sort_perm.h"
 #include "games/all_games.cuh"
 #include "pg2_kernels.cuh"
 
@@ -50,10 +51,10 @@ template <class G>
 __global__ void __launch_bounds__(128) k_step(typename G::State s, CommonState c, const int32_t* __restrict__ actions,
                                               float* __restrict__ reward, uint8_t* __restrict__ terminated,
                                               uint8_t* __restrict__ truncated, int* __restrict__ reset_list,
-                                              int* __restrict__ reset_count, int N, int max_episode_steps) {
+                                              int* __restrict__ reset_count, int N, int max_episode_steps, int auto_reset) {
     int env = blockIdx.x * blockDim.x + threadIdx.x;
     bool done = false;
-    if (env < N) done = step_body<G>(s, c, env, actions[env], reward, terminated, truncated, max_episode_steps);
+    if (env < N) done = step_body<G>(s, c, env, actions[env], reward, terminated, truncated, max_episode_steps) && auto_reset;
     // reset-list compaction: one atomic per warp
     unsigned m = __ballot_sync(0xffffffffu, done);
     if (m) {
@@ -101,7 +102,7 @@ struct EngineBase {
     virtual bool find_field(const char* name, void** ptr, int* esz, int* pe) = 0;
     virtual size_t state_bytes_per_env() = 0;
 
-    int device = 0, N = 0, max_episode_steps = 0;
+    int device = 0, N = 0, max_episode_steps = 0, auto_reset = 1;
     uint32_t base_seed = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
@@ -121,13 +122,14 @@ struct EngineBase {
     TexInfo* texinfo = nullptr;
     uint32_t* atlas = nullptr;
     int32_t* actions_pinned = nullptr;
+    uint8_t* sort_table = nullptr;
 
     int free_all() {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         cudaFree(state_mem); cudaFree(common_mem); cudaFree(obs); cudaFree(reward); cudaFree(terminated);
         cudaFree(truncated); cudaFree(actions); cudaFree(seeds_dev); cudaFree(reset_list); cudaFree(reset_count);
-        cudaFree(texinfo); cudaFree(atlas);
+        cudaFree(texinfo); cudaFree(atlas); cudaFree(sort_table);
         if (actions_pinned) cudaFreeHost(actions_pinned);
         if (stream) cudaStreamDestroy(stream);
         return 0;
@@ -139,7 +141,7 @@ struct Engine : EngineBase {
     typename G::State st;
 
     int init(const pg2_config* cfg) {
-        device = cfg->device; N = cfg->num_envs; max_episode_steps = cfg->max_episode_steps;
+        device = cfg->device; N = cfg->num_envs; max_episode_steps = cfg->max_episode_steps; auto_reset = cfg->auto_reset;
         base_seed = (uint32_t)cfg->seed + (uint32_t)cfg->first_env;
         PG2_CUDA(cudaSetDevice(device));
         cudaDeviceProp prop;
@@ -177,6 +179,14 @@ struct Engine : EngineBase {
         PG2_CUDA(cudaMalloc(&atlas, sizeof(uint32_t) * texels.size()));
         PG2_CUDA(cudaMemcpyAsync(texinfo, infos.data(), sizeof(TexInfo) * ntex, cudaMemcpyHostToDevice, stream));
         PG2_CUDA(cudaMemcpyAsync(atlas, texels.data(), sizeof(uint32_t) * texels.size(), cudaMemcpyHostToDevice, stream));
+        {
+            std::vector<uint8_t> table = build_sort_perm(SORT_MAXN);
+            PG2_CUDA(cudaMalloc(&sort_table, table.size()));
+            PG2_CUDA(cudaMemcpyAsync(sort_table, table.data(), table.size(), cudaMemcpyHostToDevice, stream));
+            PG2_CUDA(cudaStreamSynchronize(stream));
+            const uint8_t* p = sort_table;
+            PG2_CUDA(cudaMemcpyToSymbol(g_sort_perm, &p, sizeof(p)));
+        }
         PG2_CUDA(cudaStreamSynchronize(stream));
         PG2_CUDA(cudaFuncSetAttribute(k_reset<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, reset_smem()));
         // cenv_make: seed, then reset() once (level #1 is generated and never rendered, Q29)
@@ -222,7 +232,7 @@ struct Engine : EngineBase {
 
     int step_device(const int32_t* actions_dev) override {
         k_step<G><<<(N + 127) / 128, 128, 0, stream>>>(st, common, actions_dev, reward, terminated, truncated, reset_list,
-                                                     reset_count, N, max_episode_steps);
+                                                     reset_count, N, max_episode_steps, auto_reset);
         k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count, N);
         launches += 2;
         launch_render();

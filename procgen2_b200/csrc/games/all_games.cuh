@@ -1,6 +1,8 @@
 // Registry of the games compiled into the engine. PG2_FOR_EACH_GAME(X) expands X(name, Type).
 #pragma once
+#include "coinrun.cuh"
 #include "maze.cuh"
 
 #define PG2_FOR_EACH_GAME(X) \
-    X("maze", pg2::Maze)
+    X("maze", pg2::Maze)         \
+    X("coinrun", pg2::CoinRun)

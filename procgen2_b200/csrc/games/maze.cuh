@@ -228,21 +228,20 @@ struct Maze {
                                  __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h));
             f.npre = 1;
         }
-        if (is_role(1)) {
-            int n = 0;
-            if (c.sprites_valid[env]) {   // cheese (tilemap.cpp:95-98, common_systems.cpp:41-63)
+        const int ncheese = c.sprites_valid[env] ? 1 : 0;
+        emit_post_blits(f, ncheese + 1, [&](int k, Blit& b, BlitRot&) {
+            if (k < ncheese) {   // cheese (tilemap.cpp:95-98, common_systems.cpp:41-63)
                 float gx = __fmul_rn(__fadd_rn(s.goal_x[env], -0.48f), UNIT_TO_PIXELS);
                 float gy = __fmul_rn(__fadd_rn(s.goal_y[env], -0.5f), UNIT_TO_PIXELS);
                 float sc = __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 0.95f), UNIT_TO_PIXELS), (float)tex[T_CHEESE].w);
-                f.post[n++] = make_blit(tex, T_CHEESE, gx, gy, cam, sc);
+                b = make_blit(tex, T_CHEESE, gx, gy, cam, sc);
+            } else {             // agent (common_systems.cpp:138-151)
+                float ax = __fmul_rn(__fadd_rn(s.agent_x[env], -0.5f), UNIT_TO_PIXELS);
+                float ay = __fmul_rn(__fadd_rn(s.agent_y[env], -0.5f), UNIT_TO_PIXELS);
+                float sc = __fmul_rn(__fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_MOUSE].w), 1.0f);
+                b = make_blit(tex, T_MOUSE, ax, ay, cam, sc, 1.0f, s.face_forward[env] != 0);
             }
-            // agent (common_systems.cpp:138-151)
-            float ax = __fmul_rn(__fadd_rn(s.agent_x[env], -0.5f), UNIT_TO_PIXELS);
-            float ay = __fmul_rn(__fadd_rn(s.agent_y[env], -0.5f), UNIT_TO_PIXELS);
-            float sc = __fmul_rn(__fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_MOUSE].w), 1.0f);
-            f.post[n++] = make_blit(tex, T_MOUSE, ax, ay, cam, sc, 1.0f, s.face_forward[env] != 0);
-            f.npost = n;
-        }
+        });
         // tile layer (tilemap.cpp:111-131)
         const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_WALL].w);
         for (int t = tid; t < ncol + nrow; t += blockDim.x) {

@@ -39,6 +39,7 @@ inline float __uint2float_rn(uint32_t u) { return (float)u; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int __ffs(uint32_t m) { return __builtin_ffs((int)m); }
 inline int __popc(uint32_t m) { return __builtin_popcount(m); }
+inline uint32_t __ballot_sync(uint32_t, int pred) { return pred ? 1u : 0u; }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 using std::max;
 using std::min;

@@ -20,9 +20,21 @@ namespace pg2 {
 
 constexpr int MAX_WIN = 32;        // tile window extent per axis (maze: 27)
 constexpr int MAX_PRE = 2;
-constexpr int MAX_POST = 128;      // bossfight: 96 bullets + explosions + ships
+constexpr int MAX_POST = 192;      // visible post blits (coinrun: 10 particles per visible mob)
 constexpr int RENDER_THREADS = 256;
 constexpr uint16_t NO_TILE = 0xffff;
+
+// std::sort permutation table. System_Sprite_Render::update sorts (z, entity) pairs
+// by z with std::sort (common_systems.cpp:36-38); every sprite of a game has the same z, so the
+// comparator is always false and the resulting permutation depends on n only. It is computed on
+// the host with the real std::sort (sort_perm.h) and uploaded: sorted[k] = input[perm[n][k]].
+constexpr int SORT_MAXN = 128;
+#ifdef PG2_HOSTSIM
+static const uint8_t* g_sort_perm = nullptr;
+#else
+__device__ const uint8_t* g_sort_perm;
+#endif
+PG2_DEV int sort_perm(int n, int k) { return (n <= 16 || n > SORT_MAXN) ? k : g_sort_perm[n * SORT_MAXN + k]; }
 
 struct BlitRot { double s, c; };   // sin/cos of the blit angle (deterministic, see sincos_deg)
 
@@ -140,6 +152,31 @@ PG2_DEV Blit make_blit_rect(const TexInfo* tex, int tex_id, float dx, float dy, 
     rot->s = 0.0; rot->c = 1.0;
     if (b.rotated) sincos_deg(angle_deg, &rot->s, &rot->c);
     return b;
+}
+
+// Ordered, compacting append of post blits by the first warp of the CTA: candidate k (in the
+// reference's submission order) is evaluated by lane k % 32; only visible blits are stored,
+// order preserved through a ballot prefix. make(k, blit, rot) fills the blit.
+template <class MakeFn>
+PG2_DEV void emit_post_blits(Frame& f, int ncand, MakeFn make) {
+    if ((int)threadIdx.x >= WARP_LANES) return;
+    const int lane = threadIdx.x;
+    int n = f.npost;
+    for (int base = 0; base < ncand; base += WARP_LANES) {
+        int k = base + lane;
+        Blit b; BlitRot rot;
+        b.ax.visible = 0; b.rotated = 0; rot.s = 0.0; rot.c = 1.0;
+        if (k < ncand) make(k, b, rot);
+        bool vis = k < ncand && b.ax.visible;
+        uint32_t m = __ballot_sync(0xffffffffu, vis);
+        if (vis) {
+            int idx = n + __popc(m & ((1u << lane) - 1u));
+            if (idx < MAX_POST) { f.post[idx] = b; f.post_rot[idx] = rot; }
+        }
+        n += __popc(m);
+    }
+    if (lane == 0) f.npost = n < MAX_POST ? n : MAX_POST;
+    __syncwarp();
 }
 
 // Tile window of System_Tilemap::render (tilemap.cpp:294-302): inclusive tile index range.

@@ -1,0 +1,68 @@
+// System_Tilemap::get_collision (games/coinrun/tilemap.cpp:323-396; the other games' copies,
+// e.g. games/caveflyer/tilemap.cpp:305-366, are this function without the `down_only` branch):
+// two passes over the tiles under the rectangle — resolve in y where the overlap is wider than
+// tall, then in x otherwise — with the rectangle mutated in place between tiles.
+#pragma once
+#include "pg2_common.cuh"
+
+namespace pg2 {
+
+enum CollisionType { COLL_NONE = 0, COLL_FULL = 1, COLL_DOWN_ONLY = 2 };
+
+struct CollisionResult { float x, y; bool collided; };
+
+// TileAt(x, y) -> tile id with y already in render space (the callee flips: get(x, H-1-y)).
+template <class TileAt, class TypeOf>
+PG2_DEV CollisionResult tile_collision(Rect rectangle, TileAt tile_at, TypeOf type_of, bool fallthrough = false, float step_y = 0.0f) {
+    bool collided = false;
+    const int lower_x = f2i(floorf(rectangle.x));
+    const int lower_y = f2i(floorf(rectangle.y));
+    const int upper_x = f2i(ceilf(__fadd_rn(rectangle.x, rectangle.w)));
+    const int upper_y = f2i(ceilf(__fadd_rn(rectangle.y, rectangle.h)));
+    const float center_x = __fadd_rn(rectangle.x, __fmul_rn(rectangle.w, 0.5f));
+    const float center_y = __fadd_rn(rectangle.y, __fmul_rn(rectangle.h, 0.5f));
+    Rect tile; tile.w = 1.0f; tile.h = 1.0f;
+
+    for (int y = lower_y; y <= upper_y; y++)
+        for (int x = lower_x; x <= upper_x; x++) {
+            int type = type_of(tile_at(x, y));
+            if (type == COLL_NONE) continue;
+            tile.x = (float)x; tile.y = (float)y;
+            Rect col = get_collision_overlap(rectangle, tile);
+            if (col.w != 0.0f || col.h != 0.0f) {
+                float ccy = __fadd_rn(col.y, __fmul_rn(col.h, 0.5f));
+                if (col.w > col.h) {
+                    if (type == COLL_DOWN_ONLY) {
+                        bool inside = __fsub_rn(__fadd_rn(rectangle.y, rectangle.h), step_y) > tile.y;
+                        if (step_y > 0.01f && !fallthrough && !inside) {
+                            rectangle.y = ccy > center_y ? __fsub_rn(tile.y, rectangle.h) : __fadd_rn(tile.y, tile.h);
+                            collided = true;
+                        }
+                    } else {
+                        rectangle.y = ccy > center_y ? __fsub_rn(tile.y, rectangle.h) : __fadd_rn(tile.y, tile.h);
+                        collided = true;
+                    }
+                }
+            }
+        }
+    for (int y = lower_y; y <= upper_y; y++)
+        for (int x = lower_x; x <= upper_x; x++) {
+            int type = type_of(tile_at(x, y));
+            if (type == COLL_NONE) continue;
+            tile.x = (float)x; tile.y = (float)y;
+            Rect col = get_collision_overlap(rectangle, tile);
+            if (col.w != 0.0f || col.h != 0.0f) {
+                float ccx = __fadd_rn(col.x, __fmul_rn(col.w, 0.5f));
+                if (col.w <= col.h) {
+                    if (type != COLL_DOWN_ONLY) {
+                        rectangle.x = ccx > center_x ? __fsub_rn(tile.x, rectangle.w) : __fadd_rn(tile.x, tile.w);
+                        collided = true;
+                    }
+                }
+            }
+        }
+    CollisionResult r; r.x = rectangle.x; r.y = rectangle.y; r.collided = collided;
+    return r;
+}
+
+}  // namespace pg2

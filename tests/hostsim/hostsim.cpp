@@ -18,6 +18,7 @@
 #include "../../procgen2_b200/csrc/assets.h"
 #include "../../procgen2_b200/csrc/games/all_games.cuh"
 #include "../../procgen2_b200/csrc/pg2_kernels.cuh"
+#include "../../procgen2_b200/csrc/sort_perm.h"
 
 using namespace pg2;
 
@@ -80,6 +81,7 @@ struct Sim : SimBase {
 };
 
 static std::string g_err;
+static std::vector<uint8_t> g_sort_table;
 
 extern "C" {
 
@@ -87,6 +89,7 @@ const char* hs_last_error() { return g_err.c_str(); }
 
 void* hs_create(const char* game, int n, int seed, int max_ep, const char* assets) {
     std::string g = game;
+    if (g_sort_table.empty()) { g_sort_table = build_sort_perm(SORT_MAXN); g_sort_perm = g_sort_table.data(); }
     SimBase* out = nullptr;
     bool ok = false;
 #define PG2_TRY_GAME(NAME, TYPE) \
