@@ -76,6 +76,12 @@ PG2_API int32_t pg2_num_envs(pg2_engine* e);
 PG2_API int64_t pg2_kernel_launches(pg2_engine* e); /* kernels launched so far (bench.py gpu_launches) */
 PG2_API int64_t pg2_state_bytes_per_env(pg2_engine* e);
 
+/* Per-kernel device timing (CUDA events on the engine's stream around each launch of
+ * pg2_step*). enable != 0 starts/clears accumulation; pg2_profile_read synchronises and returns
+ * accumulated milliseconds {step logic, level generation, render} and the number of steps. */
+PG2_API int32_t pg2_profile(pg2_engine* e, int32_t enable);
+PG2_API int32_t pg2_profile_read(pg2_engine* e, float ms_out[3], int64_t* steps);
+
 /* Test / checkpoint access to the structure-of-arrays state: copies field `name` of the game
  * (or common) state to host memory. Returns bytes written, or <0 if the field is unknown or
  * `capacity` is too small. per_env receives the element count per environment. */

@@ -27,3 +27,8 @@ int pg2o_floats(float* out, int cap) {
     return n;
 }
 }
+
+/* The reference prints "REWARD<n>" to std::cout on every climber step (climber.cpp:357, SURVEY
+ * Q22) — not observable through the ABI; silence the stream so test logs stay readable. */
+#include <iostream>
+namespace { struct SilenceCout { SilenceCout() { std::cout.setstate(std::ios_base::failbit); } } g_silence_cout; }

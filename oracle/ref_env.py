@@ -85,6 +85,7 @@ class RefEnv:
         self.reset_data = ResetData.in_dll(self.lib, "reset_data")
         self._a = ctypes.c_int32(0)
         self._kv = KeyValue(b"action", 0, 1, _Buffer(i=ctypes.pointer(self._a)))
+        self._kv_ref = ctypes.byref(self._kv)
         os.unlink(self.path)  # mapping stays valid
 
     def _obs(self, kv):
@@ -104,6 +105,15 @@ class RefEnv:
         assert self.lib.cenv_step(ctypes.byref(self._kv), 1) == 0
         sd = self.step_data
         return self._obs(sd.observations[0]), float(sd.reward.f), bool(sd.terminated)
+
+    def raw_step(self, action):
+        """cenv_step without copying the observation out (timing loops). Returns terminated."""
+        self._a.value = int(action)
+        self.lib.cenv_step(self._kv_ref, 1)
+        return bool(self.step_data.terminated)
+
+    def raw_reset(self):
+        self.lib.cenv_reset(None, 0)
 
     # ---- probe accessors (oracle/probe/probe_<game>.cpp), present only when compiled in ----
     def probe(self, name, restype=ctypes.c_int, argtypes=()):

@@ -123,6 +123,33 @@ struct EngineBase {
     uint32_t* atlas = nullptr;
     int32_t* actions_pinned = nullptr;
     uint8_t* sort_table = nullptr;
+    // optional per-kernel timing
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;   // 4 per step
+    int64_t prof_steps = 0;
+    double prof_ms[3] = { 0, 0, 0 };
+
+    int prof_mark() {
+        cudaEvent_t ev;
+        if (cudaEventCreate(&ev) != cudaSuccess) return 1;
+        cudaEventRecord(ev, stream);
+        prof_events.push_back(ev);
+        return 0;
+    }
+    int prof_collect() {
+        cudaStreamSynchronize(stream);
+        for (size_t i = 0; i + 3 < prof_events.size(); i += 4) {
+            for (int k = 0; k < 3; k++) {
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, prof_events[i + k], prof_events[i + k + 1]);
+                prof_ms[k] += ms;
+            }
+            prof_steps++;
+        }
+        for (auto ev : prof_events) cudaEventDestroy(ev);
+        prof_events.clear();
+        return 0;
+    }
 
     int free_all() {
         cudaSetDevice(device);
@@ -231,6 +258,20 @@ struct Engine : EngineBase {
     }
 
     int step_device(const int32_t* actions_dev) override {
+        if (profiling) {
+            if (prof_events.size() >= 4096) prof_collect();
+            prof_mark();
+            k_step<G><<<(N + 127) / 128, 128, 0, stream>>>(st, common, actions_dev, reward, terminated, truncated, reset_list,
+                                                         reset_count, N, max_episode_steps, auto_reset);
+            prof_mark();
+            k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count, N);
+            prof_mark();
+            launches += 2;
+            launch_render();
+            prof_mark();
+            PG2_CUDA(cudaGetLastError());
+            return 0;
+        }
         k_step<G><<<(N + 127) / 128, 128, 0, stream>>>(st, common, actions_dev, reward, terminated, truncated, reset_list,
                                                      reset_count, N, max_episode_steps, auto_reset);
         k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count, N);
@@ -328,6 +369,24 @@ void* pg2_stream(pg2_engine* e) { return (void*)e->impl->stream; }
 int32_t pg2_num_envs(pg2_engine* e) { return e->impl->N; }
 int64_t pg2_kernel_launches(pg2_engine* e) { return e->impl->launches; }
 int64_t pg2_state_bytes_per_env(pg2_engine* e) { return (int64_t)e->impl->state_bytes_per_env(); }
+
+int32_t pg2_profile(pg2_engine* e, int32_t enable) {
+    EngineBase* b = e->impl.get();
+    cudaSetDevice(b->device);
+    b->prof_collect();
+    b->profiling = enable != 0;
+    b->prof_steps = 0;
+    b->prof_ms[0] = b->prof_ms[1] = b->prof_ms[2] = 0.0;
+    return 0;
+}
+int32_t pg2_profile_read(pg2_engine* e, float ms_out[3], int64_t* steps) {
+    EngineBase* b = e->impl.get();
+    cudaSetDevice(b->device);
+    b->prof_collect();
+    for (int k = 0; k < 3; k++) ms_out[k] = (float)b->prof_ms[k];
+    if (steps) *steps = b->prof_steps;
+    return 0;
+}
 
 int64_t pg2_read_field(pg2_engine* e, const char* name, void* out, int64_t capacity, int32_t* elem_size, int32_t* per_env) {
     EngineBase* b = e->impl.get();

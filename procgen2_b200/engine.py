@@ -59,6 +59,8 @@ def load_library():
     L.pg2_read_field.restype = ctypes.c_int64
     L.pg2_write_field.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64]
     L.pg2_write_field.restype = ctypes.c_int64
+    L.pg2_profile.argtypes = [vp, ctypes.c_int32]
+    L.pg2_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int64)]
     L.pg2_last_error.restype = ctypes.c_char_p
     _lib = L
     return L
@@ -143,6 +145,17 @@ class BatchedEnv:
         """actions: int32 CUDA tensor (num_envs,) on this engine's device."""
         assert actions.is_cuda and actions.dtype.is_floating_point is False and actions.numel() == self.num_envs
         self.step_device_ptr(actions.data_ptr())
+
+    def profile(self, enable=True):
+        """Start (and clear) / stop per-kernel CUDA-event timing of step()."""
+        _check(self._L.pg2_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> ({"step": ms, "reset": ms, "render": ms} accumulated, steps)"""
+        ms = (ctypes.c_float * 3)()
+        steps = ctypes.c_int64()
+        _check(self._L.pg2_profile_read(self._h, ms, ctypes.byref(steps)))
+        return {"step": ms[0], "reset": ms[1], "render": ms[2]}, steps.value
 
     @property
     def stream_ptr(self):

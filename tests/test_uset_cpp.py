@@ -1,0 +1,14 @@
+"""libstdc++ emulation pins: pg2::USet iteration order == std::unordered_set<int> (real one),
+checked by a small C++ program compiled on the fly."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_uset_matches_libstdcxx(tmp_path):
+    exe = str(tmp_path / "test_uset")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_uset.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("OK")
