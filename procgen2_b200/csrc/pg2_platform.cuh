@@ -36,6 +36,9 @@ inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline float __uint2float_rn(uint32_t u) { return (float)u; }
+inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int __ffs(uint32_t m) { return __builtin_ffs((int)m); }
 inline int __popc(uint32_t m) { return __builtin_popcount(m); }
