@@ -1,10 +1,12 @@
 // Registry of the games compiled into the engine. PG2_FOR_EACH_GAME(X) expands X(name, Type).
 #pragma once
 #include "bossfight.cuh"
+#include "climber.cuh"
 #include "coinrun.cuh"
 #include "maze.cuh"
 
 #define PG2_FOR_EACH_GAME(X) \
     X("maze", pg2::Maze)         \
     X("coinrun", pg2::CoinRun)   \
-    X("bossfight", pg2::BossFight)
+    X("bossfight", pg2::BossFight) \
+    X("climber", pg2::Climber)
