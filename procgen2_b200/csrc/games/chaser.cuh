@@ -1,0 +1,403 @@
+// Chaser — device restatement of /root/reference/games/chaser/:
+//   step logic  cenv_step chaser.cpp:282-320; System_Agent::update common_systems.cpp:305-444;
+//               System_Mob_AI::update :117-295 (eat :297); System_Point::update :66-106;
+//               System_Sprite_Render::update :8-40
+//   level gen   System_Tilemap::regenerate tilemap.cpp:80-243 (spawn helpers :30-78),
+//               Maze_Generator::generate_maze maze_generator.cpp:47-130, reset() chaser.cpp:420-447
+//   frame       render_game chaser.cpp:390-418; tilemap.cpp:245-267; common_systems.cpp:42-64, 446-462
+// easy_mode (compile-time default, tilemap.h:40): 11 x 11 world, 3 enemies, 4 orbs.
+// Entity ids per episode: 0-3 orbs, 4-6 eggs, 7-69 points, 70 agent.
+// abs() on floats is the float overload.
+#pragma once
+#include "../pg2_common.cuh"
+#include "../pg2_mazegen.cuh"
+#include "../pg2_render.cuh"
+#include "../pg2_rng.cuh"
+#include "../pg2_state.cuh"
+#include "../pg2_uset.cuh"
+#include "../pg2_warp.cuh"
+
+namespace pg2 {
+
+#define PG2_CHASER_FIELDS(F)                                                                    \
+    F(uint8_t, tiles, 128)      /* env-major [y + x*11]: 0 empty, 1 wall */                       \
+    F(uint8_t, free_cells, 64)  /* env-major: System_Tilemap::free_cells after regenerate (the point cells) */ \
+    F(int32_t, num_free, 1)                                                                       \
+    F(int32_t, num_ents, 1)     /* sprite entities: orbs, eggs, points */                         \
+    F(uint8_t, ent_kind, 72)    /* slot-major: 1 orb, 2 egg/mob, 3 point, 0 destroyed */          \
+    F(uint8_t, ent_cell, 72)    /* spawn cell index (y + x*11, map space) of orbs and points */   \
+    F(uint8_t, sprite_order, 72) /* iteration order of System_Sprite_Render::entities at reset */ \
+    F(uint8_t, mob_order, 4)    /* iteration order of System_Mob_AI::entities (mob slots 0..2) */ \
+    F(int32_t, nb_sprite, 1) F(int32_t, nb_mob, 1)   /* persisted bucket counts (Q25) */           \
+    F(float, mob_x, 3) F(float, mob_y, 3) F(float, mob_vx, 3) F(float, mob_vy, 3)                  \
+    F(float, mob_hatch, 3) F(uint8_t, mob_tex, 3)                                                  \
+    F(float, anim_timer, 1) F(int32_t, anim_index, 1) F(float, eat_timer, 1)                       \
+    F(float, ax, 1) F(float, ay, 1) F(float, avx, 1) F(float, avy, 1)                              \
+    F(float, next_vx, 1) F(float, next_vy, 1) F(float, input_timer, 1)                             \
+    F(int32_t, bg_index, 1) F(float, bg_offset, 1)
+
+PG2_DEFINE_STATE(ChaserState, PG2_CHASER_FIELDS)
+
+struct Chaser {
+    using State = ChaserState;
+    static constexpr int W = 11, H = 11, MAX_ENTS = 72, NMOB = 3;
+    static constexpr int SUB_STEPS = 4;
+    static constexpr int TILE_CLASSES = 1;
+    static constexpr int TILE_STRIDE = 128, FREE_STRIDE = 64;
+    enum Kind { K_NONE = 0, K_ORB, K_MOB, K_POINT };
+    enum Tex { T_WALL = 0, T_CRYSTAL, T_EGG, T_POINT, T_FLY0, T_FLY1, T_FLY2, T_WALK, T_AGENT, T_BG0, NUM_BG = 9, NUM_TEX = 18 };
+
+    static const char* const* texture_names(int* count) {
+        static const char* const names[NUM_TEX] = {
+            "assets/misc_assets/tileStone_slope.png", "assets/misc_assets/yellowCrystal.png",
+            "assets/misc_assets/enemySpikey_1b.png", "assets/custom/chaser_point.png",
+            "assets/misc_assets/enemyFlying_1.png", "assets/misc_assets/enemyFlying_2.png",
+            "assets/misc_assets/enemyFlying_3.png", "assets/misc_assets/enemyWalking_1b.png",
+            "assets/misc_assets/enemyFloating_1b.png",
+            "assets/topdown_backgrounds/floortiles.png",
+            "assets/topdown_backgrounds/backgrounddetailed1.png", "assets/topdown_backgrounds/backgrounddetailed2.png",
+            "assets/topdown_backgrounds/backgrounddetailed3.png", "assets/topdown_backgrounds/backgrounddetailed4.png",
+            "assets/topdown_backgrounds/backgrounddetailed5.png", "assets/topdown_backgrounds/backgrounddetailed6.png",
+            "assets/topdown_backgrounds/backgrounddetailed7.png", "assets/topdown_backgrounds/backgrounddetailed8.png",
+        };
+        *count = NUM_TEX;
+        return names;
+    }
+
+    // System_Tilemap::get (tilemap.h:78-83): out of bounds is `out_of_bounds` (-1), never `empty`.
+    static PG2_DEV int get(const uint8_t* tiles, int x, int y) {
+        if (x < 0 || y < 0 || x >= W || y >= H) return -1;
+        return tiles[y + x * H];
+    }
+    static PG2_DEV int sign(float x) { return x == 0.0f ? 0 : (x > 0.0f) * 2 - 1; }   // helpers.h:31-36
+    static PG2_DEV float cell_center(float v) { return __fadd_rn((float)f2i(v), 0.5f); }
+
+    // ---------------------------------------------------------------------------------------
+    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward) {
+        const int N = s.N;
+        const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
+        const float dt = 1.0f / SUB_STEPS;
+        Mt rng; rng.mt = c.mt + (size_t)env * MT_N; rng.idx = c.mti[env];
+        const int nents = s.num_ents[env];
+
+        float ax = s.ax[env], ay = s.ay[env], avx = s.avx[env], avy = s.avy[env];
+        float next_vx = s.next_vx[env], next_vy = s.next_vy[env], input_timer = s.input_timer[env];
+        float anim_timer = s.anim_timer[env], eat_timer = s.eat_timer[env];
+        int anim_index = s.anim_index[env];
+
+        const float speed = 0.2f;
+        const float input_reset_time = __fmul_rn(__fdiv_rn(1.0f, speed), 0.5f);
+        const float tol = __fmul_rn(speed, dt);
+        float movement_x = (float)((action == 7) - (action == 1));
+        float movement_y = (float)((action == 3) - (action == 5));
+        if (movement_x != 0.0f && movement_y != 0.0f) movement_y = 0.0f;
+
+        bool dead = false;
+        int point_delta = 0, points_available = 0;
+        for (int ss = 0; ss < SUB_STEPS; ss++) {
+            // ================= System_Agent::update =================
+            {
+                if (movement_x != 0.0f || movement_y != 0.0f) { next_vx = movement_x; next_vy = movement_y; input_timer = 0.0f; }
+                if (next_vx > 0.0f) {
+                    if (fabsf(__fsub_rn(ay, cell_center(ay))) <= tol && get(tiles, f2i(ax) + 1, H - 1 - f2i(ay)) == 0) {
+                        ay = cell_center(ay); avx = next_vx; avy = next_vy;
+                    }
+                } else if (next_vx < 0.0f) {
+                    if (fabsf(__fsub_rn(ay, cell_center(ay))) <= tol && get(tiles, f2i(ax) - 1, H - 1 - f2i(ay)) == 0) {
+                        ay = cell_center(ay); avx = next_vx; avy = next_vy;
+                    }
+                }
+                if (next_vy > 0.0f) {
+                    if (fabsf(__fsub_rn(ax, cell_center(ax))) <= tol && get(tiles, f2i(ax), H - 1 - (f2i(ay) + 1)) == 0) {
+                        ax = cell_center(ax); avx = next_vx; avy = next_vy;
+                    }
+                } else if (next_vy < 0.0f) {
+                    if (fabsf(__fsub_rn(ax, cell_center(ax))) <= tol && get(tiles, f2i(ax), H - 1 - (f2i(ay) - 1)) == 0) {
+                        ax = cell_center(ax); avx = next_vx; avy = next_vy;
+                    }
+                }
+                if (avx < 0.0f) {
+                    if (fabsf(__fsub_rn(ax, cell_center(ax))) <= tol && get(tiles, f2i(ax) - 1, H - 1 - f2i(ay)) != 0) { ax = cell_center(ax); avx = 0.0f; }
+                } else if (avx > 0.0f) {
+                    if (fabsf(__fsub_rn(ax, cell_center(ax))) <= tol && get(tiles, f2i(ax) + 1, H - 1 - f2i(ay)) != 0) { ax = cell_center(ax); avx = 0.0f; }
+                }
+                if (avy < 0.0f) {
+                    if (fabsf(__fsub_rn(ay, cell_center(ay))) <= tol && get(tiles, f2i(ax), H - 1 - (f2i(ay) - 1)) != 0) { ay = cell_center(ay); avy = 0.0f; }
+                } else if (avy > 0.0f) {
+                    if (fabsf(__fsub_rn(ay, cell_center(ay))) <= tol && get(tiles, f2i(ax), H - 1 - (f2i(ay) + 1)) != 0) { ay = cell_center(ay); avy = 0.0f; }
+                }
+                ax = __fadd_rn(ax, __fmul_rn(__fmul_rn(avx, speed), dt));
+                ay = __fadd_rn(ay, __fmul_rn(__fmul_rn(avy, speed), dt));
+                if (input_timer >= input_reset_time) { next_vx = 0.0f; next_vy = 0.0f; }
+                else input_timer = __fadd_rn(input_timer, dt);
+            }
+            const Rect agent_rect{ __fadd_rn(-0.5f, ax), __fadd_rn(-0.5f, ay), 1.0f, 1.0f };
+
+            // ================= System_Mob_AI::update =================
+            dead = false;
+            for (int k = 0; k < NMOB; k++) {
+                const int m = s.mob_order[k * N + env];
+                float hatch = s.mob_hatch[m * N + env];
+                if (hatch >= 50.0f) {
+                    float x = s.mob_x[m * N + env], y = s.mob_y[m * N + env], vx = s.mob_vx[m * N + env], vy = s.mob_vy[m * N + env];
+                    int tex;
+                    float mspeed;
+                    if (eat_timer == 0.0f) { tex = anim_index < 3 ? T_FLY0 + anim_index : T_FLY0 + (5 - anim_index); mspeed = 0.25f; }
+                    else { tex = T_WALK; mspeed = 0.125f; }
+                    bool at_junction = fmaxf(fabsf(__fsub_rn(x, cell_center(x))), fabsf(__fsub_rn(y, cell_center(y)))) < __fmul_rn(mspeed, dt);
+                    if ((vx == 0.0f && vy == 0.0f) || at_junction) {
+                        bool poss[4];
+                        int num = 0;
+                        const int ix = f2i(x), iy = f2i(y);
+                        poss[0] = get(tiles, ix - 1, H - 1 - iy) == 0 && -1 != -sign(vx);
+                        poss[1] = get(tiles, ix + 1, H - 1 - iy) == 0 && 1 != -sign(vx);
+                        poss[2] = get(tiles, ix, H - 1 - (iy - 1)) == 0 && -1 != -sign(vy);
+                        poss[3] = get(tiles, ix, H - 1 - (iy + 1)) == 0 && 1 != -sign(vy);
+                        for (int i = 0; i < 4; i++) num += poss[i];
+                        const float dirx[4] = { -1.0f, 1.0f, 0.0f, 0.0f }, diry[4] = { 0.0f, 0.0f, -1.0f, 1.0f };
+                        bool be_aggressive = rng.canonical() < 0.5f;
+                        int sel = 0;
+                        if (be_aggressive) {
+                            float min_dist = 999999.0f;
+                            for (int i = 0; i < 4; i++)
+                                if (poss[i]) {
+                                    float md = __fadd_rn(fabsf(__fsub_rn(__fadd_rn(x, dirx[i]), ax)), fabsf(__fsub_rn(__fadd_rn(y, diry[i]), ay)));
+                                    if (eat_timer > 0.0f) md = -md;
+                                    if (md < min_dist) { min_dist = md; sel = i; }
+                                }
+                        } else if (num > 0) {
+                            int cusp = rng.uniform_int(0, num - 1);
+                            int sum = 0;
+                            for (int i = 0; i < 4; i++) { sum += poss[i]; if (sum > cusp) { sel = i; break; } }
+                        }
+                        vx = __fmul_rn(dirx[sel], mspeed);
+                        vy = __fmul_rn(diry[sel], mspeed);
+                        if (dirx[sel] == 0.0f) x = cell_center(x);
+                        if (diry[sel] == 0.0f) y = cell_center(y);
+                    }
+                    x = __fadd_rn(x, __fmul_rn(vx, dt));
+                    y = __fadd_rn(y, __fmul_rn(vy, dt));
+                    Rect rect{ __fadd_rn(-0.5f, x), __fadd_rn(-0.5f, y), 1.0f, 1.0f };
+                    if (check_collision(agent_rect, rect)) {
+                        if (eat_timer == 0.0f) dead = true;
+                        else {   // respawn as an egg; y is NOT flipped here
+                            hatch = 0.0f;
+                            int cell = s.free_cells[(size_t)env * FREE_STRIDE + rng.uniform_int(0, s.num_free[env] - 1)];
+                            x = __fadd_rn((float)(cell / H), 0.5f);
+                            y = __fadd_rn((float)(cell % H), 0.5f);
+                            tex = T_EGG;
+                        }
+                    }
+                    s.mob_x[m * N + env] = x; s.mob_y[m * N + env] = y; s.mob_vx[m * N + env] = vx; s.mob_vy[m * N + env] = vy;
+                    s.mob_tex[m * N + env] = (uint8_t)tex;
+                } else {
+                    hatch = __fadd_rn(hatch, dt);
+                }
+                s.mob_hatch[m * N + env] = hatch;
+            }
+            if (anim_timer < 1.0f) anim_timer = __fadd_rn(anim_timer, dt);
+            else { anim_timer = __fsub_rn(anim_timer, 1.0f); anim_index = (anim_index + 1) % 6; }
+            if (eat_timer > 0.0f) eat_timer = fmaxf(0.0f, __fsub_rn(eat_timer, dt));
+
+            // ================= System_Point::update =================
+            point_delta = 0; points_available = 0;
+            for (int e = 0; e < nents; e++) {
+                int kind = s.ent_kind[e * N + env];
+                if (kind != K_ORB && kind != K_POINT) continue;
+                int cell = s.ent_cell[e * N + env];
+                float px = __fadd_rn((float)(cell / H), 0.5f), py = __fadd_rn((float)(H - 1 - cell % H), 0.5f);
+                Rect rect = kind == K_ORB ? Rect{ __fadd_rn(-0.5f, px), __fadd_rn(-0.5f, py), 1.0f, 1.0f }
+                                          : Rect{ __fadd_rn(-0.3f, px), __fadd_rn(-0.3f, py), 0.6f, 0.6f };
+                if (check_collision(agent_rect, rect)) {
+                    if (kind == K_ORB) eat_timer = 75.0f;
+                    point_delta++;
+                    s.ent_kind[e * N + env] = K_NONE;
+                } else points_available++;
+            }
+            if (dead || points_available == 0) break;
+        }
+
+        s.ax[env] = ax; s.ay[env] = ay; s.avx[env] = avx; s.avy[env] = avy;
+        s.next_vx[env] = next_vx; s.next_vy[env] = next_vy; s.input_timer[env] = input_timer;
+        s.anim_timer[env] = anim_timer; s.eat_timer[env] = eat_timer; s.anim_index[env] = anim_index;
+        c.mti[env] = rng.idx;
+        c.sprites_valid[env] = 1;
+        *reward = __fadd_rn(__fmul_rn((float)point_delta, 0.04f), __fmul_rn((float)(points_available == 0), 10.0f));
+        return dead || points_available == 0;
+    }
+
+    // ---------------------------------------------------------------------------------------
+    static PG2_DEV_NOINLINE void regenerate(const State& s, const CommonState& c, int env, WarpCtx& w) {
+        const int N = s.N, lane = w.lane;
+        uint8_t* tiles = w.alloc<uint8_t>(TILE_STRIDE);   // 0 empty, 1 wall, 2 marker
+        uint8_t* kinds = w.alloc<uint8_t>(MAX_ENTS);
+        uint8_t* cells = w.alloc<uint8_t>(MAX_ENTS);
+        uint8_t* quad = w.alloc<uint8_t>(4 * 64);
+        uint8_t* fc = w.alloc<uint8_t>(128);
+        uint8_t* order = w.alloc<uint8_t>(MAX_ENTS);
+        USet<128, 128>* us = w.alloc<USet<128, 128>>(1);
+        int nents = 0;
+
+        MazeGrid mg = kruskal_maze(w, W, H);
+        w.rng.uniform_int(0, 3);   // extra_quad: extra_orb_sign == 0 in easy mode, the draw is still consumed
+
+        int nq[4] = { 0, 0, 0, 0 };
+        for (int x = 0; x < W; x++)
+            for (int y = 0; y < H; y++) {
+                int obj = mg.get(x + 1, y + 1);
+                tiles[y + x * H] = obj == 1 ? 1 : 0;
+                if (obj == 0) {
+                    int qi = (x >= W / 2) * 2 + (y >= H / 2);
+                    quad[qi * 64 + nq[qi]] = (uint8_t)(y + x * H);
+                    nq[qi]++;
+                }
+            }
+        __syncwarp();
+        for (int i = 0; i < 4; i++) {
+            // one orb per quadrant: selected_indices = { pos }
+            int pos = w.rng.uniform_int(0, nq[i] - 1);
+            int cell = quad[i * 64 + pos];
+            kinds[nents] = K_ORB; cells[nents] = (uint8_t)cell; nents++;
+            tiles[cell] = 2;
+            __syncwarp();
+        }
+        int nfree = 0;
+        for (int i = 0; i < W * H; i++) if (tiles[i] == 0) fc[nfree++] = (uint8_t)i;
+        __syncwarp();
+        // agent + 3 eggs: distinct positions into free_cells, walked in unordered_set order (Q4)
+        us->init(1);
+        for (int j = 0; j < NMOB + 1; j++) {
+            int pos = w.rng.uniform_int(0, nfree - 1);
+            while (us->count > 0 && us->contains(pos)) pos = (pos + 1) % nfree;
+            us->insert(pos);
+        }
+        int nsel = us->order(order);
+        (void)nsel;
+        const int start = fc[order[0]];
+        const int agent_spawn_x = start / H, agent_spawn_y = start % H;
+        int egg_cell[NMOB];
+        tiles[start] = 2;
+        for (int i = 0; i < NMOB; i++) {
+            egg_cell[i] = fc[order[1 + i]];
+            kinds[nents] = K_MOB; cells[nents] = (uint8_t)egg_cell[i]; nents++;
+            tiles[egg_cell[i]] = 2;
+        }
+        __syncwarp();
+        nfree = 0;
+        for (int i = 0; i < W * H; i++) if (tiles[i] == 0) fc[nfree++] = (uint8_t)i;
+        for (int i = 0; i < nfree; i++) { kinds[nents] = K_POINT; cells[nents] = fc[i]; nents++; }
+        __syncwarp();
+
+        // ---- reset() tail (chaser.cpp:425-446)
+        int bg_index = w.rng.uniform_int(0, NUM_BG - 1);
+        float bg_offset = w.rng.uniform_real(0.0f, 1.0f);
+
+        // ---- ECS set orders: sprite_render = every entity above (ids ascending), mob_ai = eggs (ids 4..6)
+        us->init(s.nb_sprite[env]);
+        for (int e = 0; e < nents; e++) us->insert(e);
+        int n_sprite = us->order(order);
+        int nb_sprite = us->nb;
+        __syncwarp();
+        for (int k = lane; k < n_sprite; k += WARP_LANES) s.sprite_order[k * N + env] = order[k];
+        __syncwarp();
+        us->init(s.nb_mob[env]);
+        for (int i = 0; i < NMOB; i++) us->insert(4 + i);
+        us->order(order);
+        int nb_mob = us->nb;
+        __syncwarp();
+        for (int k = lane; k < NMOB; k += WARP_LANES) s.mob_order[k * N + env] = (uint8_t)(order[k] - 4);
+
+        uint8_t* gt = s.tiles + (size_t)env * TILE_STRIDE;
+        for (int i = lane; i < W * H; i += WARP_LANES) gt[i] = tiles[i] == 1 ? 1 : 0;   // markers cleared
+        uint8_t* gf = s.free_cells + (size_t)env * FREE_STRIDE;
+        for (int i = lane; i < nfree && i < FREE_STRIDE; i += WARP_LANES) gf[i] = fc[i];
+        for (int e = lane; e < nents; e += WARP_LANES) { s.ent_kind[e * N + env] = kinds[e]; s.ent_cell[e * N + env] = cells[e]; }
+        for (int i = lane; i < NMOB; i += WARP_LANES) {
+            s.mob_x[i * N + env] = __fadd_rn((float)(egg_cell[i] / H), 0.5f);
+            s.mob_y[i * N + env] = __fadd_rn((float)(H - 1 - egg_cell[i] % H), 0.5f);
+            s.mob_vx[i * N + env] = 0.0f; s.mob_vy[i * N + env] = 0.0f;
+            s.mob_hatch[i * N + env] = 0.0f; s.mob_tex[i * N + env] = T_EGG;
+        }
+        if (lane == 0) {
+            s.num_free[env] = nfree;
+            s.num_ents[env] = nents;
+            s.nb_sprite[env] = nb_sprite; s.nb_mob[env] = nb_mob;
+            s.anim_timer[env] = 0.0f; s.anim_index[env] = 0; s.eat_timer[env] = 0.0f;
+            s.ax[env] = __fadd_rn((float)agent_spawn_x, 0.5f);
+            s.ay[env] = __fadd_rn((float)(H - 1 - agent_spawn_y), 0.5f);
+            s.avx[env] = 0.0f; s.avy[env] = 0.0f; s.next_vx[env] = 0.0f; s.next_vy[env] = 0.0f; s.input_timer[env] = 0.0f;
+            s.bg_index[env] = bg_index; s.bg_offset[env] = bg_offset;
+            c.cam_x[env] = __fmul_rn(__fmul_rn((float)W, 0.5f), UNIT_TO_PIXELS);
+            c.cam_y[env] = __fmul_rn(__fmul_rn((float)H, 0.5f), UNIT_TO_PIXELS);
+            c.sprites_valid[env] = 0;
+            if (nfree > FREE_STRIDE || nents > MAX_ENTS) c.fault[env] |= 1;
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------
+    static PG2_DEV int tile_class(uint32_t) { return 0; }
+
+    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, Frame& f, const TexInfo* tex) {
+        const int tid = threadIdx.x, N = s.N;
+        // game_zoom = width * pixels_to_unit / map_width (chaser.cpp:401)
+        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(64.0f, PIXELS_TO_UNIT), (float)W) };
+        int lx, ly, ux, uy;
+        tile_window(cam, &lx, &ly, &ux, &uy);
+        const int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);
+        const int nents = s.num_ents[env];
+        const bool sprites = c.sprites_valid[env] != 0;
+        if (is_role(0)) {
+            f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = 1;
+            int bg = T_BG0 + s.bg_index[env];
+            TexInfo bt = tex[bg];
+            float extra = __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f);
+            f.pre[0] = make_blit(tex, bg, __fmul_rn(-s.bg_offset[env], extra), 0.0f, cam,
+                                 __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h));
+            f.npre = 1;
+        }
+        int nlive = 0;
+        if (sprites)
+            for (int k = 0; k < nents; k++) nlive += s.ent_kind[s.sprite_order[k * N + env] * N + env] != K_NONE;
+        emit_post_blits(f, nlive + 1, [&](int k, Blit& b, BlitRot&) {
+            if (k < nlive) {
+                int want = sort_perm(nlive, k), e = 0;
+                for (int j = 0, seen = 0; j < nents; j++) {
+                    e = s.sprite_order[j * N + env];
+                    if (s.ent_kind[e * N + env] != K_NONE && seen++ == want) break;
+                }
+                int kind = s.ent_kind[e * N + env];
+                int t; float x, y;
+                if (kind == K_MOB) {
+                    int m = e - 4;
+                    t = s.mob_tex[m * N + env]; x = s.mob_x[m * N + env]; y = s.mob_y[m * N + env];
+                } else {
+                    int cell = s.ent_cell[e * N + env];
+                    t = kind == K_ORB ? T_CRYSTAL : T_POINT;
+                    x = __fadd_rn((float)(cell / H), 0.5f); y = __fadd_rn((float)(H - 1 - cell % H), 0.5f);
+                }
+                float px = __fmul_rn(__fadd_rn(x, -0.5f), UNIT_TO_PIXELS);
+                float py = __fmul_rn(__fadd_rn(y, -0.5f), UNIT_TO_PIXELS);
+                float sc = __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 1.0f), UNIT_TO_PIXELS), (float)tex[t].w);
+                b = make_blit(tex, t, px, py, cam, sc);
+            } else {
+                float px = __fmul_rn(__fadd_rn(s.ax[env], -0.5f), UNIT_TO_PIXELS);
+                float py = __fmul_rn(__fadd_rn(s.ay[env], -0.5f), UNIT_TO_PIXELS);
+                b = make_blit(tex, T_AGENT, px, py, cam, __fmul_rn(__fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_AGENT].w), 1.0f));
+            }
+        });
+        const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_WALL].w);
+        for (int t = tid; t < ncol + nrow; t += blockDim.x) {
+            if (t < ncol) f.col[0][t] = make_axis(__fmul_rn((float)(lx + t), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tex[T_WALL].w, tscale, false, false);
+            else f.row[0][t - ncol] = make_axis(__fmul_rn((float)(ly + t - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, tex[T_WALL].h, tscale, false, true);
+        }
+        const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
+        for (int t = tid; t < ncol * nrow; t += blockDim.x) {
+            int cx = t % ncol, ry = t / ncol;
+            int id = get(tiles, lx + cx, H - 1 - (ly + ry));
+            f.tile_tex[ry * MAX_WIN + cx] = id == 1 ? (uint16_t)T_WALL : NO_TILE;
+        }
+        __syncthreads();
+    }
+};
+
+}  // namespace pg2

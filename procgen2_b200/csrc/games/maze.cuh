@@ -7,6 +7,7 @@
 // hard_mode only (compile-time default of the reference): 25x25 world, all visible.
 #pragma once
 #include "../pg2_common.cuh"
+#include "../pg2_mazegen.cuh"
 #include "../pg2_render.cuh"
 #include "../pg2_state.cuh"
 #include "../pg2_warp.cuh"
@@ -99,72 +100,10 @@ struct Maze {
         const int margin = (WORLD - maze_dim) / 2;
 
         // ---- Maze_Generator::generate_maze(maze_dim, maze_dim) (maze_generator.cpp:55-139)
-        const int mw = maze_dim, mh = maze_dim;
-        const int aw = mw + 2, ah = mh + 2;                            // padded array
-        uint8_t* grid = w.alloc<uint8_t>(27 * 27);
-        int16_t* set_idx = w.alloc<int16_t>(27 * 27);
-        uint8_t* set_rank = w.alloc<uint8_t>(27 * 27);
-        int16_t* free_cells = w.alloc<int16_t>(27 * 27);
-        uint8_t* is_free = w.alloc<uint8_t>(25 * 25);
-        uint32_t* walls = w.alloc<uint32_t>(320);                       // x1 | y1<<8 | x2<<16 | y2<<24
-        w.fill<uint8_t>(grid, aw * ah, 1);
-        w.fill<uint8_t>(is_free, 25 * 25, 0);
-        for (int i = lane; i < mw * mh; i += WARP_LANES) { set_idx[i] = (int16_t)i; set_rank[i] = 0; }
-        __syncwarp();
-        grid[1 + ah * 1] = 0;                                          // corner
-        int num_free = 0;
-        int nwalls = 0;
-        for (int i = 1; i < mw; i += 2)
-            for (int j = 0; j < mh; j += 2)
-                if (i > 0 && i < mw - 1) { walls[nwalls] = (uint32_t)(i - 1) | (uint32_t)j << 8 | (uint32_t)(i + 1) << 16 | (uint32_t)j << 24; nwalls++; }
-        for (int i = 0; i < mw; i += 2)
-            for (int j = 1; j < mh; j += 2)
-                if (j > 0 && j < mh - 1) { walls[nwalls] = (uint32_t)i | (uint32_t)(j - 1) << 8 | (uint32_t)i << 16 | (uint32_t)(j + 1) << 24; nwalls++; }
-        __syncwarp();
-
-        auto find = [&](int cell) {                                    // path halving
-            int cur = cell;
-            while (set_idx[cur] != cur) { int gp = set_idx[set_idx[cur]]; set_idx[cur] = (int16_t)gp; cur = gp; }
-            return cur;
-        };
-        auto set_free_cell = [&](int x, int y) {
-            grid[(y + 1) + ah * (x + 1)] = 0;
-            int cell = y + mh * x;
-            if (!is_free[cell]) { free_cells[num_free] = (int16_t)cell; is_free[cell] = 1; num_free++; }
-        };
-
-        while (nwalls > 0) {
-            int n = w.rng.uniform_int(0, nwalls - 1);
-            uint32_t wl = walls[n];
-            int x1 = wl & 255, y1 = (wl >> 8) & 255, x2 = (wl >> 16) & 255, y2 = wl >> 24;
-            int s0 = find(y1 + mh * x1);
-            int s1 = find(y2 + mh * x2);
-            int x0 = (x1 + x2) / 2, y0 = (y1 + y2) / 2;
-            int center = y0 + mh * x0;
-            bool can_remove = (grid[(y0 + 1) + ah * (x0 + 1)] == 1) && (s0 != s1);
-            __syncwarp();
-            if (can_remove) {
-                set_free_cell(x1, y1);
-                set_free_cell(x0, y0);
-                set_free_cell(x2, y2);
-                if (set_rank[s0] > set_rank[s1]) {
-                    set_idx[s1] = (int16_t)s0; set_idx[center] = (int16_t)s0;
-                } else {
-                    set_idx[s0] = (int16_t)s1; set_idx[center] = (int16_t)s1;
-                    if (set_rank[s0] == set_rank[s1]) set_rank[s1]++;
-                }
-            }
-            __syncwarp();
-            // walls.erase(walls.begin() + n): order-preserving shift, 32 elements at a time
-            for (int base = n; base < nwalls - 1; base += WARP_LANES) {
-                int k = base + lane;
-                uint32_t v = (k < nwalls - 1) ? walls[k + 1] : 0u;
-                __syncwarp();
-                if (k < nwalls - 1) walls[k] = v;
-                __syncwarp();
-            }
-            nwalls--;
-        }
+        MazeGrid mg = kruskal_maze(w, maze_dim, maze_dim);
+        const int mh = mg.mh, ah = mg.ah, num_free = mg.num_free;
+        uint8_t* grid = mg.grid;
+        const int16_t* free_cells = mg.free_cells;
 
         // ---- place_object(GOAL) (maze_generator.cpp:183-195): cell index 10 (START_CELL) and
         // consumed cells are rejected and redrawn

@@ -10,6 +10,7 @@ MIXES = {
     "uniform": lambda rs, T, n: rs.randint(0, 15, size=(T, n)),
     "fire": lambda rs, T, n: np.where(rs.rand(T, n) < 0.6, 9, rs.randint(0, 15, size=(T, n))),
     "right": lambda rs, T, n: np.where(rs.rand(T, n) < 0.5, rs.randint(0, 15, size=(T, n)), rs.choice([6, 7, 8, 8, 5], size=(T, n))),
+    "chase": lambda rs, T, n: np.where(rs.rand(T, n) < 0.3, rs.randint(0, 15, size=(T, n)), np.repeat(rs.choice([1, 3, 5, 7], size=(T // 8 + 1, n)), 8, axis=0)[:T]),
     "up": lambda rs, T, n: np.where(rs.rand(T, n) < 0.5, rs.randint(0, 15, size=(T, n)), rs.choice([5, 8, 2, 5, 7], size=(T, n))),
 }
 
