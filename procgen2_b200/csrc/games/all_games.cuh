@@ -1,6 +1,7 @@
 // Registry of the games compiled into the engine. PG2_FOR_EACH_GAME(X) expands X(name, Type).
 #pragma once
 #include "bossfight.cuh"
+#include "caveflyer.cuh"
 #include "chaser.cuh"
 #include "climber.cuh"
 #include "coinrun.cuh"
@@ -11,4 +12,5 @@
     X("coinrun", pg2::CoinRun)   \
     X("bossfight", pg2::BossFight) \
     X("climber", pg2::Climber)     \
-    X("chaser", pg2::Chaser)
+    X("chaser", pg2::Chaser)       \
+    X("caveflyer", pg2::CaveFlyer)

@@ -30,8 +30,9 @@ struct USet {
         }
         const short primes[] = { 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97, 103, 109, 113, 127, 137, 139,
                                  149, 157, 167, 179, 193, 199, 211, 227, 241, 257, 277, 293, 313, 337, 359, 383, 409, 439, 467, 503, 541,
-                                 577, 619, 661, 709, 761, 823, 887, 953, 1031, 1109 };
-        int p = 1109;
+                                 577, 619, 661, 709, 761, 823, 887, 953, 1031, 1109, 1193, 1289, 1381, 1493, 1613, 1741, 1879, 2029, 2179, 2357,
+                                 2549, 2753, 2971, 3209, 3469, 3739, 4027, 4349, 4703, 5087 };
+        int p = 5087;
         for (int i = 0; i < (int)(sizeof(primes) / sizeof(primes[0])); i++)
             if (primes[i] >= n) { p = primes[i]; break; }
         *next_resize = p;

@@ -11,7 +11,7 @@
 namespace pg2 {
 
 constexpr int RESET_WARPS_PER_CTA = 2;
-constexpr int RESET_ARENA_BYTES = 24 * 1024;   // per-warp scratch
+constexpr int RESET_ARENA_BYTES = 40 * 1024;   // per-warp scratch
 
 struct WarpCtx {
     WarpMt rng;

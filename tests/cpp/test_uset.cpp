@@ -2,6 +2,7 @@
 // insert / erase / clear / copy-free workloads, and the std::sort permutation table.
 #define PG2_HOSTSIM 1
 #include <stdio.h>
+#include <algorithm>
 #include <random>
 #include <unordered_set>
 #include <vector>
@@ -45,6 +46,26 @@ int main() {
             }
             ref.clear();
             us.init(us.nb);   // clear(): keeps the bucket count
+        }
+    }
+    // large generator-local sets (caveflyer / jumper best_room: up to 1600 keys, fresh set, insert only)
+    for (int trial = 0; trial < 40; trial++) {
+        std::unordered_set<int> ref;
+        static USet<1600, 2400> big;
+        big.init(1);
+        int n = 200 + rng() % 1400;
+        std::vector<int> keys(1600);
+        for (int i = 0; i < 1600; i++) keys[i] = i;
+        std::shuffle(keys.begin(), keys.end(), rng);
+        for (int i = 0; i < n; i++) { ref.insert(keys[i]); big.insert(keys[i]); }
+        std::vector<int> a(ref.begin(), ref.end());
+        std::vector<int> b(1600);
+        int m = big.order(b.data());
+        b.resize(m);
+        checks++;
+        if (a != b || (int)ref.bucket_count() != big.nb) {
+            printf("MISMATCH big trial %d: sizes %zu %d buckets %zu %d\n", trial, a.size(), m, ref.bucket_count(), big.nb);
+            return 1;
         }
     }
     printf("OK %d checks\n", checks);
