@@ -5,6 +5,7 @@
 #include "chaser.cuh"
 #include "climber.cuh"
 #include "coinrun.cuh"
+#include "jumper.cuh"
 #include "maze.cuh"
 
 #define PG2_FOR_EACH_GAME(X) \
@@ -13,4 +14,5 @@
     X("bossfight", pg2::BossFight) \
     X("climber", pg2::Climber)     \
     X("chaser", pg2::Chaser)       \
-    X("caveflyer", pg2::CaveFlyer)
+    X("caveflyer", pg2::CaveFlyer) \
+    X("jumper", pg2::Jumper)

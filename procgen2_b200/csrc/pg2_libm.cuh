@@ -97,4 +97,93 @@ PG2_DEV_NOINLINE void glibc_sincosf(float y, float* sinp, float* cosp) {
     }
 }
 
+
+// ---- atan2f --------------------------------------------------------------------------------------
+// std::atan2(float, float) -> glibc 2.39 atan2f = wrapper around __ieee754_atan2f
+// (sysdeps/ieee754/flt-32/e_atan2f.c) which calls __atanf (sysdeps/ieee754/flt-32/s_atanf.c): the
+// classic fdlibm single-precision code, compiled for baseline x86-64 (scalar SSE, no FMA; atan2f is a
+// plain function in libm.so.6, not an ifunc). Used by the jumper compass HUD (jumper.cpp:479).
+PG2_DEV float glibc_atanf(float x) {
+    const float atanhi[4] = { 4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f };
+    const float atanlo[4] = { 5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f };
+    const float aT[11] = { 3.3333334327e-01f, -2.0000000298e-01f, 1.4285714924e-01f, -1.1111110449e-01f, 9.0908870101e-02f,
+                           -7.6918758452e-02f, 6.6610731184e-02f, -5.8335702866e-02f, 4.9768779427e-02f, -3.6531571299e-02f,
+                           1.6285819933e-02f };
+    int32_t hx = (int32_t)__float_as_uint(x);
+    int32_t ix = hx & 0x7fffffff;
+    int id;
+    if (ix >= 0x4c000000) {                      // |x| >= 2^25
+        if (ix > 0x7f800000) return __fadd_rn(x, x);
+        return hx > 0 ? __fadd_rn(atanhi[3], atanlo[3]) : __fsub_rn(-atanhi[3], atanlo[3]);
+    }
+    if (ix < 0x3ee00000) {                       // |x| < 0.4375
+        if (ix < 0x31000000) return x;           // |x| < 2^-29
+        id = -1;
+    } else {
+        x = fabsf(x);
+        if (ix < 0x3f980000) {
+            if (ix < 0x3f300000) { id = 0; x = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, x), 1.0f), __fadd_rn(2.0f, x)); }
+            else { id = 1; x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f)); }
+        } else {
+            if (ix < 0x401c0000) { id = 2; x = __fdiv_rn(__fsub_rn(x, 1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x))); }
+            else { id = 3; x = __fdiv_rn(-1.0f, x); }
+        }
+    }
+    float z = __fmul_rn(x, x);
+    float w = __fmul_rn(z, z);
+    float s1 = __fmul_rn(z, __fadd_rn(aT[0], __fmul_rn(w, __fadd_rn(aT[2], __fmul_rn(w, __fadd_rn(aT[4], __fmul_rn(w, __fadd_rn(aT[6],
+               __fmul_rn(w, __fadd_rn(aT[8], __fmul_rn(w, aT[10])))))))))));
+    float s2 = __fmul_rn(w, __fadd_rn(aT[1], __fmul_rn(w, __fadd_rn(aT[3], __fmul_rn(w, __fadd_rn(aT[5], __fmul_rn(w, __fadd_rn(aT[7],
+               __fmul_rn(w, aT[9])))))))));
+    if (id < 0) return __fsub_rn(x, __fmul_rn(x, __fadd_rn(s1, s2)));
+    z = __fsub_rn(atanhi[id], __fsub_rn(__fsub_rn(__fmul_rn(x, __fadd_rn(s1, s2)), atanlo[id]), x));
+    return hx < 0 ? -z : z;
+}
+
+PG2_DEV_NOINLINE float glibc_atan2f(float y, float x) {
+    const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+    int32_t hx = (int32_t)__float_as_uint(x), hy = (int32_t)__float_as_uint(y);
+    int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+    if (ix > 0x7f800000 || iy > 0x7f800000) return __fadd_rn(x, y);
+    if (hx == 0x3f800000) return glibc_atanf(y);
+    int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+    if (iy == 0) {
+        switch (m) {
+        case 0: case 1: return y;
+        case 2: return __fadd_rn(pi, tiny);
+        default: return __fsub_rn(-pi, tiny);
+        }
+    }
+    if (ix == 0) return hy < 0 ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+    if (ix == 0x7f800000) {
+        if (iy == 0x7f800000) {
+            switch (m) {
+            case 0: return __fadd_rn(pi_o_4, tiny);
+            case 1: return __fsub_rn(-pi_o_4, tiny);
+            case 2: return __fadd_rn(__fmul_rn(3.0f, pi_o_4), tiny);
+            default: return __fsub_rn(__fmul_rn(-3.0f, pi_o_4), tiny);
+            }
+        } else {
+            switch (m) {
+            case 0: return 0.0f;
+            case 1: return -0.0f;
+            case 2: return __fadd_rn(pi, tiny);
+            default: return __fsub_rn(-pi, tiny);
+            }
+        }
+    }
+    if (iy == 0x7f800000) return hy < 0 ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+    int k = (iy - ix) >> 23;
+    float z;
+    if (k > 60) z = __fadd_rn(pi_o_2, __fmul_rn(0.5f, pi_lo));
+    else if (hx < 0 && k < -60) z = 0.0f;
+    else z = glibc_atanf(fabsf(__fdiv_rn(y, x)));
+    switch (m) {
+    case 0: return z;
+    case 1: return __uint_as_float(__float_as_uint(z) ^ 0x80000000u);
+    case 2: return __fsub_rn(pi, __fsub_rn(z, pi_lo));
+    default: return __fsub_rn(__fsub_rn(z, pi_lo), pi);
+    }
+}
+
 }  // namespace pg2

@@ -8,7 +8,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # games whose device implementation exists (extended as games land)
-IMPLEMENTED = ["maze", "coinrun", "bossfight", "climber", "chaser", "caveflyer"]
+IMPLEMENTED = ["maze", "coinrun", "bossfight", "climber", "chaser", "caveflyer", "jumper"]
 
 
 def pytest_configure(config):
