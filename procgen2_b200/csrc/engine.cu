@@ -47,18 +47,27 @@ __global__ void k_seed(CommonState c, int N, uint32_t base_seed, const int32_t* 
     seed_body(c, env, seeds ? (uint32_t)seeds[env] : base_seed + (uint32_t)env, init_persistent != 0);
 }
 
+// `epw` = environments per warp (power of two, 1..32): lanes [0, epw) of every warp own one environment each.
+// Small batches use epw = 1 (no divergence between environments, 32x more warps to hide latency); large
+// batches pack more environments per warp. Finished envs are appended to the reset list (ballot + one atomic/warp).
 template <class G>
 __global__ void __launch_bounds__(128) k_step(typename G::State s, CommonState c, const int32_t* __restrict__ actions,
                                               float* __restrict__ reward, uint8_t* __restrict__ terminated,
                                               uint8_t* __restrict__ truncated, int* __restrict__ reset_list,
-                                              int* __restrict__ reset_count, int N, int max_episode_steps, int auto_reset) {
-    int env = blockIdx.x * blockDim.x + threadIdx.x;
+                                              int* __restrict__ reset_count, int N, int max_episode_steps, int auto_reset, int epw) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = gtid & 31;
     bool done = false;
-    if (env < N) done = step_body<G>(s, c, env, actions[env], reward, terminated, truncated, max_episode_steps) && auto_reset;
-    // reset-list compaction: one atomic per warp
+    int env;
+    if (epw == 1) {   // a whole warp per environment (warp-uniform branch)
+        env = gtid >> 5;
+        if (env < N) done = step_body<G>(s, c, env, actions[env], reward, terminated, truncated, max_episode_steps, StepCtx{ lane, 32 }) && auto_reset && lane == 0;
+    } else {
+        env = (gtid >> 5) * epw + lane;
+        if (lane < epw && env < N) done = step_body<G>(s, c, env, actions[env], reward, terminated, truncated, max_episode_steps, StepCtx{ 0, 1 }) && auto_reset;
+    }
     unsigned m = __ballot_sync(0xffffffffu, done);
     if (m) {
-        int lane = threadIdx.x & 31;
         int base = 0;
         if (lane == 0) base = atomicAdd(reset_count, __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
@@ -107,6 +116,7 @@ struct EngineBase {
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
     int num_sms = 148;
+    int step_epw = 1;          // environments per warp in k_step
     // device buffers
     void* state_mem = nullptr;
     void* common_mem = nullptr;
@@ -175,6 +185,10 @@ struct Engine : EngineBase {
         PG2_CUDA(cudaGetDeviceProperties(&prop, device));
         num_sms = prop.multiProcessorCount;
         PG2_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        // k_step mapping: aim for >= 8 warps per SM sub-partition before packing several envs into one warp
+        step_epw = 1;
+        while (step_epw < 32 && N / (step_epw * 2) >= num_sms * 4 * 8) step_epw *= 2;
+        if (const char* o = getenv("PG2_STEP_EPW")) { int v = atoi(o); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) step_epw = v; }
         PG2_CUDA(cudaMalloc(&state_mem, G::State::bytes(N)));
         PG2_CUDA(cudaMemsetAsync(state_mem, 0, G::State::bytes(N), stream));
         st = G::State::bind(state_mem, N);
@@ -225,6 +239,7 @@ struct Engine : EngineBase {
         return 0;
     }
 
+    int step_grid() const { int warps = (N + step_epw - 1) / step_epw; return (warps * 32 + 127) / 128; }
     static int reset_smem() { return RESET_WARPS_PER_CTA * (MT_N * 4 + RESET_ARENA_BYTES); }
     int reset_grid(int count) const {
         int ctas = (count + RESET_WARPS_PER_CTA - 1) / RESET_WARPS_PER_CTA;
@@ -261,8 +276,8 @@ struct Engine : EngineBase {
         if (profiling) {
             if (prof_events.size() >= 4096) prof_collect();
             prof_mark();
-            k_step<G><<<(N + 127) / 128, 128, 0, stream>>>(st, common, actions_dev, reward, terminated, truncated, reset_list,
-                                                         reset_count, N, max_episode_steps, auto_reset);
+            k_step<G><<<step_grid(), 128, 0, stream>>>(st, common, actions_dev, reward, terminated, truncated, reset_list,
+                                                         reset_count, N, max_episode_steps, auto_reset, step_epw);
             prof_mark();
             k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count, N);
             prof_mark();
@@ -272,8 +287,8 @@ struct Engine : EngineBase {
             PG2_CUDA(cudaGetLastError());
             return 0;
         }
-        k_step<G><<<(N + 127) / 128, 128, 0, stream>>>(st, common, actions_dev, reward, terminated, truncated, reset_list,
-                                                     reset_count, N, max_episode_steps, auto_reset);
+        k_step<G><<<step_grid(), 128, 0, stream>>>(st, common, actions_dev, reward, terminated, truncated, reset_list,
+                                                     reset_count, N, max_episode_steps, auto_reset, step_epw);
         k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count, N);
         launches += 2;
         launch_render();

@@ -46,6 +46,7 @@ PG2_DEFINE_STATE(BossFightState, PG2_BOSSFIGHT_FIELDS)
 struct BossFight {
     using State = BossFightState;
     static constexpr int SUB_STEPS = 4;
+    static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
     static constexpr int TILE_CLASSES = 1;
     static constexpr int MB = 64, NEX = 8, AB = 32, MAX_BAR = 4;
     enum Tex {
@@ -114,7 +115,7 @@ struct BossFight {
         }
     };
 
-    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward) {
+    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward, const StepCtx& ctx) {
         const int N = s.N;
         const float dt = 1.0f / SUB_STEPS;
         const double PI = 3.14159265358979323846;

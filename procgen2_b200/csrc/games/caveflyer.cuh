@@ -42,6 +42,7 @@ struct CaveFlyer {
     using State = CaveFlyerState;
     static constexpr int W = 40, H = 40, MAX_OBJ = 64, NB = 32, NPART = 10;
     static constexpr int SUB_STEPS = 4;
+    static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
     static constexpr int TILE_CLASSES = 1;
     enum Obj { O_NONE = 0, O_OBSTACLE, O_TARGET, O_ENEMY };
     enum Tex { T_WALL = 0, T_GOAL, T_TARGET, T_OBSTACLE, T_ENEMY, T_BULLET, T_SHIP, T_PARTICLE, T_EXPL0, T_BG0 = 13, NUM_BG = 13, NUM_TEX = 26 };
@@ -73,7 +74,7 @@ struct CaveFlyer {
     }
 
     // ---------------------------------------------------------------------------------------
-    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward) {
+    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward, const StepCtx& ctx) {
         const int N = s.N;
         const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
         const float dt = 1.0f / SUB_STEPS;

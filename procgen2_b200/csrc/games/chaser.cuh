@@ -42,6 +42,7 @@ struct Chaser {
     using State = ChaserState;
     static constexpr int W = 11, H = 11, MAX_ENTS = 72, NMOB = 3;
     static constexpr int SUB_STEPS = 4;
+    static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
     static constexpr int TILE_CLASSES = 1;
     static constexpr int TILE_STRIDE = 128, FREE_STRIDE = 64;
     enum Kind { K_NONE = 0, K_ORB, K_MOB, K_POINT };
@@ -73,7 +74,7 @@ struct Chaser {
     static PG2_DEV float cell_center(float v) { return __fadd_rn((float)f2i(v), 0.5f); }
 
     // ---------------------------------------------------------------------------------------
-    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward) {
+    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward, const StepCtx& ctx) {
         const int N = s.N;
         const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
         const float dt = 1.0f / SUB_STEPS;

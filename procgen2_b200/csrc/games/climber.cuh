@@ -40,6 +40,7 @@ struct Climber {
     using State = ClimberState;
     static constexpr int W = 20, H = 64, MAX_ENTS = 40;
     static constexpr int SUB_STEPS = 4;
+    static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
     static constexpr int TILE_CLASSES = 2;   // wall_mid textures are 64x64, one wall_top texture is 64x53
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID };
     enum Ent { E_NONE = 0, E_MOB, E_POINT };
@@ -78,7 +79,7 @@ struct Climber {
     }
 
     // ---------------------------------------------------------------------------------------
-    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward) {
+    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward, const StepCtx& ctx) {
         const int N = s.N;
         const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
         const float dt = 1.0f / SUB_STEPS;

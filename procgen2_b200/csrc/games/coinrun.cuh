@@ -55,6 +55,7 @@ struct CoinRun {
     using State = CoinRunState;
     static constexpr int W = 64, H = 64, MAX_ENTS = 40, NPART = 10;
     static constexpr int SUB_STEPS = 4;
+    static constexpr bool LANE_AWARE = true;    // step(): per-entity loops are strided over ctx's lanes
     static constexpr int TILE_CLASSES = 1;
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID, LAVA_TOP, LAVA_MID, CRATE };
     enum Ent { E_NONE = 0, E_SAW, E_MOB, E_COIN };
@@ -115,7 +116,7 @@ struct CoinRun {
     }
 
     // ---------------------------------------------------------------------------------------
-    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward) {
+    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward, const StepCtx& ctx) {
         const int N = s.N;
         const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
         const float dt = 1.0f / SUB_STEPS;
@@ -134,8 +135,8 @@ struct CoinRun {
 
         bool alive = true, achieved_goal = false;
         for (int ss = 0; ss < SUB_STEPS; ss++) {
-            // ---- System_Mob_AI::update
-            for (int e = 0; e < nents; e++) {
+            // ---- System_Mob_AI::update (one mob per lane: mobs only read the tile map and their own state)
+            for (int e = ctx.lane; e < nents; e += ctx.nlanes) {
                 if (s.ent_type[e * N + env] != E_MOB) continue;
                 float x = s.ent_x[e * N + env], y = s.ent_y[e * N + env], vx = s.ent_vx[e * N + env];
                 x = __fadd_rn(x, __fmul_rn(vx, dt));
@@ -151,6 +152,7 @@ struct CoinRun {
                 s.ent_vx[e * N + env] = vx;
                 s.ent_flip[e * N + env] = vx > 0.0f;
             }
+            ctx.sync();   // the agent reads every entity's position
 
             // ---- System_Agent::update
             alive = true; achieved_goal = false;
@@ -178,20 +180,23 @@ struct CoinRun {
                 if (on_ground) avy = 0.0f;
 
                 // hazards (saws: bounds {-0.5,-0.5,1,1}; mobs: {-0.5,-0.48,1,0.98}) and goals
-                for (int e = 0; e < nents; e++) {
+                bool hit = false, got = false;
+                for (int e = ctx.lane; e < nents; e += ctx.nlanes) {
                     int type = s.ent_type[e * N + env];
                     float ex = s.ent_x[e * N + env], ey = s.ent_y[e * N + env];
                     if (type == E_SAW) {
                         Rect hz{ __fadd_rn(ex, -0.5f), __fadd_rn(ey, -0.5f), 1.0f, 1.0f };
-                        if (check_collision(world, hz)) alive = false;
+                        if (check_collision(world, hz)) hit = true;
                     } else if (type == E_MOB) {
                         Rect hz{ __fadd_rn(ex, -0.5f), __fadd_rn(ey, -0.48f), 1.0f, 0.98f };
-                        if (check_collision(world, hz)) alive = false;
+                        if (check_collision(world, hz)) hit = true;
                     } else if (type == E_COIN) {
                         Rect gl{ __fadd_rn(ex, -0.5f), __fadd_rn(ey, -0.5f), 1.0f, 1.0f };
-                        if (check_collision(world, gl)) achieved_goal = true;
+                        if (check_collision(world, gl)) got = true;
                     }
                 }
+                if (ctx.any(hit)) alive = false;
+                if (ctx.any(got)) achieved_goal = true;
                 CollisionResult lava = tile_collision(world, tile_at, [](int id) { return (id == LAVA_MID || id == LAVA_TOP) ? COLL_FULL : COLL_NONE; });
                 if (lava.collided) alive = false;
 
@@ -203,8 +208,8 @@ struct CoinRun {
                 else if (movement_x < 0.0f) face_forward = false;
             }
 
-            // ---- System_Particles::update + System_Sprite_Render::update (animation)
-            for (int e = 0; e < nents; e++) {
+            // ---- System_Particles::update + System_Sprite_Render::update (animation), one entity per lane
+            for (int e = ctx.lane; e < nents; e += ctx.nlanes) {
                 int type = s.ent_type[e * N + env];
                 if (type == E_MOB) {
                     int dead_index = -1;
@@ -236,10 +241,12 @@ struct CoinRun {
             if (!alive || achieved_goal) break;
         }
 
-        s.ax[env] = ax; s.ay[env] = ay; s.avx[env] = avx; s.avy[env] = avy; s.agent_t[env] = agent_t;
-        s.on_ground[env] = on_ground; s.face_forward[env] = face_forward;
-        c.cam_x[env] = cam_x; c.cam_y[env] = cam_y;
-        c.sprites_valid[env] = 1;
+        if (ctx.leader()) {
+            s.ax[env] = ax; s.ay[env] = ay; s.avx[env] = avx; s.avy[env] = avy; s.agent_t[env] = agent_t;
+            s.on_ground[env] = on_ground; s.face_forward[env] = face_forward;
+            c.cam_x[env] = cam_x; c.cam_y[env] = cam_y;
+            c.sprites_valid[env] = 1;
+        }
         *reward = achieved_goal ? 10.0f : 0.0f;      // result.second * 10.0f
         return !alive || achieved_goal;
     }

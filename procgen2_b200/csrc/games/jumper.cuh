@@ -40,6 +40,7 @@ struct Jumper {
     using State = JumperState;
     static constexpr int W = 40, H = 40, MAX_SPIKES = 64, NPART = 10;
     static constexpr int SUB_STEPS = 4;
+    static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
     static constexpr int TILE_CLASSES = 2;
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID, SPIKE };
     enum Tex {
@@ -71,7 +72,7 @@ struct Jumper {
     }
 
     // ---------------------------------------------------------------------------------------
-    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward) {
+    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward, const StepCtx& ctx) {
         const int N = s.N;
         const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
         const float dt = 1.0f / SUB_STEPS;

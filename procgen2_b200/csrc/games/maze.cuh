@@ -31,6 +31,7 @@ struct Maze {
     using State = MazeState;
     static constexpr int WORLD = 25;          // world_dim (tilemap.cpp:36)
     static constexpr int TIMEOUT = 500;       // maze.cpp:49
+    static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
     static constexpr int TILE_CLASSES = 1;
     static constexpr int TILE_STRIDE = 640;
     enum Tex { T_WALL = 0, T_CHEESE = 1, T_MOUSE = 2, T_BG0 = 3, NUM_BG = 9, NUM_TEX = 12 };
@@ -62,7 +63,7 @@ struct Maze {
 
     // ---------------------------------------------------------------------------------------
     // cenv_step body for one environment (thread-per-env). Returns terminated.
-    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward) {
+    static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward, const StepCtx& ctx) {
         const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
         float px = s.agent_x[env], py = s.agent_y[env];
         int movement_x = action / 3 - 1;

@@ -15,6 +15,17 @@ constexpr float UNIT_TO_PIXELS = 16.0f;          // helpers.h:8
 constexpr float PIXELS_TO_UNIT = 1.0f / 16.0f;   // helpers.h:9
 constexpr int OBS_W = 64, OBS_H = 64, OBS_BYTES = 64 * 64 * 3;
 
+// How ONE environment's cenv_step is spread over threads: nlanes == 1 (one thread owns the environment:
+// thread-per-env mapping, host-sim) or nlanes == WARP_LANES (a whole warp owns it: per-entity loops are strided
+// over the lanes, everything else is computed redundantly by all lanes, which therefore stay converged).
+struct StepCtx {
+    int lane, nlanes;
+    PG2_DEV bool any(bool p) const { return nlanes == 1 ? p : warp_any(p); }
+    PG2_DEV int sum(int v) const { return nlanes == 1 ? v : warp_sum(v); }
+    PG2_DEV void sync() const { if (nlanes != 1) __syncwarp(); }
+    PG2_DEV bool leader() const { return lane == 0; }
+};
+
 struct Rect { float x, y, w, h; };
 struct Vec2 { float x, y; };
 

@@ -20,16 +20,27 @@ PG2_DEV_NOINLINE void seed_body(const CommonState& c, int env, uint32_t seed, bo
 // cenv_step for one env (without the render): returns "episode over" (terminated or truncated)
 template <class G>
 PG2_DEV bool step_body(const typename G::State& s, const CommonState& c, int env, int action, float* reward,
-                       uint8_t* terminated, uint8_t* truncated, int max_episode_steps) {
+                       uint8_t* terminated, uint8_t* truncated, int max_episode_steps, const StepCtx& ctx) {
     float r = 0.0f;
-    bool term = G::step(s, c, env, action, &r);
+    bool term = false;
+    if (G::LANE_AWARE || ctx.nlanes == 1) {
+        term = G::step(s, c, env, action, &r, ctx);
+    } else {   // the game's step is single-threaded: the warp's leader runs it, the result is broadcast
+        if (ctx.leader()) term = G::step(s, c, env, action, &r, StepCtx{ 0, 1 });
+        __syncwarp();
+        term = warp_bcast((int)term) != 0;
+        r = warp_bcast(r);
+    }
     bool trunc = false;
     int ep = c.ep_steps[env] + 1;
     if (max_episode_steps > 0 && ep >= max_episode_steps && !term) trunc = true;
-    c.ep_steps[env] = ep;
-    reward[env] = r;
-    terminated[env] = term ? 1 : 0;
-    truncated[env] = trunc ? 1 : 0;
+    ctx.sync();
+    if (ctx.leader()) {
+        c.ep_steps[env] = ep;
+        reward[env] = r;
+        terminated[env] = term ? 1 : 0;
+        truncated[env] = trunc ? 1 : 0;
+    }
     return term || trunc;
 }
 
@@ -57,8 +68,8 @@ PG2_DEV void render_body(const typename G::State& s, const CommonState& c, int e
     __syncthreads();
     G::build_frame(s, c, env, f, tex);
     __syncthreads();
-    frame_finalize(f);
-    frame_rasterise<G>(f, tex, atlas);
+    frame_finalize<G>(f, tex);
+    frame_rasterise<G>(f, atlas);
     frame_store(f, obs + (size_t)env * OBS_BYTES);
 }
 

@@ -12,6 +12,10 @@
 #define PG2_DEV_NOINLINE __device__
 namespace pg2 {
 constexpr int WARP_LANES = 32;
+__device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_bcast(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ float warp_bcast(float v) { return __shfl_sync(0xffffffffu, v, 0); }
 }
 #else
 #include <math.h>
@@ -42,7 +46,12 @@ inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f;
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int __ffs(uint32_t m) { return __builtin_ffs((int)m); }
 inline int __popc(uint32_t m) { return __builtin_popcount(m); }
+inline int __clz(uint32_t m) { return m ? __builtin_clz(m) : 32; }
 inline uint32_t __ballot_sync(uint32_t, int pred) { return pred ? 1u : 0u; }
+inline bool warp_any(bool p) { return p; }
+inline int warp_sum(int v) { return v; }
+inline int warp_bcast(int v) { return v; }
+inline float warp_bcast(float v) { return v; }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 using std::max;
 using std::min;

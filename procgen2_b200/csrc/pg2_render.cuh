@@ -23,6 +23,7 @@ constexpr int MAX_PRE = 2;
 constexpr int MAX_POST = 192;      // visible post blits (coinrun: 10 particles per visible mob)
 constexpr int RENDER_THREADS = 256;
 constexpr uint16_t NO_TILE = 0xffff;
+constexpr uint8_t TILE_NONE = 0xff;
 
 // std::sort permutation table. System_Sprite_Render::update sorts (z, entity) pairs
 // by z with std::sort (common_systems.cpp:36-38); every sprite of a game has the same z, so the
@@ -36,7 +37,17 @@ __device__ const uint8_t* g_sort_perm;
 #endif
 PG2_DEV int sort_perm(int n, int k) { return (n <= 16 || n > SORT_MAXN) ? k : g_sort_perm[n * SORT_MAXN + k]; }
 
-struct BlitRot { double s, c; };   // sin/cos of the blit angle (deterministic, see sincos_deg)
+struct BlitRot { double s, c; };
+
+// Per-pixel form of an axis-aligned blit (built once per frame by frame_finalize): coverage test = two unsigned
+// compares, sampling = one multiply-add + shift per axis (a horizontal flip is folded into hx / incx, which
+// wrap modulo 2^32 to the exact non-negative value), texel address = base + sy * tex_w + sx.
+struct alignas(16) FastBlit {
+    int16_t x0, y0; uint16_t w, h;
+    uint32_t hx, incx;
+    uint32_t hy, incy, base;
+    uint16_t tex_w; uint8_t flags, alpha_mod;   // flags: 1 blend, 2 rotated (use the generic path), 4 invisible
+};   // sin/cos of the blit angle (deterministic, see sincos_deg)
 
 struct Frame {
     // pre / post blit lists
@@ -52,8 +63,20 @@ struct Frame {
     uint16_t tile_tex[MAX_WIN * MAX_WIN];       // texture index per window cell or NO_TILE
     uint8_t col_lo[OBS_W], col_hi[OBS_W];       // per screen column: range of tile columns covering it
     uint8_t row_lo[OBS_H], row_hi[OBS_H];       // (lo > hi: none)
-    // post-blit binning: 8x8-pixel blocks x 128 blits
-    uint32_t bin[64][MAX_POST / 32];
+    // resolved tile layer (frame_finalize): atlas offset + meta per window cell, per-class texture stride, and for
+    // every screen column / row the (at most two) covering tile columns / rows with their source texel index
+    uint32_t tile_off[MAX_WIN * MAX_WIN];
+    uint8_t tile_meta[MAX_WIN * MAX_WIN];       // TILE_NONE, or class | blend << 1
+    int16_t cls_w[2];
+    int16_t col_sx[2][2][OBS_W];                // [class][candidate][X] -> source x, -1: not covered
+    int16_t row_sy[2][2][OBS_H];
+    FastBlit fpre[MAX_PRE];
+    FastBlit fpost[MAX_POST];
+    int wcount[RENDER_THREADS / 32];            // emit_post_blits: visible blits per warp
+    int wide;                                   // some column / row is covered by more than two tiles (never observed)
+    // post-blit binning: 8x4-pixel blocks (one warp's pixels) x MAX_POST blits
+    uint32_t bin[128][MAX_POST / 32];
+    uint8_t bin_any[128];                       // bin has at least one blit
     // staged output frame
     alignas(16) uint8_t rgb[OBS_BYTES];
 };
@@ -154,29 +177,36 @@ PG2_DEV Blit make_blit_rect(const TexInfo* tex, int tex_id, float dx, float dy, 
     return b;
 }
 
-// Ordered, compacting append of post blits by the first warp of the CTA: candidate k (in the
-// reference's submission order) is evaluated by lane k % 32; only visible blits are stored,
-// order preserved through a ballot prefix. make(k, blit, rot) fills the blit.
+// Ordered, compacting append of post blits by the whole CTA: candidate k (in the reference's
+// submission order) is evaluated by thread k % blockDim; only visible blits are stored, order
+// preserved through a warp ballot + a prefix over the warps' counts. make(k, blit, rot) fills the blit.
+// Must be called by every thread of the CTA.
 template <class MakeFn>
 PG2_DEV void emit_post_blits(Frame& f, int ncand, MakeFn make) {
-    if ((int)threadIdx.x >= WARP_LANES) return;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid % WARP_LANES, warp = tid / WARP_LANES;
+    const int nwarps = ((int)blockDim.x + WARP_LANES - 1) / WARP_LANES;
+    __syncthreads();
     int n = f.npost;
-    for (int base = 0; base < ncand; base += WARP_LANES) {
-        int k = base + lane;
+    for (int base = 0; base < ncand; base += blockDim.x) {
+        int k = base + tid;
         Blit b; BlitRot rot;
         b.ax.visible = 0; b.rotated = 0; rot.s = 0.0; rot.c = 1.0;
         if (k < ncand) make(k, b, rot);
         bool vis = k < ncand && b.ax.visible;
         uint32_t m = __ballot_sync(0xffffffffu, vis);
+        if (lane == 0) f.wcount[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w2 = 0; w2 < nwarps; w2++) { int cnt = f.wcount[w2]; if (w2 < warp) before += cnt; total += cnt; }
         if (vis) {
-            int idx = n + __popc(m & ((1u << lane) - 1u));
+            int idx = n + before + __popc(m & ((1u << lane) - 1u));
             if (idx < MAX_POST) { f.post[idx] = b; f.post_rot[idx] = rot; }
         }
-        n += __popc(m);
+        n += total;
+        __syncthreads();
     }
-    if (lane == 0) f.npost = n < MAX_POST ? n : MAX_POST;
-    __syncwarp();
+    if (tid == 0) f.npost = n < MAX_POST ? n : MAX_POST;
+    __syncthreads();
 }
 
 // Tile window of System_Tilemap::render (tilemap.cpp:294-302): inclusive tile index range.
@@ -229,13 +259,30 @@ PG2_DEV void blit_bounds(const Blit& b, int* x0, int* y0, int* x1, int* y1) {
     }
 }
 
+PG2_DEV FastBlit make_fast(const Blit& b) {
+    FastBlit fb;
+    fb.x0 = (int16_t)max(-32768, min(32767, b.ax.d0)); fb.y0 = (int16_t)max(-32768, min(32767, b.ay.d0));
+    fb.w = (uint16_t)min(65535, max(0, b.ax.dlen)); fb.h = (uint16_t)min(65535, max(0, b.ay.dlen));
+    fb.incx = b.flip_h ? 0u - b.ax.inc : b.ax.inc;
+    fb.hx = b.flip_h ? b.ax.inc / 2u + (uint32_t)(b.ax.dlen - 1) * b.ax.inc : b.ax.inc / 2u;
+    fb.hy = b.ay.inc / 2u; fb.incy = b.ay.inc;
+    fb.base = b.tex_offset + (uint32_t)b.ay.s0 * b.tex_w + (uint32_t)b.ax.s0;
+    fb.tex_w = b.tex_w;
+    fb.alpha_mod = b.alpha_mod;
+    bool clipped = b.ax.d0 < -32768 || b.ax.d0 > 32767 || b.ay.d0 < -32768 || b.ay.d0 > 32767 || b.ax.dlen > 65535 || b.ay.dlen > 65535;
+    fb.flags = (uint8_t)((b.blend ? 1 : 0) | ((b.rotated || clipped) ? 2 : 0) | (b.ax.visible ? 0 : 4));
+    return fb;
+}
+
 // After the game's frame builder filled pre/post blits, the tile window, col/row descriptors
-// and tile_tex (and __syncthreads()'d), derive the per-column / per-row candidate lists and
-// the post-blit bins.
-PG2_DEV_NOINLINE void frame_finalize(Frame& f) {
-    int tid = threadIdx.x;
-    for (int i = tid; i < 64 * (MAX_POST / 32); i += blockDim.x) (&f.bin[0][0])[i] = 0u;
-    // covering ranges: thread t < 64 -> screen column t, 64..127 -> screen row t-64
+// and tile_tex (and __syncthreads()'d): resolve the tile layer into lookup tables and bin the post blits.
+template <class G>
+PG2_DEV_NOINLINE void frame_finalize(Frame& f, const TexInfo* __restrict__ texinfo) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 128 * (MAX_POST / 32); i += blockDim.x) (&f.bin[0][0])[i] = 0u;
+    for (int i = tid; i < 128; i += blockDim.x) f.bin_any[i] = 0;
+    if (tid == 0) f.wide = 0;
+    // covering ranges: k < 64 -> screen column k, 64..127 -> screen row k-64
     for (int k = tid; k < 128; k += blockDim.x) {
         bool is_row = k >= 64;
         int p = k & 63;
@@ -251,60 +298,222 @@ PG2_DEV_NOINLINE void frame_finalize(Frame& f) {
         if (is_row) { f.row_lo[p] = (uint8_t)lo; f.row_hi[p] = (uint8_t)hi; }
         else        { f.col_lo[p] = (uint8_t)lo; f.col_hi[p] = (uint8_t)hi; }
     }
+    // window cells: texture index -> atlas offset / class / blend
+    for (int t = tid; t < f.ncol * f.nrow; t += blockDim.x) {
+        int cell = (t / f.ncol) * MAX_WIN + t % f.ncol;
+        uint32_t tex = f.tile_tex[cell];
+        if (tex == NO_TILE) { f.tile_meta[cell] = TILE_NONE; continue; }
+        TexInfo ti = texinfo[tex];
+        int cls = (G::TILE_CLASSES > 1) ? G::tile_class(tex) : 0;
+        f.tile_off[cell] = ti.offset;
+        f.tile_meta[cell] = (uint8_t)(cls | (ti.blend ? 2 : 0));
+        f.cls_w[cls] = (int16_t)ti.w;     // every texture of a class has the same shape
+    }
     __syncthreads();
+    // per screen column / row and class: source texel of the (at most two) covering tiles
+    for (int k = tid; k < 128 * 2 * 2; k += blockDim.x) {
+        int p = k & 63, is_row = (k >> 6) & 1, j = (k >> 7) & 1, cls = k >> 8;
+        int lo = is_row ? f.row_lo[p] : f.col_lo[p], hi = is_row ? f.row_hi[p] : f.col_hi[p];
+        int16_t v = -1;
+        if (cls < f.nclass && lo + j <= hi) {
+            const Axis& a = is_row ? f.row[cls][lo + j] : f.col[cls][lo + j];
+            if (a.visible && (unsigned)(p - a.d0) < (unsigned)a.dlen) v = (int16_t)axis_sample(a, p, false);
+        }
+        if (is_row) f.row_sy[cls][j][p] = v; else f.col_sx[cls][j][p] = v;
+        if (j == 0 && cls == 0 && lo <= hi && hi - lo > 1) f.wide = 1;
+    }
+    for (int k = tid; k < f.npre; k += blockDim.x) f.fpre[k] = make_fast(f.pre[k]);
     for (int k = tid; k < f.npost; k += blockDim.x) {
         const Blit& b = f.post[k];
+        f.fpost[k] = make_fast(b);
         if (!b.ax.visible) continue;
         int x0, y0, x1, y1;
         blit_bounds(b, &x0, &y0, &x1, &y1);
-        x0 = max(x0, 0) >> 3; y0 = max(y0, 0) >> 3; x1 = min(x1, 63) >> 3; y1 = min(y1, 63) >> 3;
+        if (x1 < 0 || y1 < 0 || x0 > 63 || y0 > 63) continue;
+        x0 = max(x0, 0) >> 3; y0 = max(y0, 0) >> 2; x1 = min(x1, 63) >> 3; y1 = min(y1, 63) >> 2;
         for (int by = y0; by <= y1; by++)
-            for (int bx = x0; bx <= x1; bx++) atomicOr(&f.bin[by * 8 + bx][k >> 5], 1u << (k & 31));
+            for (int bx = x0; bx <= x1; bx++) { atomicOr(&f.bin[by * 8 + bx][k >> 5], 1u << (k & 31)); f.bin_any[by * 8 + bx] = 1; }
     }
     __syncthreads();
 }
 
-// Shade all 4096 pixels into f.rgb. `texinfo` = the game's texture table, `tile_class[tex]`
-// is implied by TexInfo shape through the game's CLASS_OF callback (template parameter).
-template <class G>
-PG2_DEV_NOINLINE void frame_rasterise(Frame& f, const TexInfo* __restrict__ texinfo, const uint32_t* __restrict__ atlas) {
-    for (int p = threadIdx.x; p < OBS_W * OBS_H; p += blockDim.x) {
-        int X = p & 63, Y = p >> 6;
-        uint32_t r = 0, g = 0, b = 0;   // SDL_RenderClear(0,0,0,255)
-        for (int k = 0; k < f.npre; k++)
-            if (f.pre[k].ax.visible) shade_blit(f.pre[k], nullptr, atlas, X, Y, r, g, b);
-        // tile layer: y-major, x-minor painter's order
-        {
-            int rlo = f.row_lo[Y], rhi = f.row_hi[Y], clo = f.col_lo[X], chi = f.col_hi[X];
-            for (int ry = rlo; ry <= rhi; ry++)
-                for (int cx = clo; cx <= chi; cx++) {
-                    uint32_t tex = f.tile_tex[ry * MAX_WIN + cx];
-                    if (tex == NO_TILE) continue;
-                    int cls = (G::TILE_CLASSES > 1) ? G::tile_class(tex) : 0;
-                    const Axis& ax = f.col[cls][cx];
-                    const Axis& ay = f.row[cls][ry];
-                    if (!ax.visible || !ay.visible) continue;
-                    if ((unsigned)(X - ax.d0) >= (unsigned)ax.dlen || (unsigned)(Y - ay.d0) >= (unsigned)ay.dlen) continue;
-                    TexInfo ti = texinfo[tex];
-                    int sx = axis_sample(ax, X, false), sy = axis_sample(ay, Y, false);
-                    uint32_t texel = __ldg(atlas + ti.offset + (uint32_t)sy * ti.w + (uint32_t)sx);
-                    blend_texel(r, g, b, texel, ti.blend, 255u);
-                }
+// Texel of blit `b` under pixel (X, Y); false when the pixel is not covered.
+PG2_DEV bool blit_texel(const Blit& b, const BlitRot* rot, const uint32_t* __restrict__ atlas, int X, int Y, uint32_t* texel) {
+    int sx, sy;
+    if (!b.rotated) {
+        if ((unsigned)(X - b.ax.d0) >= (unsigned)b.ax.dlen || (unsigned)(Y - b.ay.d0) >= (unsigned)b.ay.dlen) return false;
+        sx = axis_sample(b.ax, X, b.flip_h);
+        sy = axis_sample(b.ay, Y, false);
+    } else {
+        // inverse-map the pixel centre into the un-rotated destination rect (oracle/raster.c step 4)
+        double hw = __dmul_rn((double)b.ax.dlen, 0.5), hh = __dmul_rn((double)b.ay.dlen, 0.5);
+        double cx = __dadd_rn((double)b.ax.d0, hw), cy = __dadd_rn((double)b.ay.d0, hh);
+        double px = __dsub_rn(__dadd_rn((double)X, 0.5), cx);
+        double py = __dsub_rn(__dadd_rn((double)Y, 0.5), cy);
+        double u = __dadd_rn(__dmul_rn(px, rot->c), __dmul_rn(py, rot->s));
+        double v = __dsub_rn(__dmul_rn(py, rot->c), __dmul_rn(px, rot->s));
+        double fu = floor(__dadd_rn(u, hw)), fv = floor(__dadd_rn(v, hh));
+        if (fu < 0.0 || fv < 0.0 || fu >= (double)b.ax.dlen || fv >= (double)b.ay.dlen) return false;
+        int i = (int)fu, j = (int)fv;
+        sx = b.ax.s0 + (int)((b.ax.inc / 2u + (uint32_t)i * b.ax.inc) >> 16);
+        sy = b.ay.s0 + (int)((b.ay.inc / 2u + (uint32_t)j * b.ay.inc) >> 16);
+    }
+    *texel = __ldg(atlas + b.tex_offset + (uint32_t)sy * b.tex_w + (uint32_t)sx);
+    return true;
+}
+
+// Effective alpha of a texel of a layer: 255 for opaque-copy textures, else A * alpha_mod / 255.
+PG2_DEV uint32_t layer_alpha(uint32_t texel, uint32_t blend, uint32_t alpha_mod) {
+    if (!blend) return 255u;
+    uint32_t ta = texel >> 24;
+    return alpha_mod != 255u ? (ta * alpha_mod) / 255u : ta;
+}
+
+// Reference order (bottom-up) evaluation of one pixel: clear -> pre -> tiles (y-major, x-minor) -> post.
+PG2_DEV_NOINLINE uint32_t shade_pixel_ordered(const Frame& f, const uint32_t* __restrict__ atlas, int X, int Y) {
+    uint32_t r = 0, g = 0, b = 0;   // SDL_RenderClear(0,0,0,255)
+    uint32_t texel;
+    for (int k = 0; k < f.npre; k++)
+        if (f.pre[k].ax.visible && blit_texel(f.pre[k], nullptr, atlas, X, Y, &texel)) blend_texel(r, g, b, texel, f.pre[k].blend, f.pre[k].alpha_mod);
+    {
+        int rlo = f.row_lo[Y], rhi = f.row_hi[Y], clo = f.col_lo[X], chi = f.col_hi[X];
+        for (int ry = rlo; ry <= rhi; ry++)
+            for (int cx = clo; cx <= chi; cx++) {
+                int cell = ry * MAX_WIN + cx;
+                uint32_t meta = f.tile_meta[cell];
+                if (meta == TILE_NONE) continue;
+                int cls = meta & 1;
+                const Axis& ax = f.col[cls][cx];
+                const Axis& ay = f.row[cls][ry];
+                if (!ax.visible || !ay.visible) continue;
+                if ((unsigned)(X - ax.d0) >= (unsigned)ax.dlen || (unsigned)(Y - ay.d0) >= (unsigned)ay.dlen) continue;
+                int sx = axis_sample(ax, X, false), sy = axis_sample(ay, Y, false);
+                texel = __ldg(atlas + f.tile_off[cell] + (uint32_t)sy * (uint32_t)f.cls_w[cls] + (uint32_t)sx);
+                blend_texel(r, g, b, texel, meta & 2u, 255u);
+            }
+    }
+    const uint32_t* bins = f.bin[(Y >> 2) * 8 + (X >> 3)];
+    for (int w = 0; w < MAX_POST / 32; w++) {
+        uint32_t m = bins[w];
+        while (m) {
+            int k = w * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            if (blit_texel(f.post[k], &f.post_rot[k], atlas, X, Y, &texel)) blend_texel(r, g, b, texel, f.post[k].blend, f.post[k].alpha_mod);
         }
-        // post blits through the 8x8 bins, ascending index = submission order
-        const uint32_t* bins = f.bin[(Y >> 3) * 8 + (X >> 3)];
+    }
+    return r | g << 8 | b << 16;
+}
+
+// SRC-over of one texel onto a packed 0x00BBGGRR colour; effective alpha 255 replaces and 0 is the identity
+// (both exact in blend_texel's integer arithmetic), anything else takes the full per-channel path.
+PG2_DEV uint32_t blend_packed(uint32_t color, uint32_t texel, uint32_t blend, uint32_t alpha_mod) {
+    uint32_t a = layer_alpha(texel, blend, alpha_mod);
+    if (a == 255u) return texel;
+    if (a == 0u) return color;
+    uint32_t r = color & 255u, g = (color >> 8) & 255u, b = (color >> 16) & 255u;
+    blend_texel(r, g, b, texel, blend, alpha_mod);
+    return r | g << 8 | b << 16;
+}
+
+PG2_DEV bool fast_texel(const FastBlit& fbr, const Blit& full, const BlitRot* rot, const uint32_t* __restrict__ atlas, int X, int Y, uint32_t* texel) {
+    const FastBlit fb = fbr;
+    if (fb.flags & 6u) {
+        if (fb.flags & 4u) return false;
+        return blit_texel(full, rot, atlas, X, Y, texel);
+    }
+    uint32_t i = (uint32_t)(X - fb.x0), j = (uint32_t)(Y - fb.y0);
+    if (i >= fb.w || j >= fb.h) return false;
+    uint32_t sx = (fb.hx + i * fb.incx) >> 16, sy = (fb.hy + j * fb.incy) >> 16;
+    *texel = __ldg(atlas + fb.base + sy * fb.tex_w + sx);
+    return true;
+}
+
+// clear -> pre -> tiles of one pixel in reference (bottom-up) order, packed result
+PG2_DEV_NOINLINE uint32_t shade_base_ordered(const Frame& f, const uint32_t* __restrict__ atlas, int X, int Y) {
+    uint32_t color = 0u, texel;
+    for (int k = 0; k < f.npre; k++)
+        if (fast_texel(f.fpre[k], f.pre[k], nullptr, atlas, X, Y, &texel)) color = blend_packed(color, texel, f.fpre[k].flags & 1u, f.fpre[k].alpha_mod);
+    const int rlo = f.row_lo[Y], nr = (int)f.row_hi[Y] - rlo + 1;
+    const int clo = f.col_lo[X], nc = (int)f.col_hi[X] - clo + 1;
+    for (int jr = 0; jr < nr && jr < 2; jr++)
+        for (int jc = 0; jc < nc && jc < 2; jc++) {
+            int cell = (rlo + jr) * MAX_WIN + clo + jc;
+            uint32_t meta = f.tile_meta[cell];
+            if (meta == TILE_NONE) continue;
+            int cls = meta & 1;
+            int sx = f.col_sx[cls][jc][X], sy = f.row_sy[cls][jr][Y];
+            if ((sx | sy) < 0) continue;
+            texel = __ldg(atlas + f.tile_off[cell] + (uint32_t)sy * (uint32_t)f.cls_w[cls] + (uint32_t)sx);
+            color = blend_packed(color, texel, meta & 2u, 255u);
+        }
+    return color;
+}
+
+// Shade all 4096 pixels into f.rgb. A warp owns 8x4-pixel blocks (lane = pixel); loop trip counts are uniform over
+// the warp (<= 2x2 candidate tiles, the block's post-blit bin) and lanes whose pixel is not covered are predicated
+// off, so a warp never serialises different pixels' layer lists.
+//   base colour: tile candidates TOP-DOWN ((hi,hi) .. (lo,lo) = reverse painter's order), then the pre blits; the
+//     first opaque texel decides the pixel (alpha 255 replaces, alpha 0 is the identity — exact). A partially
+//     transparent texel met on the way sends that pixel through shade_base_ordered (reference order) instead.
+//   post blits: bottom-up in submission order on top of the base colour.
+template <class G>
+PG2_DEV_NOINLINE void frame_rasterise(Frame& f, const uint32_t* __restrict__ atlas) {
+    const bool wide = f.wide != 0;
+    const int npre = f.npre;
+    for (int item = threadIdx.x; item < OBS_W * OBS_H; item += blockDim.x) {
+        const int block = item >> 5, l = item & 31;
+        const int X = ((block & 7) << 3) + (l & 7), Y = ((block >> 3) << 2) + (l >> 3);
+        uint32_t color = 0u, texel;
+        if (wide) {
+            color = shade_pixel_ordered(f, atlas, X, Y);
+        } else {
+            bool resolved = false, semi = false;
+            const int rlo = f.row_lo[Y], nr = (int)f.row_hi[Y] - rlo + 1;
+            const int clo = f.col_lo[X], nc = (int)f.col_hi[X] - clo + 1;
 #pragma unroll
-        for (int w = 0; w < MAX_POST / 32; w++) {
-            uint32_t m = bins[w];
-            while (m) {
-                int k = w * 32 + __ffs(m) - 1;
-                m &= m - 1;
-                shade_blit(f.post[k], &f.post_rot[k], atlas, X, Y, r, g, b);
+            for (int t = 0; t < 4; t++) {
+                const int jr = 1 - (t >> 1), jc = 1 - (t & 1);
+                bool act = !resolved && jr < nr && jc < nc;
+                if (!warp_any(act)) continue;
+                if (act) {
+                    int cell = (rlo + jr) * MAX_WIN + clo + jc;
+                    uint32_t meta = f.tile_meta[cell];
+                    int cls = meta & 1;
+                    int sx = f.col_sx[cls][jc][X], sy = f.row_sy[cls][jr][Y];
+                    if (meta != TILE_NONE && (sx | sy) >= 0) {
+                        texel = __ldg(atlas + f.tile_off[cell] + (uint32_t)sy * (uint32_t)f.cls_w[cls] + (uint32_t)sx);
+                        uint32_t a = (meta & 2u) ? texel >> 24 : 255u;
+                        if (a == 255u) { color = texel; resolved = true; }
+                        else if (a != 0u) { semi = true; resolved = true; }
+                    }
+                }
+            }
+            if (warp_any(!resolved)) {
+                for (int k = npre - 1; k >= 0; k--) {
+                    if (!resolved && fast_texel(f.fpre[k], f.pre[k], nullptr, atlas, X, Y, &texel)) {
+                        uint32_t a = layer_alpha(texel, f.fpre[k].flags & 1u, f.fpre[k].alpha_mod);
+                        if (a == 255u) { color = texel; resolved = true; }
+                        else if (a != 0u) { semi = true; resolved = true; }
+                    }
+                }
+            }
+            if (semi) color = shade_base_ordered(f, atlas, X, Y);
+            if (f.bin_any[block]) {
+                const uint32_t* bins = f.bin[block];
+#pragma unroll
+                for (int w = 0; w < MAX_POST / 32; w++) {
+                    uint32_t m = bins[w];
+                    while (m) {
+                        int k = w * 32 + __ffs(m) - 1;
+                        m &= m - 1;
+                        if (fast_texel(f.fpost[k], f.post[k], &f.post_rot[k], atlas, X, Y, &texel))
+                            color = blend_packed(color, texel, f.fpost[k].flags & 1u, f.fpost[k].alpha_mod);
+                    }
+                }
             }
         }
-        f.rgb[3 * p + 0] = (uint8_t)r;
-        f.rgb[3 * p + 1] = (uint8_t)g;
-        f.rgb[3 * p + 2] = (uint8_t)b;
+        uint8_t* out = f.rgb + 3 * (Y * OBS_W + X);
+        out[0] = (uint8_t)color; out[1] = (uint8_t)(color >> 8); out[2] = (uint8_t)(color >> 16);
     }
 }
 

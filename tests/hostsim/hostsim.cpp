@@ -70,7 +70,7 @@ struct Sim : SimBase {
     }
     void step(const int32_t* actions) override {
         for (int e = 0; e < N; e++) {
-            bool done = step_body<G>(st, c, e, actions[e], reward.data(), terminated.data(), truncated.data(), max_episode_steps);
+            bool done = step_body<G>(st, c, e, actions[e], reward.data(), terminated.data(), truncated.data(), max_episode_steps, StepCtx{ 0, 1 });
             if (done) reset_body<G>(st, c, e, mt_scratch.data(), arena.data(), 0);
             render(e);
         }
