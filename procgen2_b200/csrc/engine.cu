@@ -79,12 +79,13 @@ __global__ void __launch_bounds__(128) k_step(typename G::State s, CommonState c
 template <class G>
 __global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::State s, CommonState c,
                                                                     const int* __restrict__ reset_list,
-                                                                    const int* __restrict__ reset_count, int N) {
+                                                                    int* __restrict__ reset_count, int N) {
     extern __shared__ __align__(16) char smem[];
     const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* mt = (uint32_t*)smem + warp_in_cta * MT_N;
     char* arena = smem + RESET_WARPS_PER_CTA * MT_N * 4 + warp_in_cta * RESET_ARENA_BYTES;
     const int count = reset_list ? *reset_count : N;
+    if (blockIdx.x == 0 && threadIdx.x == 0) reset_count[1] = 0;   // k_render's frame ticket
     const int total_warps = gridDim.x * RESET_WARPS_PER_CTA;
     for (int w = blockIdx.x * RESET_WARPS_PER_CTA + warp_in_cta; w < count; w += total_warps) {
         int env = reset_list ? reset_list[w] : w;
@@ -92,13 +93,27 @@ __global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::
     }
 }
 
+// Persistent CTAs; frames are handed out through a ticket counter (counters[1], zeroed by k_reset, which precedes
+// every k_render on the stream), so a CTA that drew cheap frames simply takes more of them.
 template <class G>
 __global__ void __launch_bounds__(RENDER_THREADS) k_render(typename G::State s, CommonState c, const TexInfo* __restrict__ tex,
                                                            const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs,
-                                                           int* __restrict__ reset_count, int N) {
-    __shared__ Frame f;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *reset_count = 0;   // consumed by k_reset earlier on this stream
-    for (int env = blockIdx.x; env < N; env += gridDim.x) render_body<G>(s, c, env, f, tex, atlas, obs);
+                                                           int* __restrict__ counters, int N) {
+    __shared__ FrameOf<G> f;
+    __shared__ int s_env;
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[0] = 0;   // reset list consumed by k_reset earlier on this stream
+    frame_init_tiletex<G>(f, tex);
+    for (;;) {
+        if (threadIdx.x == 0) {
+            s_env = atomicAdd(&counters[1], 1);
+            f.npre = 0; f.npost = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1;
+        }
+        __syncthreads();
+        const int env = s_env;
+        if (env >= N) break;
+        render_body<G>(s, c, env, f, tex, atlas, obs, false);
+    }
+    if (threadIdx.x == 0) frame_store_wait();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -186,8 +201,10 @@ struct Engine : EngineBase {
         num_sms = prop.multiProcessorCount;
         PG2_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         // k_step mapping: aim for >= 8 warps per SM sub-partition before packing several envs into one warp
+        // lane-aware games always give a whole warp to an environment; the others pack several environments
+        // into a warp once there are >= 8 warps per SM sub-partition
         step_epw = 1;
-        while (step_epw < 32 && N / (step_epw * 2) >= num_sms * 4 * 8) step_epw *= 2;
+        if (!G::LANE_AWARE) while (step_epw < 32 && N / (step_epw * 2) >= num_sms * 4 * 8) step_epw *= 2;
         if (const char* o = getenv("PG2_STEP_EPW")) { int v = atoi(o); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) step_epw = v; }
         PG2_CUDA(cudaMalloc(&state_mem, G::State::bytes(N)));
         PG2_CUDA(cudaMemsetAsync(state_mem, 0, G::State::bytes(N), stream));
@@ -206,8 +223,8 @@ struct Engine : EngineBase {
         PG2_CUDA(cudaMalloc(&actions, sizeof(int32_t) * N));
         PG2_CUDA(cudaMalloc(&seeds_dev, sizeof(int32_t) * N));
         PG2_CUDA(cudaMalloc(&reset_list, sizeof(int) * N));
-        PG2_CUDA(cudaMalloc(&reset_count, sizeof(int)));
-        PG2_CUDA(cudaMemsetAsync(reset_count, 0, sizeof(int), stream));
+        PG2_CUDA(cudaMalloc(&reset_count, 2 * sizeof(int)));   // [0] reset-list length, [1] k_render frame ticket
+        PG2_CUDA(cudaMemsetAsync(reset_count, 0, 2 * sizeof(int), stream));
         PG2_CUDA(cudaMallocHost(&actions_pinned, sizeof(int32_t) * N));
         // texture atlas: decode the game's textures from the packed blob, upload once
         int ntex = 0;
@@ -246,11 +263,13 @@ struct Engine : EngineBase {
         return ctas < num_sms * 4 ? (ctas < 1 ? 1 : ctas) : num_sms * 4;
     }
     void launch_reset_all() {
-        k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, nullptr, nullptr, N);
+        k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, nullptr, reset_count, N);
         launches++;
     }
     void launch_render() {
-        int grid = N < num_sms * 8 ? N : num_sms * 8;
+        int per_sm = 8;
+        if (const char* o = getenv("PG2_RENDER_CTAS_PER_SM")) per_sm = atoi(o) > 0 ? atoi(o) : per_sm;
+        int grid = N < num_sms * per_sm ? N : num_sms * per_sm;
         k_render<G><<<grid, RENDER_THREADS, 0, stream>>>(st, common, texinfo, atlas, obs, reset_count, N);
         launches++;
     }

@@ -47,6 +47,8 @@ struct BossFight {
     using State = BossFightState;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
+    static constexpr int MAX_POST = 112;        // capacity of the frame's post-blit list
+    static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr int TILE_CLASSES = 1;
     static constexpr int MB = 64, NEX = 8, AB = 32, MAX_BAR = 4;
     enum Tex {
@@ -456,7 +458,8 @@ struct BossFight {
     // NOTE: bullets / explosions that died keep frame == -1 and are skipped exactly like the reference does;
     // the pools are NOT cleared by reset() in the reference either (only the counters are), but a slot is
     // only ever visited while it lies within `num` positions behind `next`, i.e. after being rewritten.
-    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, Frame& f, const TexInfo* tex) {
+    template <class F>
+    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int N = s.N;
         const Camera cam{ 0.0f, 0.0f, 1.0f };
         const double PI = 3.14159265358979323846;

@@ -43,6 +43,8 @@ struct CaveFlyer {
     static constexpr int W = 40, H = 40, MAX_OBJ = 64, NB = 32, NPART = 10;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
+    static constexpr int MAX_POST = 112;        // capacity of the frame's post-blit list
+    static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr int TILE_CLASSES = 1;
     enum Obj { O_NONE = 0, O_OBSTACLE, O_TARGET, O_ENEMY };
     enum Tex { T_WALL = 0, T_GOAL, T_TARGET, T_OBSTACLE, T_ENEMY, T_BULLET, T_SHIP, T_PARTICLE, T_EXPL0, T_BG0 = 13, NUM_BG = 13, NUM_TEX = 26 };
@@ -352,7 +354,8 @@ struct CaveFlyer {
     // ---------------------------------------------------------------------------------------
     static PG2_DEV int tile_class(uint32_t) { return 0; }
 
-    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, Frame& f, const TexInfo* tex) {
+    template <class F>
+    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x, N = s.N;
         const double PI = 3.14159265358979323846;
         Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(0.5f, 64.0f), 64.0f) };
@@ -434,7 +437,7 @@ struct CaveFlyer {
         for (int t = tid; t < ncol * nrow; t += blockDim.x) {
             int cx = t % ncol, ry = t / ncol;
             int id = get(tiles, lx + cx, H - 1 - (ly + ry));
-            f.tile_tex[ry * MAX_WIN + cx] = id == 1 ? (uint16_t)T_WALL : NO_TILE;
+            f.tile_tex[ry * MAX_WIN + cx] = id == 1 ? (uint8_t)T_WALL : NO_TILE;
         }
         __syncthreads();
     }

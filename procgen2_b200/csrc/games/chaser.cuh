@@ -43,6 +43,8 @@ struct Chaser {
     static constexpr int W = 11, H = 11, MAX_ENTS = 72, NMOB = 3;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
+    static constexpr int MAX_POST = 80;        // capacity of the frame's post-blit list
+    static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr int TILE_CLASSES = 1;
     static constexpr int TILE_STRIDE = 128, FREE_STRIDE = 64;
     enum Kind { K_NONE = 0, K_ORB, K_MOB, K_POINT };
@@ -338,7 +340,8 @@ struct Chaser {
     // ---------------------------------------------------------------------------------------
     static PG2_DEV int tile_class(uint32_t) { return 0; }
 
-    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, Frame& f, const TexInfo* tex) {
+    template <class F>
+    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x, N = s.N;
         // game_zoom = width * pixels_to_unit / map_width (chaser.cpp:401)
         Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(64.0f, PIXELS_TO_UNIT), (float)W) };
@@ -395,7 +398,7 @@ struct Chaser {
         for (int t = tid; t < ncol * nrow; t += blockDim.x) {
             int cx = t % ncol, ry = t / ncol;
             int id = get(tiles, lx + cx, H - 1 - (ly + ry));
-            f.tile_tex[ry * MAX_WIN + cx] = id == 1 ? (uint16_t)T_WALL : NO_TILE;
+            f.tile_tex[ry * MAX_WIN + cx] = id == 1 ? (uint8_t)T_WALL : NO_TILE;
         }
         __syncthreads();
     }

@@ -41,6 +41,8 @@ struct Climber {
     static constexpr int W = 20, H = 64, MAX_ENTS = 40;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
+    static constexpr int MAX_POST = 48;        // capacity of the frame's post-blit list
+    static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr int TILE_CLASSES = 2;   // wall_mid textures are 64x64, one wall_top texture is 64x53
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID };
     enum Ent { E_NONE = 0, E_MOB, E_POINT };
@@ -295,7 +297,8 @@ struct Climber {
     // ---------------------------------------------------------------------------------------
     static PG2_DEV int tile_class(uint32_t tex) { return tex < (uint32_t)T_WALL_MID0 ? 1 : 0; }
 
-    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, Frame& f, const TexInfo* tex) {
+    template <class F>
+    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x, N = s.N;
         Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(0.2f, 64.0f), 64.0f) };
         int lx, ly, ux, uy;
@@ -353,9 +356,9 @@ struct Climber {
         for (int t = tid; t < ncol * nrow; t += blockDim.x) {
             int cx = t % ncol, ry = t / ncol;
             int id = get(tiles, lx + cx, H - 1 - (ly + ry));
-            uint16_t tt = NO_TILE;
-            if (id == WALL_MID) tt = (uint16_t)(T_WALL_MID0 + theme);
-            else if (id == WALL_TOP) tt = (uint16_t)(T_WALL_TOP0 + theme);
+            uint8_t tt = NO_TILE;
+            if (id == WALL_MID) tt = (uint8_t)(T_WALL_MID0 + theme);
+            else if (id == WALL_TOP) tt = (uint8_t)(T_WALL_TOP0 + theme);
             f.tile_tex[ry * MAX_WIN + cx] = tt;
         }
         __syncthreads();

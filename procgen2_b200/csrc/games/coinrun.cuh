@@ -56,6 +56,8 @@ struct CoinRun {
     static constexpr int W = 64, H = 64, MAX_ENTS = 40, NPART = 10;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = true;    // step(): per-entity loops are strided over ctx's lanes
+    static constexpr int MAX_POST = 192;        // capacity of the frame's post-blit list
+    static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr int TILE_CLASSES = 1;
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID, LAVA_TOP, LAVA_MID, CRATE };
     enum Ent { E_NONE = 0, E_SAW, E_MOB, E_COIN };
@@ -439,7 +441,8 @@ struct CoinRun {
     // ---------------------------------------------------------------------------------------
     static PG2_DEV int tile_class(uint32_t) { return 0; }
 
-    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, Frame& f, const TexInfo* tex) {
+    template <class F>
+    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x, N = s.N;
         Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(0.3f, 64.0f), 64.0f) };   // game_zoom * width / obs_width
         int lx, ly, ux, uy;
@@ -514,12 +517,12 @@ struct CoinRun {
             int x = lx + cx, y = H - 1 - (ly + ry);
             int raw = (x < 0 || y < 0 || x >= W || y >= H) ? WALL_MID : tiles[y + x * H];
             int id = raw & 15;
-            uint16_t tt = NO_TILE;
-            if (id == WALL_MID) tt = (uint16_t)(T_WALL_MID0 + theme);
-            else if (id == WALL_TOP) tt = (uint16_t)(T_WALL_TOP0 + theme);
+            uint8_t tt = NO_TILE;
+            if (id == WALL_MID) tt = (uint8_t)(T_WALL_MID0 + theme);
+            else if (id == WALL_TOP) tt = (uint8_t)(T_WALL_TOP0 + theme);
             else if (id == LAVA_MID) tt = T_LAVA_MID;
             else if (id == LAVA_TOP) tt = T_LAVA_TOP;
-            else if (id == CRATE) tt = (uint16_t)(T_CRATE0 + (raw >> 4));
+            else if (id == CRATE) tt = (uint8_t)(T_CRATE0 + (raw >> 4));
             f.tile_tex[ry * MAX_WIN + cx] = tt;
         }
         __syncthreads();

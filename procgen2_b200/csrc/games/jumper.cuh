@@ -41,6 +41,8 @@ struct Jumper {
     static constexpr int W = 40, H = 40, MAX_SPIKES = 64, NPART = 10;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
+    static constexpr int MAX_POST = 80;        // capacity of the frame's post-blit list
+    static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr int TILE_CLASSES = 2;
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID, SPIKE };
     enum Tex {
@@ -344,7 +346,8 @@ struct Jumper {
     // ---------------------------------------------------------------------------------------
     static PG2_DEV int tile_class(uint32_t tex) { return tex < (uint32_t)T_WALL_MID0 ? 1 : 0; }
 
-    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, Frame& f, const TexInfo* tex) {
+    template <class F>
+    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x, N = s.N;
         const float zoom = 0.3f;
         Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(zoom, 64.0f), 64.0f) };
@@ -438,9 +441,9 @@ struct Jumper {
         for (int t = tid; t < ncol * nrow; t += blockDim.x) {
             int cx = t % ncol, ry = t / ncol;
             int id = get(tiles, lx + cx, H - 1 - (ly + ry));
-            uint16_t tt = NO_TILE;
-            if (id == WALL_MID) tt = (uint16_t)(T_WALL_MID0 + theme);
-            else if (id == WALL_TOP) tt = (uint16_t)(T_WALL_TOP0 + theme);
+            uint8_t tt = NO_TILE;
+            if (id == WALL_MID) tt = (uint8_t)(T_WALL_MID0 + theme);
+            else if (id == WALL_TOP) tt = (uint8_t)(T_WALL_TOP0 + theme);
             f.tile_tex[ry * MAX_WIN + cx] = tt;
         }
         __syncthreads();

@@ -32,6 +32,8 @@ struct Maze {
     static constexpr int WORLD = 25;          // world_dim (tilemap.cpp:36)
     static constexpr int TIMEOUT = 500;       // maze.cpp:49
     static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
+    static constexpr int MAX_POST = 4;        // capacity of the frame's post-blit list
+    static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr int TILE_CLASSES = 1;
     static constexpr int TILE_STRIDE = 640;
     enum Tex { T_WALL = 0, T_CHEESE = 1, T_MOUSE = 2, T_BG0 = 3, NUM_BG = 9, NUM_TEX = 12 };
@@ -151,7 +153,8 @@ struct Maze {
     // render_game(true): fill the frame description (whole CTA cooperates).
     static PG2_DEV int tile_class(uint32_t) { return 0; }
 
-    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, Frame& f, const TexInfo* tex) {
+    template <class F>
+    static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x;
         Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(64.0f, __fmul_rn(UNIT_TO_PIXELS, (float)WORLD)) };
         int lx, ly, ux, uy;
@@ -192,7 +195,7 @@ struct Maze {
         for (int t = tid; t < ncol * nrow; t += blockDim.x) {
             int cx = t % ncol, ry = t / ncol;
             int id = get(tiles, lx + cx, WORLD - 1 - (ly + ry));
-            f.tile_tex[ry * MAX_WIN + cx] = id ? (uint16_t)T_WALL : NO_TILE;
+            f.tile_tex[ry * MAX_WIN + cx] = id ? (uint8_t)T_WALL : NO_TILE;
         }
         __syncthreads();
     }

@@ -64,6 +64,11 @@ PG2_DEV Rect get_collision_overlap(const Rect& r1, const Rect& r2) {
     return res;
 }
 
+// 16.16 source increment (sl << 16) / dl; a 32-bit divide whenever the numerator fits (always, for real textures).
+PG2_DEV uint32_t fixed_inc(int sl, int dl) {
+    return sl < 65536 ? ((uint32_t)sl << 16) / (uint32_t)dl : (uint32_t)(((uint64_t)sl << 16) / (uint64_t)dl);
+}
+
 // One axis of Renderer::render_texture (renderer.cpp:5-82). The reference treats x and y
 // independently, so the crop/pad/compensate arithmetic is evaluated per axis; the same
 // descriptor also serves whole tile columns / rows of the tile layer.
@@ -114,7 +119,7 @@ PG2_DEV Axis make_axis(float pos, float cam, float cs, float size, int tex_len, 
     int d0 = f2i(dst0), dl = f2i(dstl);
     if (sl <= 0 || dl <= 0) return a;
     a.d0 = d0; a.dlen = dl; a.s0 = s0;
-    a.inc = (uint32_t)(((uint64_t)sl << 16) / (uint64_t)dl);
+    a.inc = fixed_inc(sl, dl);
     a.visible = 1;
     return a;
 }
@@ -125,7 +130,7 @@ PG2_DEV Axis make_axis_direct(float dst0, float dstl, int tex_len) {
     Axis a; a.visible = 0; a.s0 = 0; a.inc = 0;
     a.d0 = f2i(dst0); a.dlen = f2i(dstl);
     if (a.dlen <= 0 || tex_len <= 0) return a;
-    a.inc = (uint32_t)(((uint64_t)tex_len << 16) / (uint64_t)a.dlen);
+    a.inc = fixed_inc(tex_len, a.dlen);
     a.visible = 1;
     return a;
 }

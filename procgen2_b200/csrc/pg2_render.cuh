@@ -21,9 +21,11 @@ namespace pg2 {
 constexpr int MAX_WIN = 32;        // tile window extent per axis (maze: 27)
 constexpr int MAX_PRE = 2;
 constexpr int MAX_POST = 192;      // visible post blits (coinrun: 10 particles per visible mob)
-constexpr int RENDER_THREADS = 256;
-constexpr uint16_t NO_TILE = 0xffff;
-constexpr uint8_t TILE_NONE = 0xff;
+#ifndef PG2_RENDER_THREADS
+#define PG2_RENDER_THREADS 128
+#endif
+constexpr int RENDER_THREADS = PG2_RENDER_THREADS;
+constexpr uint8_t NO_TILE = 0xff;
 
 // std::sort permutation table. System_Sprite_Render::update sorts (z, entity) pairs
 // by z with std::sort (common_systems.cpp:36-38); every sprite of a game has the same z, so the
@@ -37,48 +39,50 @@ __device__ const uint8_t* g_sort_perm;
 #endif
 PG2_DEV int sort_perm(int n, int k) { return (n <= 16 || n > SORT_MAXN) ? k : g_sort_perm[n * SORT_MAXN + k]; }
 
-struct BlitRot { double s, c; };
+struct BlitRot { double s, c; };   // sin/cos of the blit angle (deterministic, see sincos_deg)
 
-// Per-pixel form of an axis-aligned blit (built once per frame by frame_finalize): coverage test = two unsigned
-// compares, sampling = one multiply-add + shift per axis (a horizontal flip is folded into hx / incx, which
-// wrap modulo 2^32 to the exact non-negative value), texel address = base + sy * tex_w + sx.
+// Per-pixel form of a blit (what the frame keeps): coverage test = two unsigned compares, sampling = one
+// multiply-add + shift per axis (a horizontal flip is folded into hx / incx, which wrap modulo 2^32 to the
+// exact non-negative value), texel address = base + sy * tex_w + sx.
 struct alignas(16) FastBlit {
-    int16_t x0, y0; uint16_t w, h;
-    uint32_t hx, incx;
-    uint32_t hy, incy, base;
-    uint16_t tex_w; uint8_t flags, alpha_mod;   // flags: 1 blend, 2 rotated (use the generic path), 4 invisible
-};   // sin/cos of the blit angle (deterministic, see sincos_deg)
+    int16_t x0, y0; uint16_t w, h;              // integer destination rect (SDL truncates the float rect)
+    uint32_t hx, incx;                          // sx = (hx + i * incx) >> 16
+    uint32_t hy, incy, base;                    // base = tex_offset + s0y * tex_w + s0x
+    uint16_t tex_w; uint8_t flags, alpha_mod;   // flags: 1 blend, 2 rotated, 4 invisible
+};
 
-struct Frame {
-    // pre / post blit lists
+struct TileTex { uint32_t offset; uint16_t w; uint8_t blend, cls; };   // tile textures: ids < MAX_TILE_TEX
+constexpr int MAX_TILE_TEX = 32;
+
+// Frame description of ONE environment, in shared memory. MAXP = capacity of the post-blit list (per game),
+// ROT = whether the game ever rotates a blit (bossfight, caveflyer, jumper HUD).
+template <int MAXP, bool ROT>
+struct FrameT {
+    static constexpr int MAX_POST = MAXP, WORDS = (MAXP + 31) / 32, NROT = ROT ? MAXP : 1;
+    static constexpr bool ROTATES = ROT;
     Blit pre[MAX_PRE];
-    Blit post[MAX_POST];
-    BlitRot post_rot[MAX_POST];
+    FastBlit fpre[MAX_PRE];
+    FastBlit fpost[MAXP];
+    BlitRot post_rot[NROT];
     int npre, npost;
     // tile layer: window origin (tile coordinates, y in render space), extents, descriptors per
     // texture shape class (textures of one class share width and height)
     int tx0, ty0, ncol, nrow, nclass;
     Axis col[2][MAX_WIN];
     Axis row[2][MAX_WIN];
-    uint16_t tile_tex[MAX_WIN * MAX_WIN];       // texture index per window cell or NO_TILE
+    uint8_t tile_tex[MAX_WIN * MAX_WIN];        // tile texture id per window cell or NO_TILE
     uint8_t col_lo[OBS_W], col_hi[OBS_W];       // per screen column: range of tile columns covering it
     uint8_t row_lo[OBS_H], row_hi[OBS_H];       // (lo > hi: none)
-    // resolved tile layer (frame_finalize): atlas offset + meta per window cell, per-class texture stride, and for
-    // every screen column / row the (at most two) covering tile columns / rows with their source texel index
-    uint32_t tile_off[MAX_WIN * MAX_WIN];
-    uint8_t tile_meta[MAX_WIN * MAX_WIN];       // TILE_NONE, or class | blend << 1
-    int16_t cls_w[2];
+    // for every screen column / row and class: source texel index under the (at most two) covering tiles
     int16_t col_sx[2][2][OBS_W];                // [class][candidate][X] -> source x, -1: not covered
     int16_t row_sy[2][2][OBS_H];
-    FastBlit fpre[MAX_PRE];
-    FastBlit fpost[MAX_POST];
     int wcount[RENDER_THREADS / 32];            // emit_post_blits: visible blits per warp
     int wide;                                   // some column / row is covered by more than two tiles (never observed)
-    // post-blit binning: 8x4-pixel blocks (one warp's pixels) x MAX_POST blits
-    uint32_t bin[128][MAX_POST / 32];
-    uint8_t bin_any[128];                       // bin has at least one blit
-    // staged output frame
-    alignas(16) uint8_t rgb[OBS_BYTES];
+    // post-blit binning: 8x4-pixel blocks (one warp's pixels) x MAXP blits
+    uint32_t bin[128][WORDS];
+    uint8_t bin_any[128];
+    TileTex tiletex[MAX_TILE_TEX];              // per CTA (filled once): atlas offset / stride / blend / class
+    alignas(16) uint8_t rgb[OBS_BYTES];         // staged output frame
 };
 
 // Deterministic sin/cos in degrees, mirrored operation by operation from oracle/raster.c
@@ -177,15 +181,37 @@ PG2_DEV Blit make_blit_rect(const TexInfo* tex, int tex_id, float dx, float dy, 
     return b;
 }
 
+// Wait until every bulk store issued by this thread has finished READING shared memory (see frame_store).
+PG2_DEV void frame_store_wait() {
+#ifndef PG2_HOSTSIM
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+
+PG2_DEV FastBlit make_fast(const Blit& b) {
+    FastBlit fb;
+    bool off = b.ax.d0 < -32768 || b.ax.d0 > 32767 || b.ay.d0 < -32768 || b.ay.d0 > 32767 || b.ax.dlen > 65535 || b.ay.dlen > 65535;
+    fb.x0 = (int16_t)b.ax.d0; fb.y0 = (int16_t)b.ay.d0;
+    fb.w = (uint16_t)max(0, b.ax.dlen); fb.h = (uint16_t)max(0, b.ay.dlen);
+    fb.incx = b.flip_h ? 0u - b.ax.inc : b.ax.inc;
+    fb.hx = b.flip_h ? b.ax.inc / 2u + (uint32_t)(b.ax.dlen - 1) * b.ax.inc : b.ax.inc / 2u;
+    fb.hy = b.ay.inc / 2u; fb.incy = b.ay.inc;
+    fb.base = b.tex_offset + (uint32_t)b.ay.s0 * b.tex_w + (uint32_t)b.ax.s0;
+    fb.tex_w = b.tex_w;
+    fb.alpha_mod = b.alpha_mod;
+    // a destination rect outside the int16 range cannot intersect the 64x64 target
+    fb.flags = (uint8_t)((b.blend ? 1 : 0) | (b.rotated ? 2 : 0) | ((b.ax.visible && !off) ? 0 : 4));
+    return fb;
+}
+
 // Ordered, compacting append of post blits by the whole CTA: candidate k (in the reference's
 // submission order) is evaluated by thread k % blockDim; only visible blits are stored, order
 // preserved through a warp ballot + a prefix over the warps' counts. make(k, blit, rot) fills the blit.
-// Must be called by every thread of the CTA.
-template <class MakeFn>
-PG2_DEV void emit_post_blits(Frame& f, int ncand, MakeFn make) {
+// Must be called by every thread of the CTA, after a __syncthreads() that follows the frame's initialisation.
+template <class F, class MakeFn>
+PG2_DEV void emit_post_blits(F& f, int ncand, MakeFn make) {
     const int tid = threadIdx.x, lane = tid % WARP_LANES, warp = tid / WARP_LANES;
     const int nwarps = ((int)blockDim.x + WARP_LANES - 1) / WARP_LANES;
-    __syncthreads();
     int n = f.npost;
     for (int base = 0; base < ncand; base += blockDim.x) {
         int k = base + tid;
@@ -200,12 +226,15 @@ PG2_DEV void emit_post_blits(Frame& f, int ncand, MakeFn make) {
         for (int w2 = 0; w2 < nwarps; w2++) { int cnt = f.wcount[w2]; if (w2 < warp) before += cnt; total += cnt; }
         if (vis) {
             int idx = n + before + __popc(m & ((1u << lane) - 1u));
-            if (idx < MAX_POST) { f.post[idx] = b; f.post_rot[idx] = rot; }
+            if (idx < F::MAX_POST) {
+                f.fpost[idx] = make_fast(b);
+                if (F::ROTATES) f.post_rot[idx] = rot;
+            }
         }
         n += total;
         __syncthreads();
     }
-    if (tid == 0) f.npost = n < MAX_POST ? n : MAX_POST;
+    if (tid == 0) f.npost = n < F::MAX_POST ? n : F::MAX_POST;
     __syncthreads();
 }
 
@@ -223,63 +252,12 @@ PG2_DEV void tile_window(const Camera& cam, int* lower_x, int* lower_y, int* upp
 
 // ---- per-pixel evaluation ---------------------------------------------------------------------
 
-PG2_DEV void shade_blit(const Blit& b, const BlitRot* rot, const uint32_t* __restrict__ atlas,
-                                           int X, int Y, uint32_t& r, uint32_t& g, uint32_t& bl) {
-    int sx, sy;
-    if (!b.rotated) {
-        if ((unsigned)(X - b.ax.d0) >= (unsigned)b.ax.dlen || (unsigned)(Y - b.ay.d0) >= (unsigned)b.ay.dlen) return;
-        sx = axis_sample(b.ax, X, b.flip_h);
-        sy = axis_sample(b.ay, Y, false);
-    } else {
-        // inverse-map the pixel centre into the un-rotated destination rect (oracle/raster.c step 4)
-        double hw = __dmul_rn((double)b.ax.dlen, 0.5), hh = __dmul_rn((double)b.ay.dlen, 0.5);
-        double cx = __dadd_rn((double)b.ax.d0, hw), cy = __dadd_rn((double)b.ay.d0, hh);
-        double px = __dsub_rn(__dadd_rn((double)X, 0.5), cx);
-        double py = __dsub_rn(__dadd_rn((double)Y, 0.5), cy);
-        double u = __dadd_rn(__dmul_rn(px, rot->c), __dmul_rn(py, rot->s));
-        double v = __dsub_rn(__dmul_rn(py, rot->c), __dmul_rn(px, rot->s));
-        double fu = floor(__dadd_rn(u, hw)), fv = floor(__dadd_rn(v, hh));
-        if (fu < 0.0 || fv < 0.0 || fu >= (double)b.ax.dlen || fv >= (double)b.ay.dlen) return;
-        int i = (int)fu, j = (int)fv;
-        sx = b.ax.s0 + (int)((b.ax.inc / 2u + (uint32_t)i * b.ax.inc) >> 16);
-        sy = b.ay.s0 + (int)((b.ay.inc / 2u + (uint32_t)j * b.ay.inc) >> 16);
-    }
-    uint32_t texel = __ldg(atlas + b.tex_offset + (uint32_t)sy * b.tex_w + (uint32_t)sx);
-    blend_texel(r, g, bl, texel, b.blend, b.alpha_mod);
-}
-
-// Conservative screen-space bounds of a blit (exact for axis-aligned ones).
-PG2_DEV void blit_bounds(const Blit& b, int* x0, int* y0, int* x1, int* y1) {
-    if (!b.rotated) {
-        *x0 = b.ax.d0; *x1 = b.ax.d0 + b.ax.dlen - 1; *y0 = b.ay.d0; *y1 = b.ay.d0 + b.ay.dlen - 1;
-    } else {
-        int rad = (b.ax.dlen + b.ay.dlen) / 2 + 2;   // >= half diagonal
-        int cx = b.ax.d0 + b.ax.dlen / 2, cy = b.ay.d0 + b.ay.dlen / 2;
-        *x0 = cx - rad; *x1 = cx + rad; *y0 = cy - rad; *y1 = cy + rad;
-    }
-}
-
-PG2_DEV FastBlit make_fast(const Blit& b) {
-    FastBlit fb;
-    fb.x0 = (int16_t)max(-32768, min(32767, b.ax.d0)); fb.y0 = (int16_t)max(-32768, min(32767, b.ay.d0));
-    fb.w = (uint16_t)min(65535, max(0, b.ax.dlen)); fb.h = (uint16_t)min(65535, max(0, b.ay.dlen));
-    fb.incx = b.flip_h ? 0u - b.ax.inc : b.ax.inc;
-    fb.hx = b.flip_h ? b.ax.inc / 2u + (uint32_t)(b.ax.dlen - 1) * b.ax.inc : b.ax.inc / 2u;
-    fb.hy = b.ay.inc / 2u; fb.incy = b.ay.inc;
-    fb.base = b.tex_offset + (uint32_t)b.ay.s0 * b.tex_w + (uint32_t)b.ax.s0;
-    fb.tex_w = b.tex_w;
-    fb.alpha_mod = b.alpha_mod;
-    bool clipped = b.ax.d0 < -32768 || b.ax.d0 > 32767 || b.ay.d0 < -32768 || b.ay.d0 > 32767 || b.ax.dlen > 65535 || b.ay.dlen > 65535;
-    fb.flags = (uint8_t)((b.blend ? 1 : 0) | ((b.rotated || clipped) ? 2 : 0) | (b.ax.visible ? 0 : 4));
-    return fb;
-}
-
-// After the game's frame builder filled pre/post blits, the tile window, col/row descriptors
-// and tile_tex (and __syncthreads()'d): resolve the tile layer into lookup tables and bin the post blits.
-template <class G>
-PG2_DEV_NOINLINE void frame_finalize(Frame& f, const TexInfo* __restrict__ texinfo) {
+// After the game's frame builder filled pre/post blits, the tile window, col/row descriptors and tile_tex
+// (and __syncthreads()'d): per-column / per-row lookup tables of the tile layer, post-blit bins.
+template <class G, class F>
+PG2_DEV_NOINLINE void frame_finalize(F& f) {
     const int tid = threadIdx.x;
-    for (int i = tid; i < 128 * (MAX_POST / 32); i += blockDim.x) (&f.bin[0][0])[i] = 0u;
+    for (int i = tid; i < 128 * F::WORDS; i += blockDim.x) (&f.bin[0][0])[i] = 0u;
     for (int i = tid; i < 128; i += blockDim.x) f.bin_any[i] = 0;
     if (tid == 0) f.wide = 0;
     // covering ranges: k < 64 -> screen column k, 64..127 -> screen row k-64
@@ -298,17 +276,7 @@ PG2_DEV_NOINLINE void frame_finalize(Frame& f, const TexInfo* __restrict__ texin
         if (is_row) { f.row_lo[p] = (uint8_t)lo; f.row_hi[p] = (uint8_t)hi; }
         else        { f.col_lo[p] = (uint8_t)lo; f.col_hi[p] = (uint8_t)hi; }
     }
-    // window cells: texture index -> atlas offset / class / blend
-    for (int t = tid; t < f.ncol * f.nrow; t += blockDim.x) {
-        int cell = (t / f.ncol) * MAX_WIN + t % f.ncol;
-        uint32_t tex = f.tile_tex[cell];
-        if (tex == NO_TILE) { f.tile_meta[cell] = TILE_NONE; continue; }
-        TexInfo ti = texinfo[tex];
-        int cls = (G::TILE_CLASSES > 1) ? G::tile_class(tex) : 0;
-        f.tile_off[cell] = ti.offset;
-        f.tile_meta[cell] = (uint8_t)(cls | (ti.blend ? 2 : 0));
-        f.cls_w[cls] = (int16_t)ti.w;     // every texture of a class has the same shape
-    }
+    for (int k = tid; k < f.npre; k += blockDim.x) f.fpre[k] = make_fast(f.pre[k]);
     __syncthreads();
     // per screen column / row and class: source texel of the (at most two) covering tiles
     for (int k = tid; k < 128 * 2 * 2; k += blockDim.x) {
@@ -322,43 +290,46 @@ PG2_DEV_NOINLINE void frame_finalize(Frame& f, const TexInfo* __restrict__ texin
         if (is_row) f.row_sy[cls][j][p] = v; else f.col_sx[cls][j][p] = v;
         if (j == 0 && cls == 0 && lo <= hi && hi - lo > 1) f.wide = 1;
     }
-    for (int k = tid; k < f.npre; k += blockDim.x) f.fpre[k] = make_fast(f.pre[k]);
     for (int k = tid; k < f.npost; k += blockDim.x) {
-        const Blit& b = f.post[k];
-        f.fpost[k] = make_fast(b);
-        if (!b.ax.visible) continue;
-        int x0, y0, x1, y1;
-        blit_bounds(b, &x0, &y0, &x1, &y1);
+        const FastBlit fb = f.fpost[k];
+        if (fb.flags & 4u) continue;
+        int x0 = fb.x0, y0 = fb.y0, x1 = fb.x0 + fb.w - 1, y1 = fb.y0 + fb.h - 1;
+        if (fb.flags & 2u) {   // conservative bounds of a rotated rect: centre +- half diagonal
+            int rad = ((int)fb.w + (int)fb.h) / 2 + 2;
+            int cx = fb.x0 + fb.w / 2, cy = fb.y0 + fb.h / 2;
+            x0 = cx - rad; x1 = cx + rad; y0 = cy - rad; y1 = cy + rad;
+        }
         if (x1 < 0 || y1 < 0 || x0 > 63 || y0 > 63) continue;
         x0 = max(x0, 0) >> 3; y0 = max(y0, 0) >> 2; x1 = min(x1, 63) >> 3; y1 = min(y1, 63) >> 2;
         for (int by = y0; by <= y1; by++)
             for (int bx = x0; bx <= x1; bx++) { atomicOr(&f.bin[by * 8 + bx][k >> 5], 1u << (k & 31)); f.bin_any[by * 8 + bx] = 1; }
     }
+    if (tid == 0) frame_store_wait();   // the previous frame's bulk store has read f.rgb
     __syncthreads();
 }
 
-// Texel of blit `b` under pixel (X, Y); false when the pixel is not covered.
-PG2_DEV bool blit_texel(const Blit& b, const BlitRot* rot, const uint32_t* __restrict__ atlas, int X, int Y, uint32_t* texel) {
-    int sx, sy;
-    if (!b.rotated) {
-        if ((unsigned)(X - b.ax.d0) >= (unsigned)b.ax.dlen || (unsigned)(Y - b.ay.d0) >= (unsigned)b.ay.dlen) return false;
-        sx = axis_sample(b.ax, X, b.flip_h);
-        sy = axis_sample(b.ay, Y, false);
-    } else {
-        // inverse-map the pixel centre into the un-rotated destination rect (oracle/raster.c step 4)
-        double hw = __dmul_rn((double)b.ax.dlen, 0.5), hh = __dmul_rn((double)b.ay.dlen, 0.5);
-        double cx = __dadd_rn((double)b.ax.d0, hw), cy = __dadd_rn((double)b.ay.d0, hh);
+// Texel of a blit under pixel (X, Y); false when the pixel is not covered.
+PG2_DEV bool fast_texel(const FastBlit& fbr, const BlitRot* rot, const uint32_t* __restrict__ atlas, int X, int Y, uint32_t* texel) {
+    const FastBlit fb = fbr;
+    uint32_t i, j;
+    if (fb.flags & 6u) {
+        if (fb.flags & 4u) return false;
+        // rotated: inverse-map the pixel centre into the un-rotated destination rect (oracle/raster.c step 4)
+        double hw = __dmul_rn((double)fb.w, 0.5), hh = __dmul_rn((double)fb.h, 0.5);
+        double cx = __dadd_rn((double)fb.x0, hw), cy = __dadd_rn((double)fb.y0, hh);
         double px = __dsub_rn(__dadd_rn((double)X, 0.5), cx);
         double py = __dsub_rn(__dadd_rn((double)Y, 0.5), cy);
         double u = __dadd_rn(__dmul_rn(px, rot->c), __dmul_rn(py, rot->s));
         double v = __dsub_rn(__dmul_rn(py, rot->c), __dmul_rn(px, rot->s));
         double fu = floor(__dadd_rn(u, hw)), fv = floor(__dadd_rn(v, hh));
-        if (fu < 0.0 || fv < 0.0 || fu >= (double)b.ax.dlen || fv >= (double)b.ay.dlen) return false;
-        int i = (int)fu, j = (int)fv;
-        sx = b.ax.s0 + (int)((b.ax.inc / 2u + (uint32_t)i * b.ax.inc) >> 16);
-        sy = b.ay.s0 + (int)((b.ay.inc / 2u + (uint32_t)j * b.ay.inc) >> 16);
+        if (fu < 0.0 || fv < 0.0 || fu >= (double)fb.w || fv >= (double)fb.h) return false;
+        i = (uint32_t)(int)fu; j = (uint32_t)(int)fv;
+    } else {
+        i = (uint32_t)(X - fb.x0); j = (uint32_t)(Y - fb.y0);
+        if (i >= fb.w || j >= fb.h) return false;
     }
-    *texel = __ldg(atlas + b.tex_offset + (uint32_t)sy * b.tex_w + (uint32_t)sx);
+    uint32_t sx = (fb.hx + i * fb.incx) >> 16, sy = (fb.hy + j * fb.incy) >> 16;
+    *texel = __ldg(atlas + fb.base + sy * fb.tex_w + sx);
     return true;
 }
 
@@ -367,41 +338,6 @@ PG2_DEV uint32_t layer_alpha(uint32_t texel, uint32_t blend, uint32_t alpha_mod)
     if (!blend) return 255u;
     uint32_t ta = texel >> 24;
     return alpha_mod != 255u ? (ta * alpha_mod) / 255u : ta;
-}
-
-// Reference order (bottom-up) evaluation of one pixel: clear -> pre -> tiles (y-major, x-minor) -> post.
-PG2_DEV_NOINLINE uint32_t shade_pixel_ordered(const Frame& f, const uint32_t* __restrict__ atlas, int X, int Y) {
-    uint32_t r = 0, g = 0, b = 0;   // SDL_RenderClear(0,0,0,255)
-    uint32_t texel;
-    for (int k = 0; k < f.npre; k++)
-        if (f.pre[k].ax.visible && blit_texel(f.pre[k], nullptr, atlas, X, Y, &texel)) blend_texel(r, g, b, texel, f.pre[k].blend, f.pre[k].alpha_mod);
-    {
-        int rlo = f.row_lo[Y], rhi = f.row_hi[Y], clo = f.col_lo[X], chi = f.col_hi[X];
-        for (int ry = rlo; ry <= rhi; ry++)
-            for (int cx = clo; cx <= chi; cx++) {
-                int cell = ry * MAX_WIN + cx;
-                uint32_t meta = f.tile_meta[cell];
-                if (meta == TILE_NONE) continue;
-                int cls = meta & 1;
-                const Axis& ax = f.col[cls][cx];
-                const Axis& ay = f.row[cls][ry];
-                if (!ax.visible || !ay.visible) continue;
-                if ((unsigned)(X - ax.d0) >= (unsigned)ax.dlen || (unsigned)(Y - ay.d0) >= (unsigned)ay.dlen) continue;
-                int sx = axis_sample(ax, X, false), sy = axis_sample(ay, Y, false);
-                texel = __ldg(atlas + f.tile_off[cell] + (uint32_t)sy * (uint32_t)f.cls_w[cls] + (uint32_t)sx);
-                blend_texel(r, g, b, texel, meta & 2u, 255u);
-            }
-    }
-    const uint32_t* bins = f.bin[(Y >> 2) * 8 + (X >> 3)];
-    for (int w = 0; w < MAX_POST / 32; w++) {
-        uint32_t m = bins[w];
-        while (m) {
-            int k = w * 32 + __ffs(m) - 1;
-            m &= m - 1;
-            if (blit_texel(f.post[k], &f.post_rot[k], atlas, X, Y, &texel)) blend_texel(r, g, b, texel, f.post[k].blend, f.post[k].alpha_mod);
-        }
-    }
-    return r | g << 8 | b << 16;
 }
 
 // SRC-over of one texel onto a packed 0x00BBGGRR colour; effective alpha 255 replaces and 0 is the identity
@@ -415,36 +351,32 @@ PG2_DEV uint32_t blend_packed(uint32_t color, uint32_t texel, uint32_t blend, ui
     return r | g << 8 | b << 16;
 }
 
-PG2_DEV bool fast_texel(const FastBlit& fbr, const Blit& full, const BlitRot* rot, const uint32_t* __restrict__ atlas, int X, int Y, uint32_t* texel) {
-    const FastBlit fb = fbr;
-    if (fb.flags & 6u) {
-        if (fb.flags & 4u) return false;
-        return blit_texel(full, rot, atlas, X, Y, texel);
-    }
-    uint32_t i = (uint32_t)(X - fb.x0), j = (uint32_t)(Y - fb.y0);
-    if (i >= fb.w || j >= fb.h) return false;
-    uint32_t sx = (fb.hx + i * fb.incx) >> 16, sy = (fb.hy + j * fb.incy) >> 16;
-    *texel = __ldg(atlas + fb.base + sy * fb.tex_w + sx);
-    return true;
-}
-
-// clear -> pre -> tiles of one pixel in reference (bottom-up) order, packed result
-PG2_DEV_NOINLINE uint32_t shade_base_ordered(const Frame& f, const uint32_t* __restrict__ atlas, int X, int Y) {
-    uint32_t color = 0u, texel;
+// clear -> pre -> tiles of one pixel in reference (bottom-up) order; `general` walks the whole covering range
+// (frames where more than two tiles cover a column / row), else the two-candidate tables are used.
+template <class F>
+PG2_DEV_NOINLINE uint32_t shade_base_ordered(const F& f, const uint32_t* __restrict__ atlas, int X, int Y, bool general) {
+    uint32_t color = 0u, texel;   // SDL_RenderClear(0,0,0,255)
     for (int k = 0; k < f.npre; k++)
-        if (fast_texel(f.fpre[k], f.pre[k], nullptr, atlas, X, Y, &texel)) color = blend_packed(color, texel, f.fpre[k].flags & 1u, f.fpre[k].alpha_mod);
-    const int rlo = f.row_lo[Y], nr = (int)f.row_hi[Y] - rlo + 1;
-    const int clo = f.col_lo[X], nc = (int)f.col_hi[X] - clo + 1;
-    for (int jr = 0; jr < nr && jr < 2; jr++)
-        for (int jc = 0; jc < nc && jc < 2; jc++) {
-            int cell = (rlo + jr) * MAX_WIN + clo + jc;
-            uint32_t meta = f.tile_meta[cell];
-            if (meta == TILE_NONE) continue;
-            int cls = meta & 1;
-            int sx = f.col_sx[cls][jc][X], sy = f.row_sy[cls][jr][Y];
-            if ((sx | sy) < 0) continue;
-            texel = __ldg(atlas + f.tile_off[cell] + (uint32_t)sy * (uint32_t)f.cls_w[cls] + (uint32_t)sx);
-            color = blend_packed(color, texel, meta & 2u, 255u);
+        if (fast_texel(f.fpre[k], nullptr, atlas, X, Y, &texel)) color = blend_packed(color, texel, f.fpre[k].flags & 1u, f.fpre[k].alpha_mod);
+    const int rlo = f.row_lo[Y], rhi = f.row_hi[Y], clo = f.col_lo[X], chi = f.col_hi[X];
+    for (int ry = rlo; ry <= rhi; ry++)
+        for (int cx = clo; cx <= chi; cx++) {
+            uint32_t t = f.tile_tex[ry * MAX_WIN + cx];
+            if (t == NO_TILE) continue;
+            const TileTex tt = f.tiletex[t];
+            int sx, sy;
+            if (general) {
+                const Axis& ax = f.col[tt.cls][cx];
+                const Axis& ay = f.row[tt.cls][ry];
+                if (!ax.visible || !ay.visible) continue;
+                if ((unsigned)(X - ax.d0) >= (unsigned)ax.dlen || (unsigned)(Y - ay.d0) >= (unsigned)ay.dlen) continue;
+                sx = axis_sample(ax, X, false); sy = axis_sample(ay, Y, false);
+            } else {
+                sx = f.col_sx[tt.cls][cx - clo][X]; sy = f.row_sy[tt.cls][ry - rlo][Y];
+                if ((sx | sy) < 0) continue;
+            }
+            texel = __ldg(atlas + tt.offset + (uint32_t)sy * tt.w + (uint32_t)sx);
+            color = blend_packed(color, texel, tt.blend, 255u);
         }
     return color;
 }
@@ -456,18 +388,16 @@ PG2_DEV_NOINLINE uint32_t shade_base_ordered(const Frame& f, const uint32_t* __r
 //     first opaque texel decides the pixel (alpha 255 replaces, alpha 0 is the identity — exact). A partially
 //     transparent texel met on the way sends that pixel through shade_base_ordered (reference order) instead.
 //   post blits: bottom-up in submission order on top of the base colour.
-template <class G>
-PG2_DEV_NOINLINE void frame_rasterise(Frame& f, const uint32_t* __restrict__ atlas) {
+template <class G, class F>
+PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas) {
     const bool wide = f.wide != 0;
     const int npre = f.npre;
     for (int item = threadIdx.x; item < OBS_W * OBS_H; item += blockDim.x) {
         const int block = item >> 5, l = item & 31;
         const int X = ((block & 7) << 3) + (l & 7), Y = ((block >> 3) << 2) + (l >> 3);
         uint32_t color = 0u, texel;
-        if (wide) {
-            color = shade_pixel_ordered(f, atlas, X, Y);
-        } else {
-            bool resolved = false, semi = false;
+        bool resolved = false, semi = wide;
+        if (!wide) {
             const int rlo = f.row_lo[Y], nr = (int)f.row_hi[Y] - rlo + 1;
             const int clo = f.col_lo[X], nc = (int)f.col_hi[X] - clo + 1;
 #pragma unroll
@@ -476,39 +406,40 @@ PG2_DEV_NOINLINE void frame_rasterise(Frame& f, const uint32_t* __restrict__ atl
                 bool act = !resolved && jr < nr && jc < nc;
                 if (!warp_any(act)) continue;
                 if (act) {
-                    int cell = (rlo + jr) * MAX_WIN + clo + jc;
-                    uint32_t meta = f.tile_meta[cell];
-                    int cls = meta & 1;
-                    int sx = f.col_sx[cls][jc][X], sy = f.row_sy[cls][jr][Y];
-                    if (meta != TILE_NONE && (sx | sy) >= 0) {
-                        texel = __ldg(atlas + f.tile_off[cell] + (uint32_t)sy * (uint32_t)f.cls_w[cls] + (uint32_t)sx);
-                        uint32_t a = (meta & 2u) ? texel >> 24 : 255u;
-                        if (a == 255u) { color = texel; resolved = true; }
-                        else if (a != 0u) { semi = true; resolved = true; }
+                    uint32_t tid = f.tile_tex[(rlo + jr) * MAX_WIN + clo + jc];
+                    if (tid != NO_TILE) {
+                        const TileTex tt = f.tiletex[tid];
+                        int sx = f.col_sx[tt.cls][jc][X], sy = f.row_sy[tt.cls][jr][Y];
+                        if ((sx | sy) >= 0) {
+                            texel = __ldg(atlas + tt.offset + (uint32_t)sy * tt.w + (uint32_t)sx);
+                            uint32_t a = tt.blend ? texel >> 24 : 255u;
+                            if (a == 255u) { color = texel; resolved = true; }
+                            else if (a != 0u) { semi = true; resolved = true; }
+                        }
                     }
                 }
             }
             if (warp_any(!resolved)) {
                 for (int k = npre - 1; k >= 0; k--) {
-                    if (!resolved && fast_texel(f.fpre[k], f.pre[k], nullptr, atlas, X, Y, &texel)) {
+                    if (!resolved && fast_texel(f.fpre[k], nullptr, atlas, X, Y, &texel)) {
                         uint32_t a = layer_alpha(texel, f.fpre[k].flags & 1u, f.fpre[k].alpha_mod);
                         if (a == 255u) { color = texel; resolved = true; }
                         else if (a != 0u) { semi = true; resolved = true; }
                     }
                 }
             }
-            if (semi) color = shade_base_ordered(f, atlas, X, Y);
-            if (f.bin_any[block]) {
-                const uint32_t* bins = f.bin[block];
+        }
+        if (semi) color = shade_base_ordered(f, atlas, X, Y, wide);
+        if (f.bin_any[block]) {
+            const uint32_t* bins = f.bin[block];
 #pragma unroll
-                for (int w = 0; w < MAX_POST / 32; w++) {
-                    uint32_t m = bins[w];
-                    while (m) {
-                        int k = w * 32 + __ffs(m) - 1;
-                        m &= m - 1;
-                        if (fast_texel(f.fpost[k], f.post[k], &f.post_rot[k], atlas, X, Y, &texel))
-                            color = blend_packed(color, texel, f.fpost[k].flags & 1u, f.fpost[k].alpha_mod);
-                    }
+            for (int w = 0; w < F::WORDS; w++) {
+                uint32_t m = bins[w];
+                while (m) {
+                    int k = w * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    if (fast_texel(f.fpost[k], &f.post_rot[F::ROTATES ? k : 0], atlas, X, Y, &texel))
+                        color = blend_packed(color, texel, f.fpost[k].flags & 1u, f.fpost[k].alpha_mod);
                 }
             }
         }
@@ -517,8 +448,11 @@ PG2_DEV_NOINLINE void frame_rasterise(Frame& f, const uint32_t* __restrict__ atl
     }
 }
 
-// One 12 288-byte TMA bulk store shared -> global (Blackwell/Hopper async proxy).
-PG2_DEV void frame_store(Frame& f, uint8_t* __restrict__ dst) {
+// The finished frame leaves the SM as ONE 12 288-byte TMA bulk store shared -> global (async proxy). The copy is
+// only ISSUED here; the CTA goes on with the next frame's description and waits (frame_store_wait) right before
+// it overwrites f.rgb again, so the drain of the staging buffer overlaps useful work.
+template <class F>
+PG2_DEV void frame_store(F& f, uint8_t* __restrict__ dst) {
 #ifdef PG2_HOSTSIM
     memcpy(dst, f.rgb, OBS_BYTES);
     return;
@@ -529,10 +463,23 @@ PG2_DEV void frame_store(Frame& f, uint8_t* __restrict__ dst) {
         uint32_t src = (uint32_t)__cvta_generic_to_shared(f.rgb);
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "n"(OBS_BYTES) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be reused afterwards
+    }
+#endif
+}
+
+// Per-CTA table of the game's tile textures (ids < MAX_TILE_TEX), filled once before the first frame.
+template <class G, class F>
+PG2_DEV void frame_init_tiletex(F& f, const TexInfo* __restrict__ tex) {
+    int ntex = 0;
+    (void)ntex;
+    for (int t = threadIdx.x; t < MAX_TILE_TEX && t < G::NUM_TEX; t += blockDim.x) {
+        TexInfo ti = tex[t];
+        TileTex tt;
+        tt.offset = ti.offset; tt.w = ti.w; tt.blend = ti.blend ? 1 : 0;
+        tt.cls = (uint8_t)((G::TILE_CLASSES > 1) ? G::tile_class((uint32_t)t) : 0);
+        f.tiletex[t] = tt;
     }
     __syncthreads();
-#endif
 }
 
 }  // namespace pg2

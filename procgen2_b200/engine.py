@@ -32,7 +32,7 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.ENGINE
+    path = os.environ.get("PG2_ENGINE_LIB", _build.ENGINE)   # override: A/B experiments with alternative builds
     if not os.path.exists(path):
         raise RuntimeError("CUDA extension %s is missing: run `python -m procgen2_b200.build` "
                            "(there is no CPU fallback)" % path)

@@ -40,7 +40,7 @@ struct Sim : SimBase {
     std::vector<uint32_t> mt_scratch;
     std::vector<TexInfo> tex;
     std::vector<uint32_t> atlas;
-    std::unique_ptr<Frame> frame;
+    std::unique_ptr<FrameOf<G>> frame;
 
     bool init(int n, uint32_t base_seed, int max_ep, const char* assets, std::string* err) {
         N = n; max_episode_steps = max_ep;
@@ -50,11 +50,12 @@ struct Sim : SimBase {
         c = CommonState::bind(common_mem.data(), N);
         arena.assign(RESET_ARENA_BYTES, 0);
         mt_scratch.assign(MT_N, 0);
-        frame.reset(new Frame());
+        frame.reset(new FrameOf<G>());
         obs.assign((size_t)N * OBS_BYTES, 0); terminated.assign(N, 0); truncated.assign(N, 0); reward.assign(N, 0.0f);
         int ntex = 0;
         const char* const* names = G::texture_names(&ntex);
         if (!load_textures(assets, names, ntex, &tex, &atlas, err)) return false;
+        frame_init_tiletex<G>(*frame, tex.data());
         for (int e = 0; e < N; e++) seed_body(c, e, base_seed + (uint32_t)e, true);
         for (int e = 0; e < N; e++) reset_body<G>(st, c, e, mt_scratch.data(), arena.data(), 0);
         return true;
