@@ -64,6 +64,15 @@ PG2_API int32_t pg2_step_device(pg2_engine* e, const int32_t* actions_device);
  * terminated / truncated: num_envs uint8. */
 PG2_API int32_t pg2_fetch(pg2_engine* e, uint8_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated);
 
+/* Depth-1 pipelined stepping for host-buffer callers: enqueues step t (H2D of its actions, the kernels, D2H of
+ * its results into the given host buffers — pinned for true overlap — on a second stream) and returns when the
+ * results of step t-1, written to the buffers passed to the PREVIOUS call, are complete. Alternate two sets of
+ * host buffers; pg2_pipeline_flush() completes the last step. The HBM outputs are double-buffered from the first
+ * call on, so pg2_*_device() pointers alternate between two buffers in this mode. */
+PG2_API int32_t pg2_step_pipelined(pg2_engine* e, const int32_t* actions_host, uint8_t* obs, float* reward,
+                                   uint8_t* terminated, uint8_t* truncated);
+PG2_API int32_t pg2_pipeline_flush(pg2_engine* e);
+
 /* Device-resident results (valid until the next step on the engine's stream). */
 PG2_API uint8_t* pg2_obs_device(pg2_engine* e);
 PG2_API float* pg2_reward_device(pg2_engine* e);

@@ -147,6 +147,18 @@ struct EngineBase {
     TexInfo* texinfo = nullptr;
     uint32_t* atlas = nullptr;
     int32_t* actions_pinned = nullptr;
+    // depth-1 pipelined stepping (pg2_step_pipelined): double-buffered outputs + a copy stream
+    bool pipelined = false;
+    int cur = 0;
+    uint8_t* obs_b[2] = { nullptr, nullptr };
+    float* reward_b[2] = { nullptr, nullptr };
+    uint8_t* term_b[2] = { nullptr, nullptr };
+    uint8_t* trunc_b[2] = { nullptr, nullptr };
+    int32_t* actions_b[2] = { nullptr, nullptr };
+    int32_t* pinned_b[2] = { nullptr, nullptr };
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_step[2] = { nullptr, nullptr }, ev_copy[2] = { nullptr, nullptr }, ev_h2d[2] = { nullptr, nullptr };
+    bool copy_pending[2] = { false, false };
     uint8_t* sort_table = nullptr;
     // optional per-kernel timing
     bool profiling = false;
@@ -179,10 +191,17 @@ struct EngineBase {
     int free_all() {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
+        if (pipelined) { cudaStreamSynchronize(copy_stream); obs = obs_b[0]; reward = reward_b[0]; terminated = term_b[0]; truncated = trunc_b[0]; }
         cudaFree(state_mem); cudaFree(common_mem); cudaFree(obs); cudaFree(reward); cudaFree(terminated);
         cudaFree(truncated); cudaFree(actions); cudaFree(seeds_dev); cudaFree(reset_list); cudaFree(reset_count);
         cudaFree(texinfo); cudaFree(atlas); cudaFree(sort_table);
         if (actions_pinned) cudaFreeHost(actions_pinned);
+        if (pipelined) {
+            // slot 0 aliases the primary buffers (freed above)
+            cudaFree(obs_b[1]); cudaFree(reward_b[1]); cudaFree(term_b[1]); cudaFree(trunc_b[1]);
+            for (int k = 0; k < 2; k++) { cudaFree(actions_b[k]); cudaFreeHost(pinned_b[k]); cudaEventDestroy(ev_step[k]); cudaEventDestroy(ev_copy[k]); cudaEventDestroy(ev_h2d[k]); }
+            cudaStreamDestroy(copy_stream);
+        }
         if (stream) cudaStreamDestroy(stream);
         return 0;
     }
@@ -386,6 +405,64 @@ int32_t pg2_fetch(pg2_engine* e, uint8_t* obs, float* reward, uint8_t* terminate
     if (terminated) PG2_CUDA(cudaMemcpyAsync(terminated, b->terminated, b->N, cudaMemcpyDeviceToHost, b->stream));
     if (truncated) PG2_CUDA(cudaMemcpyAsync(truncated, b->truncated, b->N, cudaMemcpyDeviceToHost, b->stream));
     PG2_CUDA(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+// Depth-1 pipelined stepping: enqueue step t (H2D of its actions, the three kernels, D2H of its results into the
+// given host buffers on a second stream) and return once the results of step t-1 — written to the buffers passed
+// to the PREVIOUS call — are complete. The caller alternates two sets of (pinned) host buffers; outputs are
+// double-buffered in HBM so that the copy of step t-1 overlaps the kernels of step t.
+static int enable_pipeline(EngineBase* b) {
+    const int N = b->N;
+    b->obs_b[0] = b->obs; b->reward_b[0] = b->reward; b->term_b[0] = b->terminated; b->trunc_b[0] = b->truncated;
+    PG2_CUDA(cudaMalloc(&b->obs_b[1], (size_t)N * OBS_BYTES));
+    PG2_CUDA(cudaMalloc(&b->reward_b[1], sizeof(float) * N));
+    PG2_CUDA(cudaMalloc(&b->term_b[1], N));
+    PG2_CUDA(cudaMalloc(&b->trunc_b[1], N));
+    PG2_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        PG2_CUDA(cudaMalloc(&b->actions_b[k], sizeof(int32_t) * N));
+        PG2_CUDA(cudaMallocHost(&b->pinned_b[k], sizeof(int32_t) * N));
+        PG2_CUDA(cudaEventCreateWithFlags(&b->ev_step[k], cudaEventDisableTiming));
+        PG2_CUDA(cudaEventCreateWithFlags(&b->ev_copy[k], cudaEventDisableTiming));
+        PG2_CUDA(cudaEventCreateWithFlags(&b->ev_h2d[k], cudaEventDisableTiming));
+    }
+    b->cur = 0;
+    b->pipelined = true;
+    return 0;
+}
+
+int32_t pg2_step_pipelined(pg2_engine* e, const int32_t* actions_host, uint8_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated) {
+    EngineBase* b = e->impl.get();
+    PG2_CUDA(cudaSetDevice(b->device));
+    if (!b->pipelined && enable_pipeline(b)) return 1;
+    const int prev = b->cur, slot = b->cur ^ 1, N = b->N;
+    // this slot's HBM outputs were last read by the copy issued two calls ago, its staging buffer by that call's H2D
+    if (b->copy_pending[slot]) PG2_CUDA(cudaStreamWaitEvent(b->stream, b->ev_copy[slot], 0));
+    PG2_CUDA(cudaEventSynchronize(b->ev_h2d[slot]));
+    memcpy(b->pinned_b[slot], actions_host, sizeof(int32_t) * N);
+    PG2_CUDA(cudaMemcpyAsync(b->actions_b[slot], b->pinned_b[slot], sizeof(int32_t) * N, cudaMemcpyHostToDevice, b->stream));
+    PG2_CUDA(cudaEventRecord(b->ev_h2d[slot], b->stream));
+    b->obs = b->obs_b[slot]; b->reward = b->reward_b[slot]; b->terminated = b->term_b[slot]; b->truncated = b->trunc_b[slot];
+    if (b->step_device(b->actions_b[slot])) return 1;
+    PG2_CUDA(cudaEventRecord(b->ev_step[slot], b->stream));
+    PG2_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_step[slot], 0));
+    if (obs) PG2_CUDA(cudaMemcpyAsync(obs, b->obs, (size_t)N * OBS_BYTES, cudaMemcpyDeviceToHost, b->copy_stream));
+    if (reward) PG2_CUDA(cudaMemcpyAsync(reward, b->reward, sizeof(float) * N, cudaMemcpyDeviceToHost, b->copy_stream));
+    if (terminated) PG2_CUDA(cudaMemcpyAsync(terminated, b->terminated, N, cudaMemcpyDeviceToHost, b->copy_stream));
+    if (truncated) PG2_CUDA(cudaMemcpyAsync(truncated, b->truncated, N, cudaMemcpyDeviceToHost, b->copy_stream));
+    PG2_CUDA(cudaEventRecord(b->ev_copy[slot], b->copy_stream));
+    b->copy_pending[slot] = true;
+    if (b->copy_pending[prev]) PG2_CUDA(cudaEventSynchronize(b->ev_copy[prev]));   // results of the previous call are ready
+    b->cur = slot;
+    return 0;
+}
+
+// Wait for the results of the last pg2_step_pipelined call.
+int32_t pg2_pipeline_flush(pg2_engine* e) {
+    EngineBase* b = e->impl.get();
+    PG2_CUDA(cudaSetDevice(b->device));
+    if (b->pipelined) PG2_CUDA(cudaStreamSynchronize(b->copy_stream));
     return 0;
 }
 

@@ -42,7 +42,7 @@ struct CaveFlyer {
     using State = CaveFlyerState;
     static constexpr int W = 40, H = 40, MAX_OBJ = 64, NB = 32, NPART = 10;
     static constexpr int SUB_STEPS = 4;
-    static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
+    static constexpr bool LANE_AWARE = false;   // step() supports warp-per-env (ctx) but measures faster thread-per-env (r01j)
     static constexpr int MAX_POST = 112;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr int TILE_CLASSES = 1;
@@ -136,11 +136,10 @@ struct CaveFlyer {
                 world.x = __fadd_rn(ax, -0.4f); world.y = __fadd_rn(ay, -0.4f);
                 if (dpx != 0.0f) avx = 0.0f;
                 if (dpy != 0.0f) avy = 0.0f;
-                for (int k = 0; k < nobj; k++) {
-                    int o = s.hazard_order[k * N + env];
-                    if (s.obj_type[o * N + env] == O_NONE) continue;
-                    if (check_collision(world, obj_rect(o))) { alive = false; break; }
-                }
+                bool hit = false;
+                for (int o = ctx.lane; o < nobj; o += ctx.nlanes)
+                    if (s.obj_type[o * N + env] != O_NONE && check_collision(world, obj_rect(o))) hit = true;
+                if (ctx.any(hit)) alive = false;
                 if (check_collision(world, goal_rect)) achieved_goal = true;
                 cam_x = __fmul_rn(ax, UNIT_TO_PIXELS);
                 cam_y = __fmul_rn(ay, UNIT_TO_PIXELS);
@@ -174,8 +173,9 @@ struct CaveFlyer {
                 p_enabled = movement_y > 0.0f;
             }
 
-            // ================= System_Mob_AI::update =================
-            for (int o = 0; o < nobj; o++) {
+            // ================= System_Mob_AI::update (one enemy per lane) =================
+            ctx.sync();
+            for (int o = ctx.lane; o < nobj; o += ctx.nlanes) {
                 if (s.obj_type[o * N + env] != O_ENEMY) continue;
                 float x = s.obj_x[o * N + env], y = s.obj_y[o * N + env], vx = s.obj_vx[o * N + env], vy = s.obj_vy[o * N + env];
                 x = __fadd_rn(x, __fmul_rn(vx, dt));
@@ -186,6 +186,7 @@ struct CaveFlyer {
             }
 
             // ================= System_Particles::update =================
+            ctx.sync();
             {
                 int dead_index = -1;
                 for (int i = 0; i < NPART; i++) {
@@ -214,11 +215,14 @@ struct CaveFlyer {
             if (!alive || achieved_goal) break;
         }
 
-        s.ax[env] = ax; s.ay[env] = ay; s.arot[env] = rot; s.avx[env] = avx; s.avy[env] = avy;
-        s.next_bullet[env] = next_bullet; s.num_bullets[env] = num_bullets; s.bullet_timer[env] = bullet_timer;
-        s.p_timer[env] = p_timer; s.p_enabled[env] = p_enabled;
-        c.cam_x[env] = cam_x; c.cam_y[env] = cam_y;
-        c.sprites_valid[env] = 1;
+        ctx.sync();
+        if (ctx.leader()) {
+            s.ax[env] = ax; s.ay[env] = ay; s.arot[env] = rot; s.avx[env] = avx; s.avy[env] = avy;
+            s.next_bullet[env] = next_bullet; s.num_bullets[env] = num_bullets; s.bullet_timer[env] = bullet_timer;
+            s.p_timer[env] = p_timer; s.p_enabled[env] = p_enabled;
+            c.cam_x[env] = cam_x; c.cam_y[env] = cam_y;
+            c.sprites_valid[env] = 1;
+        }
         *reward = __fadd_rn(__fmul_rn((float)achieved_goal, 10.0f), __fmul_rn((float)targets_destroyed, 3.0f));
         return !alive || achieved_goal;
     }

@@ -42,7 +42,7 @@ struct Chaser {
     using State = ChaserState;
     static constexpr int W = 11, H = 11, MAX_ENTS = 72, NMOB = 3;
     static constexpr int SUB_STEPS = 4;
-    static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
+    static constexpr bool LANE_AWARE = true;    // step(): the point loop is strided over ctx's lanes, the rest is uniform
     static constexpr int MAX_POST = 80;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr int TILE_CLASSES = 1;
@@ -203,8 +203,10 @@ struct Chaser {
             if (eat_timer > 0.0f) eat_timer = fmaxf(0.0f, __fsub_rn(eat_timer, dt));
 
             // ================= System_Point::update =================
-            point_delta = 0; points_available = 0;
-            for (int e = 0; e < nents; e++) {
+            ctx.sync();
+            int delta = 0, avail = 0;
+            bool ate_orb = false;
+            for (int e = ctx.lane; e < nents; e += ctx.nlanes) {
                 int kind = s.ent_kind[e * N + env];
                 if (kind != K_ORB && kind != K_POINT) continue;
                 int cell = s.ent_cell[e * N + env];
@@ -212,19 +214,25 @@ struct Chaser {
                 Rect rect = kind == K_ORB ? Rect{ __fadd_rn(-0.5f, px), __fadd_rn(-0.5f, py), 1.0f, 1.0f }
                                           : Rect{ __fadd_rn(-0.3f, px), __fadd_rn(-0.3f, py), 0.6f, 0.6f };
                 if (check_collision(agent_rect, rect)) {
-                    if (kind == K_ORB) eat_timer = 75.0f;
-                    point_delta++;
+                    if (kind == K_ORB) ate_orb = true;
+                    delta++;
                     s.ent_kind[e * N + env] = K_NONE;
-                } else points_available++;
+                } else avail++;
             }
+            if (ctx.any(ate_orb)) eat_timer = 75.0f;   // System_Mob_AI::eat()
+            point_delta = ctx.sum(delta);
+            points_available = ctx.sum(avail);
             if (dead || points_available == 0) break;
         }
 
-        s.ax[env] = ax; s.ay[env] = ay; s.avx[env] = avx; s.avy[env] = avy;
-        s.next_vx[env] = next_vx; s.next_vy[env] = next_vy; s.input_timer[env] = input_timer;
-        s.anim_timer[env] = anim_timer; s.eat_timer[env] = eat_timer; s.anim_index[env] = anim_index;
-        c.mti[env] = rng.idx;
-        c.sprites_valid[env] = 1;
+        ctx.sync();
+        if (ctx.leader()) {
+            s.ax[env] = ax; s.ay[env] = ay; s.avx[env] = avx; s.avy[env] = avy;
+            s.next_vx[env] = next_vx; s.next_vy[env] = next_vy; s.input_timer[env] = input_timer;
+            s.anim_timer[env] = anim_timer; s.eat_timer[env] = eat_timer; s.anim_index[env] = anim_index;
+            c.mti[env] = rng.idx;
+            c.sprites_valid[env] = 1;
+        }
         *reward = __fadd_rn(__fmul_rn((float)point_delta, 0.04f), __fmul_rn((float)(points_available == 0), 10.0f));
         return dead || points_available == 0;
     }

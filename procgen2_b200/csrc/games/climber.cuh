@@ -40,7 +40,7 @@ struct Climber {
     using State = ClimberState;
     static constexpr int W = 20, H = 64, MAX_ENTS = 40;
     static constexpr int SUB_STEPS = 4;
-    static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
+    static constexpr bool LANE_AWARE = true;    // step(): per-entity loops are strided over ctx's lanes
     static constexpr int MAX_POST = 48;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr int TILE_CLASSES = 2;   // wall_mid textures are 64x64, one wall_top texture is 64x53
@@ -127,8 +127,9 @@ struct Climber {
             const Rect agent_rect{ __fadd_rn(-0.5f, ax), __fadd_rn(-1.0f, ay), 1.0f, 1.0f };
 
             // ---- System_Mob_AI::update, System_Point::update, System_Sprite_Render::update (animation)
-            dead = false; point_delta = 0; points_available = 0;
-            for (int e = 0; e < nents; e++) {
+            bool hit = false;
+            int delta = 0, avail = 0;
+            for (int e = ctx.lane; e < nents; e += ctx.nlanes) {
                 int type = s.ent_type[e * N + env];
                 if (type == E_MOB) {
                     float x = s.ent_x[e * N + env], y = s.ent_y[e * N + env], vx = s.ent_vx[e * N + env];
@@ -137,35 +138,36 @@ struct Climber {
                     CollisionResult wc = tile_collision(wall_sensor, tile_at, wall);
                     x = __fadd_rn(wc.x, 0.5f);
                     Rect rect{ __fadd_rn(-0.4f, x), __fadd_rn(-0.4f, y), 0.8f, 0.8f };
-                    if (check_collision(agent_rect, rect)) dead = true;
+                    if (check_collision(agent_rect, rect)) hit = true;
                     int spawn_x = s.ent_spawn_x[e * N + env];
                     bool end_patrol = x > (float)(spawn_x + 4) || x < (float)(spawn_x - 4);
                     if (wc.collided || end_patrol) vx = __fmul_rn(vx, -1.0f);
                     s.ent_x[e * N + env] = x; s.ent_vx[e * N + env] = vx;
                     s.ent_flip[e * N + env] = vx < 0.0f;
-                }
-            }
-            for (int e = 0; e < nents; e++) {
-                int type = s.ent_type[e * N + env];
-                if (type == E_POINT) {
-                    Rect rect{ __fadd_rn(-0.5f, s.ent_x[e * N + env]), __fadd_rn(-0.5f, s.ent_y[e * N + env]), 1.0f, 1.0f };
-                    if (check_collision(agent_rect, rect)) { point_delta++; s.ent_type[e * N + env] = E_NONE; }
-                    else points_available++;
-                } else if (type == E_MOB) {
+                    // System_Sprite_Render::update (animation) of the same entity
                     float t = __fadd_rn(s.ent_anim_t[e * N + env], dt);
                     int adv = f2i(__fmul_rn(t, 0.2f));
                     t = __fsub_rn(t, __fdiv_rn((float)adv, 0.2f));
                     s.ent_anim_t[e * N + env] = t;
                     s.ent_frame[e * N + env] = (uint8_t)((s.ent_frame[e * N + env] + adv) % 2);
+                } else if (type == E_POINT) {
+                    Rect rect{ __fadd_rn(-0.5f, s.ent_x[e * N + env]), __fadd_rn(-0.5f, s.ent_y[e * N + env]), 1.0f, 1.0f };
+                    if (check_collision(agent_rect, rect)) { delta++; s.ent_type[e * N + env] = E_NONE; }
+                    else avail++;
                 }
             }
+            dead = ctx.any(hit);
+            point_delta = ctx.sum(delta);
+            points_available = ctx.sum(avail);
             if (dead || points_available == 0) break;
         }
 
-        s.ax[env] = ax; s.ay[env] = ay; s.avx[env] = avx; s.avy[env] = avy; s.agent_t[env] = agent_t;
-        s.on_ground[env] = on_ground; s.face_forward[env] = face_forward;
-        c.cam_y[env] = cam_y;
-        c.sprites_valid[env] = 1;
+        if (ctx.leader()) {
+            s.ax[env] = ax; s.ay[env] = ay; s.avx[env] = avx; s.avy[env] = avy; s.agent_t[env] = agent_t;
+            s.on_ground[env] = on_ground; s.face_forward[env] = face_forward;
+            c.cam_y[env] = cam_y;
+            c.sprites_valid[env] = 1;
+        }
         *reward = __fadd_rn((float)point_delta, __fmul_rn((float)(points_available == 0), 10.0f));
         return dead || points_available == 0;
     }

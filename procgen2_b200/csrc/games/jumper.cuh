@@ -40,7 +40,7 @@ struct Jumper {
     using State = JumperState;
     static constexpr int W = 40, H = 40, MAX_SPIKES = 64, NPART = 10;
     static constexpr int SUB_STEPS = 4;
-    static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
+    static constexpr bool LANE_AWARE = false;   // step() supports warp-per-env (ctx) but measures faster thread-per-env (r01j)
     static constexpr int MAX_POST = 80;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr int TILE_CLASSES = 2;
@@ -122,12 +122,14 @@ struct Jumper {
                 if (dpx != 0.0f) avx = 0.0f;
                 if (dpy > 0.0f && cd.collided) avy = 0.0f;
                 if (on_ground) avy = 0.0f;
-                for (int k = 0; k < nspikes; k++) {
+                bool hit = false;
+                for (int k = ctx.lane; k < nspikes; k += ctx.nlanes) {
                     int cell = s.spike_cell[k * N + env];
                     float sx = __fadd_rn((float)(cell / H), 0.5f), sy = __fadd_rn((float)(H - 1 - cell % H), 0.5f);
                     Rect hz{ __fadd_rn(sx, -0.25f), __fadd_rn(sy, -0.25f), 0.5f, 0.5f };
-                    if (check_collision(world, hz)) { alive = false; break; }
+                    if (check_collision(world, hz)) hit = true;
                 }
+                if (ctx.any(hit)) alive = false;
                 if (check_collision(world, goal_rect)) achieved_goal = true;
                 cam_x = __fmul_rn(ax, UNIT_TO_PIXELS);
                 cam_y = __fmul_rn(__fsub_rn(ay, 0.5f), UNIT_TO_PIXELS);
@@ -139,33 +141,46 @@ struct Jumper {
                 to_goal_y = __fsub_rn(goal_y, ay);
                 p_enabled = !on_ground || fabsf(avx) > 0.01f;
             }
-            // ---- System_Particles::update (offset { 0.0f, -0.2f }, lifespan 5, spawn_time 0.5)
+            // ---- System_Particles::update (offset { 0.0f, -0.2f }, lifespan 5, spawn_time 0.5): one particle per lane
             {
-                int dead_index = -1;
-                for (int i = 0; i < NPART; i++) {
+                bool dead_here = false;
+                for (int i = ctx.lane; i < NPART; i += ctx.nlanes) {
                     float life = __fsub_rn(s.p_life[i * N + env], dt);
                     s.p_life[i * N + env] = life;
-                    if (life <= 0.0f) dead_index = i;
+                    if (life <= 0.0f) dead_here = true;
+                }
+                // dead_index = the LAST dead particle in index order
+                int dead_index = -1;
+                if (ctx.nlanes == 1) {
+                    for (int i = 0; i < NPART; i++) if (s.p_life[i * N + env] <= 0.0f) dead_index = i;
+                } else {
+                    uint32_t m = __ballot_sync(0xffffffffu, dead_here && ctx.lane < NPART);
+                    dead_index = m ? 31 - __clz(m) : -1;
                 }
                 p_timer = __fadd_rn(p_timer, dt);
                 if (dead_index != -1 && p_timer >= 0.5f && p_enabled) {
                     p_timer = fmodf(p_timer, 0.5f);
                     int pi = dead_index * N + env;
-                    s.p_life[pi] = 5.0f;
-                    s.p_x[pi] = __fadd_rn(ax, 0.0f);
-                    s.p_y[pi] = __fadd_rn(ay, -0.2f);
+                    if (ctx.leader()) {
+                        s.p_life[pi] = 5.0f;
+                        s.p_x[pi] = __fadd_rn(ax, 0.0f);
+                        s.p_y[pi] = __fadd_rn(ay, -0.2f);
+                    }
                 }
+                ctx.sync();
             }
             if (!alive || achieved_goal) break;
         }
 
-        s.ax[env] = ax; s.ay[env] = ay; s.avx[env] = avx; s.avy[env] = avy; s.agent_t[env] = agent_t;
-        s.on_ground[env] = on_ground; s.face_forward[env] = face_forward;
-        s.jump_timer[env] = jump_timer; s.jumps_left[env] = jumps_left;
-        s.to_goal_x[env] = to_goal_x; s.to_goal_y[env] = to_goal_y;
-        s.p_timer[env] = p_timer; s.p_enabled[env] = p_enabled;
-        c.cam_x[env] = cam_x; c.cam_y[env] = cam_y;
-        c.sprites_valid[env] = 1;
+        if (ctx.leader()) {
+            s.ax[env] = ax; s.ay[env] = ay; s.avx[env] = avx; s.avy[env] = avy; s.agent_t[env] = agent_t;
+            s.on_ground[env] = on_ground; s.face_forward[env] = face_forward;
+            s.jump_timer[env] = jump_timer; s.jumps_left[env] = jumps_left;
+            s.to_goal_x[env] = to_goal_x; s.to_goal_y[env] = to_goal_y;
+            s.p_timer[env] = p_timer; s.p_enabled[env] = p_enabled;
+            c.cam_x[env] = cam_x; c.cam_y[env] = cam_y;
+            c.sprites_valid[env] = 1;
+        }
         *reward = __fmul_rn((float)achieved_goal, 10.0f);
         return !alive || achieved_goal;
     }

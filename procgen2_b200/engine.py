@@ -46,6 +46,8 @@ def load_library():
     L.pg2_step.argtypes = [vp, vp]
     L.pg2_step_device.argtypes = [vp, vp]
     L.pg2_fetch.argtypes = [vp, vp, vp, vp, vp]
+    L.pg2_step_pipelined.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.pg2_pipeline_flush.argtypes = [vp]
     for name in ("pg2_obs_device", "pg2_reward_device", "pg2_terminated_device", "pg2_truncated_device", "pg2_stream"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = vp
@@ -119,6 +121,17 @@ class BatchedEnv:
 
     def fetch_into(self, obs=None, reward=None, terminated=None, truncated=None):
         _check(self._L.pg2_fetch(self._h, *(x.ctypes.data if x is not None else None for x in (obs, reward, terminated, truncated))))
+
+    def step_pipelined(self, actions, obs, reward, terminated, truncated=None):
+        """Depth-1 pipelined step (pg2_step_pipelined): enqueue this step with its results going to the given
+        (pinned) host arrays; returns when the PREVIOUS call's arrays are complete. Alternate two sets."""
+        a = np.ascontiguousarray(actions, np.int32)
+        assert a.shape == (self.num_envs,)
+        _check(self._L.pg2_step_pipelined(self._h, a.ctypes.data, *(x.ctypes.data if x is not None else None
+                                                                     for x in (obs, reward, terminated, truncated))))
+
+    def flush(self):
+        _check(self._L.pg2_pipeline_flush(self._h))
 
     def sync(self):
         _check(self._L.pg2_sync(self._h))

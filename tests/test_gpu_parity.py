@@ -174,3 +174,31 @@ def test_device_resident_views_and_reseed():
     f2 = env.fetch()[0]
     np.testing.assert_array_equal(f1, f2)
     env.close()
+
+
+def test_pipelined_stepping_equals_sequential():
+    """pg2_step_pipelined (double-buffered outputs, D2H on a second stream) returns, one call late, exactly what
+    pg2_step + pg2_fetch return."""
+    from procgen2_b200.engine import BatchedEnv
+    n, T = 64, 60
+    rs = np.random.RandomState(21)
+    acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
+    a = BatchedEnv("coinrun", n, seed=31)
+    b = BatchedEnv("coinrun", n, seed=31)
+    a.reset(); b.reset()
+    seq = []
+    for t in range(T):
+        a.step(acts[t])
+        o, r, d, _ = a.fetch()
+        seq.append((o, r, d))
+    bufs = [(np.empty((n, 64, 64, 3), np.uint8), np.empty(n, np.float32), np.empty(n, np.uint8)) for _ in range(2)]
+    for t in range(T):
+        b.step_pipelined(acts[t], *bufs[t & 1])
+        if t > 0:   # the previous call's buffers are complete now
+            o, r, d = bufs[(t - 1) & 1]
+            np.testing.assert_array_equal(o, seq[t - 1][0]); np.testing.assert_array_equal(r, seq[t - 1][1])
+            np.testing.assert_array_equal(d.astype(bool), seq[t - 1][2])
+    b.flush()
+    o, r, d = bufs[(T - 1) & 1]
+    np.testing.assert_array_equal(o, seq[T - 1][0]); np.testing.assert_array_equal(r, seq[T - 1][1])
+    a.close(); b.close()
