@@ -203,6 +203,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the one JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=dev)
 
     N = a.envs_per_gpu

@@ -76,6 +76,8 @@ struct FrameT {
     // for every screen column / row and class: source texel index under the (at most two) covering tiles
     int16_t col_sx[2][2][OBS_W];                // [class][candidate][X] -> source x, -1: not covered
     int16_t row_sy[2][2][OBS_H];
+    int32_t pre_sx[MAX_PRE][OBS_W];             // pre blits (backgrounds), resolved per column / row:
+    int32_t pre_row[MAX_PRE][OBS_H];            //   texel index = pre_row[k][Y] + pre_sx[k][X], -1: not covered
     int wcount[RENDER_THREADS / 32];            // emit_post_blits: visible blits per warp
     int wide;                                   // some column / row is covered by more than two tiles (never observed)
     // post-blit binning: 8x4-pixel blocks (one warp's pixels) x MAXP blits
@@ -277,6 +279,17 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
         else        { f.col_lo[p] = (uint8_t)lo; f.col_hi[p] = (uint8_t)hi; }
     }
     for (int k = tid; k < f.npre; k += blockDim.x) f.fpre[k] = make_fast(f.pre[k]);
+    for (int k = tid; k < f.npre * 128; k += blockDim.x) {
+        const Blit& b = f.pre[k >> 7];
+        int p = k & 63, is_row = (k >> 6) & 1;
+        const Axis& a = is_row ? b.ay : b.ax;
+        int32_t v = -1;
+        if (b.ax.visible && !b.rotated && (unsigned)(p - a.d0) < (unsigned)a.dlen) {
+            int smp = axis_sample(a, p, is_row ? false : (b.flip_h != 0));
+            v = is_row ? (int32_t)(b.tex_offset + (uint32_t)smp * b.tex_w) : smp;
+        }
+        if (is_row) f.pre_row[k >> 7][p] = v; else f.pre_sx[k >> 7][p] = v;
+    }
     __syncthreads();
     // per screen column / row and class: source texel of the (at most two) covering tiles
     for (int k = tid; k < 128 * 2 * 2; k += blockDim.x) {
@@ -400,12 +413,15 @@ PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas) 
         if (!wide) {
             const int rlo = f.row_lo[Y], nr = (int)f.row_hi[Y] - rlo + 1;
             const int clo = f.col_lo[X], nc = (int)f.col_hi[X] - clo + 1;
+            // every lane walks ITS candidates from the topmost one: candidate index q = jr * ncc + jc, descending
+            const int nrr = min(max(nr, 0), 2), ncc = min(max(nc, 0), 2);
+            int q = nrr * ncc - 1;
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-                const int jr = 1 - (t >> 1), jc = 1 - (t & 1);
-                bool act = !resolved && jr < nr && jc < nc;
-                if (!warp_any(act)) continue;
+                bool act = !resolved && q >= 0;
+                if (!warp_any(act)) break;
                 if (act) {
+                    const int jr = ncc == 2 ? q >> 1 : q, jc = ncc == 2 ? q & 1 : 0;
                     uint32_t tid = f.tile_tex[(rlo + jr) * MAX_WIN + clo + jc];
                     if (tid != NO_TILE) {
                         const TileTex tt = f.tiletex[tid];
@@ -417,11 +433,14 @@ PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas) 
                             else if (a != 0u) { semi = true; resolved = true; }
                         }
                     }
+                    q--;
                 }
             }
             if (warp_any(!resolved)) {
                 for (int k = npre - 1; k >= 0; k--) {
-                    if (!resolved && fast_texel(f.fpre[k], nullptr, atlas, X, Y, &texel)) {
+                    const int cx = f.pre_sx[k][X], ro = f.pre_row[k][Y];
+                    if (!resolved && (cx | ro) >= 0) {
+                        texel = __ldg(atlas + (uint32_t)ro + (uint32_t)cx);
                         uint32_t a = layer_alpha(texel, f.fpre[k].flags & 1u, f.fpre[k].alpha_mod);
                         if (a == 255u) { color = texel; resolved = true; }
                         else if (a != 0u) { semi = true; resolved = true; }
