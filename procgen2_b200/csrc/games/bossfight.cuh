@@ -463,7 +463,7 @@ struct BossFight {
         const int N = s.N;
         const Camera cam{ 0.0f, 0.0f, 1.0f };
         const double PI = 3.14159265358979323846;
-        if (is_role(0)) {
+        if (is_role(1)) {
             f.tx0 = 0; f.ty0 = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1;
             int bg = T_BG0 + s.bg_index[env];
             float sc = __fdiv_rn(__fmul_rn(__fdiv_rn(1.0f, (float)tex[bg].h), 64.0f), 1.0f);

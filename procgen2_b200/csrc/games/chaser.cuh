@@ -358,7 +358,7 @@ struct Chaser {
         const int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);
         const int nents = s.num_ents[env];
         const bool sprites = c.sprites_valid[env] != 0;
-        if (is_role(0)) {
+        if (is_role(1)) {
             f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = 1;
             int bg = T_BG0 + s.bg_index[env];
             TexInfo bt = tex[bg];
@@ -370,6 +370,18 @@ struct Chaser {
         int nlive = 0;
         if (sprites)
             for (int k = 0; k < nents; k++) nlive += s.ent_kind[s.sprite_order[k * N + env] * N + env] != K_NONE;
+        // tile layer first, on the CTA's LAST threads: it overlaps the blit construction of the first warps below
+        const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_WALL].w);
+        for (int t = (int)blockDim.x - 1 - tid; t < ncol + nrow; t += blockDim.x) {
+            if (t < ncol) f.col[0][t] = make_axis(__fmul_rn((float)(lx + t), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tex[T_WALL].w, tscale, false, false);
+            else f.row[0][t - ncol] = make_axis(__fmul_rn((float)(ly + t - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, tex[T_WALL].h, tscale, false, true);
+        }
+        const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
+        for (int t = (int)blockDim.x - 1 - tid; t < ncol * nrow; t += blockDim.x) {
+            int cx = t % ncol, ry = t / ncol;
+            int id = get(tiles, lx + cx, H - 1 - (ly + ry));
+            f.tile_tex[ry * MAX_WIN + cx] = id == 1 ? (uint8_t)T_WALL : NO_TILE;
+        }
         emit_post_blits(f, nlive + 1, [&](int k, Blit& b, BlitRot&) {
             if (k < nlive) {
                 int want = sort_perm(nlive, k), e = 0;
@@ -397,17 +409,6 @@ struct Chaser {
                 b = make_blit(tex, T_AGENT, px, py, cam, __fmul_rn(__fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_AGENT].w), 1.0f));
             }
         });
-        const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_WALL].w);
-        for (int t = tid; t < ncol + nrow; t += blockDim.x) {
-            if (t < ncol) f.col[0][t] = make_axis(__fmul_rn((float)(lx + t), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tex[T_WALL].w, tscale, false, false);
-            else f.row[0][t - ncol] = make_axis(__fmul_rn((float)(ly + t - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, tex[T_WALL].h, tscale, false, true);
-        }
-        const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
-        for (int t = tid; t < ncol * nrow; t += blockDim.x) {
-            int cx = t % ncol, ry = t / ncol;
-            int id = get(tiles, lx + cx, H - 1 - (ly + ry));
-            f.tile_tex[ry * MAX_WIN + cx] = id == 1 ? (uint8_t)T_WALL : NO_TILE;
-        }
         __syncthreads();
     }
 };

@@ -309,7 +309,7 @@ struct Climber {
         const int nents = s.num_ents[env];
         const bool sprites = c.sprites_valid[env] != 0;
         const int theme = s.map_theme[env];
-        if (is_role(0)) {
+        if (is_role(1)) {
             f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = 2;
             int bg = T_BG0 + s.bg_index[env];
             TexInfo bt = tex[bg];
@@ -322,6 +322,24 @@ struct Climber {
         int nlive = 0;
         if (sprites)
             for (int k = 0; k < nents; k++) nlive += s.ent_type[s.sprite_order[k * N + env] * N + env] != E_NONE;
+        // tile layer first, on the CTA's LAST threads: it overlaps the blit construction of the first warps below
+        // tile layer: class 0 = wall_mid texture of the theme, class 1 = wall_top texture
+        for (int t = (int)blockDim.x - 1 - tid; t < 2 * (ncol + nrow); t += blockDim.x) {
+            int cls = t / (ncol + nrow), u = t % (ncol + nrow);
+            int ti = (cls ? T_WALL_TOP0 : T_WALL_MID0) + theme;
+            float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[ti].w);
+            if (u < ncol) f.col[cls][u] = make_axis(__fmul_rn((float)(lx + u), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tex[ti].w, tscale, false, false);
+            else f.row[cls][u - ncol] = make_axis(__fmul_rn((float)(ly + u - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, tex[ti].h, tscale, false, true);
+        }
+        const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
+        for (int t = (int)blockDim.x - 1 - tid; t < ncol * nrow; t += blockDim.x) {
+            int cx = t % ncol, ry = t / ncol;
+            int id = get(tiles, lx + cx, H - 1 - (ly + ry));
+            uint8_t tt = NO_TILE;
+            if (id == WALL_MID) tt = (uint8_t)(T_WALL_MID0 + theme);
+            else if (id == WALL_TOP) tt = (uint8_t)(T_WALL_TOP0 + theme);
+            f.tile_tex[ry * MAX_WIN + cx] = tt;
+        }
         emit_post_blits(f, nlive + 1, [&](int k, Blit& b, BlitRot&) {
             if (k < nlive) {
                 int want = sort_perm(nlive, k), e = 0;
@@ -346,23 +364,6 @@ struct Climber {
                 b = make_blit(tex, t, px, py, cam, __fdiv_rn(__fmul_rn(0.8f, UNIT_TO_PIXELS), (float)tex[t].w), 1.0f, s.face_forward[env] == 0);
             }
         });
-        // tile layer: class 0 = wall_mid texture of the theme, class 1 = wall_top texture
-        for (int t = tid; t < 2 * (ncol + nrow); t += blockDim.x) {
-            int cls = t / (ncol + nrow), u = t % (ncol + nrow);
-            int ti = (cls ? T_WALL_TOP0 : T_WALL_MID0) + theme;
-            float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[ti].w);
-            if (u < ncol) f.col[cls][u] = make_axis(__fmul_rn((float)(lx + u), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tex[ti].w, tscale, false, false);
-            else f.row[cls][u - ncol] = make_axis(__fmul_rn((float)(ly + u - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, tex[ti].h, tscale, false, true);
-        }
-        const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
-        for (int t = tid; t < ncol * nrow; t += blockDim.x) {
-            int cx = t % ncol, ry = t / ncol;
-            int id = get(tiles, lx + cx, H - 1 - (ly + ry));
-            uint8_t tt = NO_TILE;
-            if (id == WALL_MID) tt = (uint8_t)(T_WALL_MID0 + theme);
-            else if (id == WALL_TOP) tt = (uint8_t)(T_WALL_TOP0 + theme);
-            f.tile_tex[ry * MAX_WIN + cx] = tt;
-        }
         __syncthreads();
     }
 };

@@ -160,7 +160,7 @@ struct Maze {
         int lx, ly, ux, uy;
         tile_window(cam, &lx, &ly, &ux, &uy);
         int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);
-        if (is_role(0)) {
+        if (is_role(1)) {
             f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = 1;
             // background (maze.cpp:402-408)
             int bg = T_BG0 + s.bg_index[env];
@@ -172,6 +172,19 @@ struct Maze {
             f.npre = 1;
         }
         const int ncheese = c.sprites_valid[env] ? 1 : 0;
+        // tile layer first, on the CTA's LAST threads: it overlaps the blit construction of the first warps below
+        // tile layer (tilemap.cpp:111-131)
+        const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_WALL].w);
+        for (int t = (int)blockDim.x - 1 - tid; t < ncol + nrow; t += blockDim.x) {
+            if (t < ncol) f.col[0][t] = make_axis(__fmul_rn((float)(lx + t), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tex[T_WALL].w, tscale, false, false);
+            else f.row[0][t - ncol] = make_axis(__fmul_rn((float)(ly + t - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, tex[T_WALL].h, tscale, false, true);
+        }
+        const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
+        for (int t = (int)blockDim.x - 1 - tid; t < ncol * nrow; t += blockDim.x) {
+            int cx = t % ncol, ry = t / ncol;
+            int id = get(tiles, lx + cx, WORLD - 1 - (ly + ry));
+            f.tile_tex[ry * MAX_WIN + cx] = id ? (uint8_t)T_WALL : NO_TILE;
+        }
         emit_post_blits(f, ncheese + 1, [&](int k, Blit& b, BlitRot&) {
             if (k < ncheese) {   // cheese (tilemap.cpp:95-98, common_systems.cpp:41-63)
                 float gx = __fmul_rn(__fadd_rn(s.goal_x[env], -0.48f), UNIT_TO_PIXELS);
@@ -185,18 +198,6 @@ struct Maze {
                 b = make_blit(tex, T_MOUSE, ax, ay, cam, sc, 1.0f, s.face_forward[env] != 0);
             }
         });
-        // tile layer (tilemap.cpp:111-131)
-        const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_WALL].w);
-        for (int t = tid; t < ncol + nrow; t += blockDim.x) {
-            if (t < ncol) f.col[0][t] = make_axis(__fmul_rn((float)(lx + t), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tex[T_WALL].w, tscale, false, false);
-            else f.row[0][t - ncol] = make_axis(__fmul_rn((float)(ly + t - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, tex[T_WALL].h, tscale, false, true);
-        }
-        const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
-        for (int t = tid; t < ncol * nrow; t += blockDim.x) {
-            int cx = t % ncol, ry = t / ncol;
-            int id = get(tiles, lx + cx, WORLD - 1 - (ly + ry));
-            f.tile_tex[ry * MAX_WIN + cx] = id ? (uint8_t)T_WALL : NO_TILE;
-        }
         __syncthreads();
     }
 };

@@ -53,6 +53,7 @@ inline int warp_sum(int v) { return v; }
 inline int warp_bcast(int v) { return v; }
 inline float warp_bcast(float v) { return v; }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 using std::max;
 using std::min;
 }

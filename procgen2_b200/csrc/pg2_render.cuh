@@ -79,6 +79,7 @@ struct FrameT {
     int32_t pre_sx[MAX_PRE][OBS_W];             // pre blits (backgrounds), resolved per column / row:
     int32_t pre_row[MAX_PRE][OBS_H];            //   texel index = pre_row[k][Y] + pre_sx[k][X], -1: not covered
     int wcount[RENDER_THREADS / 32];            // emit_post_blits: visible blits per warp
+    int next_block;                             // frame_rasterise: dynamic hand-out of the 128 pixel blocks to warps
     int wide;                                   // some column / row is covered by more than two tiles (never observed)
     // post-blit binning: 8x4-pixel blocks (one warp's pixels) x MAXP blits
     uint32_t bin[128][WORDS];
@@ -261,7 +262,7 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
     const int tid = threadIdx.x;
     for (int i = tid; i < 128 * F::WORDS; i += blockDim.x) (&f.bin[0][0])[i] = 0u;
     for (int i = tid; i < 128; i += blockDim.x) f.bin_any[i] = 0;
-    if (tid == 0) f.wide = 0;
+    if (tid == 0) { f.wide = 0; f.next_block = 0; }
     // covering ranges: k < 64 -> screen column k, 64..127 -> screen row k-64
     for (int k = tid; k < 128; k += blockDim.x) {
         bool is_row = k >= 64;
@@ -405,8 +406,14 @@ template <class G, class F>
 PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas) {
     const bool wide = f.wide != 0;
     const int npre = f.npre;
-    for (int item = threadIdx.x; item < OBS_W * OBS_H; item += blockDim.x) {
-        const int block = item >> 5, l = item & 31;
+    const int lane = threadIdx.x % WARP_LANES;
+    for (;;) {
+      // blocks are handed out dynamically: a warp that drew cheap blocks (no sprites) simply takes more of them
+      int block = 0;
+      if (lane == 0) block = atomicAdd(&f.next_block, 1);
+      block = warp_bcast(block);
+      if (block >= 128) break;
+      for (int l = lane; l < 32; l += WARP_LANES) {
         const int X = ((block & 7) << 3) + (l & 7), Y = ((block >> 3) << 2) + (l >> 3);
         uint32_t color = 0u, texel;
         bool resolved = false, semi = wide;
@@ -464,6 +471,7 @@ PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas) 
         }
         uint8_t* out = f.rgb + 3 * (Y * OBS_W + X);
         out[0] = (uint8_t)color; out[1] = (uint8_t)(color >> 8); out[2] = (uint8_t)(color >> 16);
+      }
     }
 }
 
