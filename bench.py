@@ -13,9 +13,10 @@ the global env index space, seeds = base + global index), no collective on the s
 value    device-resident throughput: actions already in HBM, observations stay in HBM; every step is
          timed with CUDA events on the engine's stream and an L2 flush (256 MiB memset) runs
          between steps, outside the event pairs.
-e2e      same metric through the host-buffer C ABI (pg2_step with host actions, pg2_fetch into pinned
-         host memory: H2D of the actions and D2H of observations/rewards/terminated inside the timed
-         region).
+e2e      same metric through the host-buffer C ABI: every step copies its actions H2D from pinned memory and
+         its observations / rewards / terminated flags D2H into pinned memory, inside the timed region.
+         pg2_step_pipelined overlaps the D2H of step t-1 with the kernels of step t (depth-1 pipeline, two
+         alternating host buffer sets); e2e.sequential is the strictly serial pg2_step + pg2_fetch pair.
 roofline dominant kernel (k_render) against the measured HBM copy bandwidth in MEASURED_PEAKS.json,
          algorithmic bytes = 12 297 B per env-step.
 """
@@ -36,6 +37,15 @@ ALG_BYTES_PER_ENV_STEP = 12288 + 4 + 4 + 1   # obs write + action read + reward 
 METRIC = "env-steps/sec incl. 64x64 RGB render"
 UNIT = "env-steps/s"
 BASE_SEED = 0
+
+
+def measured_traffic(game, envs):
+    """dram bytes per launch of the dominant kernel, from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s@%d" % (game, envs))
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) if t else None
+    except Exception:
+        return None
 
 
 def peaks():
@@ -310,7 +320,7 @@ def main():
                     "steps": e2e_steps, "api": "pg2_step_pipelined(host actions -> pinned host obs/reward/terminated), depth-1 pipeline",
                     "sequential": N * world * e2e_steps / seq_s},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": measured_traffic(a.game, N),
                          "kernel": "k_render<%s>" % a.game, "kernel_ms": render_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_ENV_STEP * N},
             "kernel_ms_per_step": {k: v / max(prof_steps, 1) for k, v in prof.items()},
