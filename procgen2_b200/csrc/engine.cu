@@ -47,29 +47,42 @@ __global__ void k_seed(CommonState c, int N, uint32_t base_seed, const int32_t* 
     seed_body(c, env, seeds ? (uint32_t)seeds[env] : base_seed + (uint32_t)env, init_persistent != 0);
 }
 
+// Device counters (int[4]): [0], [1] = length of the reset list, indexed by step parity (k_step of step t appends to
+// [t & 1] and zeroes the other one, which the previous step has consumed); [2] = frame ticket of the main render,
+// [3] = frame ticket of the tail render (both zeroed by k_step / before a full reset).
+//
 // `epw` = environments per warp (power of two, 1..32): lanes [0, epw) of every warp own one environment each.
-// Small batches use epw = 1 (no divergence between environments, 32x more warps to hide latency); large
-// batches pack more environments per warp. Finished envs are appended to the reset list (ballot + one atomic/warp).
+// Lane-aware games use epw = 1 (a whole warp per environment, per-entity loops strided over the lanes); the others
+// pack several environments into a warp once the batch is large. Finished envs are appended to the reset list
+// (ballot + one atomic per warp) and flagged in `pending` (the overlapped render skips them).
 template <class G>
 __global__ void __launch_bounds__(128) k_step(typename G::State s, CommonState c, const int32_t* __restrict__ actions,
                                               float* __restrict__ reward, uint8_t* __restrict__ terminated,
                                               uint8_t* __restrict__ truncated, int* __restrict__ reset_list,
-                                              int* __restrict__ reset_count, int N, int max_episode_steps, int auto_reset, int epw) {
+                                              uint8_t* __restrict__ pending, int* __restrict__ counters, int parity,
+                                              int N, int max_episode_steps, int auto_reset, int epw) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = gtid & 31;
+    if (gtid == 0) { counters[parity ^ 1] = 0; counters[2] = 0; counters[3] = 0; }
     bool done = false;
     int env;
     if (epw == 1) {   // a whole warp per environment (warp-uniform branch)
         env = gtid >> 5;
-        if (env < N) done = step_body<G>(s, c, env, actions[env], reward, terminated, truncated, max_episode_steps, StepCtx{ lane, 32 }) && auto_reset && lane == 0;
+        if (env < N) {
+            done = step_body<G>(s, c, env, actions[env], reward, terminated, truncated, max_episode_steps, StepCtx{ lane, 32 }) && auto_reset && lane == 0;
+            if (lane == 0) pending[env] = done;
+        }
     } else {
         env = (gtid >> 5) * epw + lane;
-        if (lane < epw && env < N) done = step_body<G>(s, c, env, actions[env], reward, terminated, truncated, max_episode_steps, StepCtx{ 0, 1 }) && auto_reset;
+        if (lane < epw && env < N) {
+            done = step_body<G>(s, c, env, actions[env], reward, terminated, truncated, max_episode_steps, StepCtx{ 0, 1 }) && auto_reset;
+            pending[env] = done;
+        }
     }
     unsigned m = __ballot_sync(0xffffffffu, done);
     if (m) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(reset_count, __popc(m));
+        if (lane == 0) base = atomicAdd(&counters[parity], __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (done) reset_list[base + __popc(m & ((1u << lane) - 1u))] = env;
     }
@@ -79,13 +92,12 @@ __global__ void __launch_bounds__(128) k_step(typename G::State s, CommonState c
 template <class G>
 __global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::State s, CommonState c,
                                                                     const int* __restrict__ reset_list,
-                                                                    int* __restrict__ reset_count, int N) {
+                                                                    const int* __restrict__ reset_count, int N) {
     extern __shared__ __align__(16) char smem[];
     const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* mt = (uint32_t*)smem + warp_in_cta * MT_N;
     char* arena = smem + RESET_WARPS_PER_CTA * MT_N * 4 + warp_in_cta * RESET_ARENA_BYTES;
     const int count = reset_list ? *reset_count : N;
-    if (blockIdx.x == 0 && threadIdx.x == 0) reset_count[1] = 0;   // k_render's frame ticket
     const int total_warps = gridDim.x * RESET_WARPS_PER_CTA;
     for (int w = blockIdx.x * RESET_WARPS_PER_CTA + warp_in_cta; w < count; w += total_warps) {
         int env = reset_list ? reset_list[w] : w;
@@ -93,24 +105,28 @@ __global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::
     }
 }
 
-// Persistent CTAs; frames are handed out through a ticket counter (counters[1], zeroed by k_reset, which precedes
-// every k_render on the stream), so a CTA that drew cheap frames simply takes more of them.
+// Persistent CTAs; frames are handed out through a ticket counter, so a CTA that drew cheap frames simply takes
+// more of them. mode 0: every env; mode 1: every env that is NOT being reset this step (k_reset runs concurrently
+// on a second stream); mode 2: exactly the envs of the reset list (after k_reset).
 template <class G>
 __global__ void __launch_bounds__(RENDER_THREADS) k_render(typename G::State s, CommonState c, const TexInfo* __restrict__ tex,
                                                            const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs,
-                                                           int* __restrict__ counters, int N) {
+                                                           int* __restrict__ ticket, int mode, const int* __restrict__ list,
+                                                           const int* __restrict__ list_count, const uint8_t* __restrict__ pending, int N) {
     __shared__ FrameOf<G> f;
     __shared__ int s_env;
-    if (blockIdx.x == 0 && threadIdx.x == 0) counters[0] = 0;   // reset list consumed by k_reset earlier on this stream
+    const int count = mode == 2 ? *list_count : N;
     frame_init_tiletex<G>(f, tex);
     for (;;) {
         if (threadIdx.x == 0) {
-            s_env = atomicAdd(&counters[1], 1);
+            int t = atomicAdd(ticket, 1);
+            if (mode == 1) while (t < count && pending[t]) t = atomicAdd(ticket, 1);
+            s_env = t < count ? (mode == 2 ? list[t] : t) : -1;
             f.npre = 0; f.npost = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1;
         }
         __syncthreads();
         const int env = s_env;
-        if (env >= N) break;
+        if (env < 0) break;
         render_body<G>(s, c, env, f, tex, atlas, obs, false);
     }
     if (threadIdx.x == 0) frame_store_wait();
@@ -143,7 +159,12 @@ struct EngineBase {
     int32_t* actions = nullptr;
     int32_t* seeds_dev = nullptr;
     int* reset_list = nullptr;
-    int* reset_count = nullptr;
+    int* reset_count = nullptr;      // device counters int[4], see k_step
+    uint8_t* pending = nullptr;      // env is in this step's reset list
+    int parity = 0;
+    bool overlap_reset = false;      // k_reset on a second stream, concurrent with the render of the other envs
+    cudaStream_t reset_stream = nullptr;
+    cudaEvent_t ev_stepped = nullptr, ev_reset_done = nullptr;
     TexInfo* texinfo = nullptr;
     uint32_t* atlas = nullptr;
     int32_t* actions_pinned = nullptr;
@@ -166,25 +187,38 @@ struct EngineBase {
     int64_t prof_steps = 0;
     double prof_ms[3] = { 0, 0, 0 };
 
-    int prof_mark() {
+    // per-step timing marks: 4 on the main stream (k_step | k_reset | rest) + 2 around the main render when it runs
+    // on the second stream (overlap_reset)
+    std::vector<cudaEvent_t> prof_side;
+    int prof_mark() { return prof_mark_to(stream, prof_events); }
+    int prof_mark_on(cudaStream_t on) { return prof_mark_to(on, prof_side); }
+    int prof_mark_to(cudaStream_t on, std::vector<cudaEvent_t>& v) {
         cudaEvent_t ev;
         if (cudaEventCreate(&ev) != cudaSuccess) return 1;
-        cudaEventRecord(ev, stream);
-        prof_events.push_back(ev);
+        cudaEventRecord(ev, on);
+        v.push_back(ev);
         return 0;
     }
     int prof_collect() {
         cudaStreamSynchronize(stream);
+        if (reset_stream) cudaStreamSynchronize(reset_stream);
         for (size_t i = 0; i + 3 < prof_events.size(); i += 4) {
             for (int k = 0; k < 3; k++) {
                 float ms = 0.0f;
                 cudaEventElapsedTime(&ms, prof_events[i + k], prof_events[i + k + 1]);
+                if (overlap_reset && k == 2) continue;   // exposed wait + tail render: not a kernel time
                 prof_ms[k] += ms;
             }
             prof_steps++;
         }
+        for (size_t i = 0; i + 1 < prof_side.size(); i += 2) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, prof_side[i], prof_side[i + 1]);
+            prof_ms[2] += ms;
+        }
         for (auto ev : prof_events) cudaEventDestroy(ev);
-        prof_events.clear();
+        for (auto ev : prof_side) cudaEventDestroy(ev);
+        prof_events.clear(); prof_side.clear();
         return 0;
     }
 
@@ -194,7 +228,8 @@ struct EngineBase {
         if (pipelined) { cudaStreamSynchronize(copy_stream); obs = obs_b[0]; reward = reward_b[0]; terminated = term_b[0]; truncated = trunc_b[0]; }
         cudaFree(state_mem); cudaFree(common_mem); cudaFree(obs); cudaFree(reward); cudaFree(terminated);
         cudaFree(truncated); cudaFree(actions); cudaFree(seeds_dev); cudaFree(reset_list); cudaFree(reset_count);
-        cudaFree(texinfo); cudaFree(atlas); cudaFree(sort_table);
+        cudaFree(texinfo); cudaFree(atlas); cudaFree(sort_table); cudaFree(pending);
+        if (reset_stream) { cudaStreamSynchronize(reset_stream); cudaStreamDestroy(reset_stream); cudaEventDestroy(ev_stepped); cudaEventDestroy(ev_reset_done); }
         if (actions_pinned) cudaFreeHost(actions_pinned);
         if (pipelined) {
             // slot 0 aliases the primary buffers (freed above)
@@ -242,8 +277,17 @@ struct Engine : EngineBase {
         PG2_CUDA(cudaMalloc(&actions, sizeof(int32_t) * N));
         PG2_CUDA(cudaMalloc(&seeds_dev, sizeof(int32_t) * N));
         PG2_CUDA(cudaMalloc(&reset_list, sizeof(int) * N));
-        PG2_CUDA(cudaMalloc(&reset_count, 2 * sizeof(int)));   // [0] reset-list length, [1] k_render frame ticket
-        PG2_CUDA(cudaMemsetAsync(reset_count, 0, 2 * sizeof(int), stream));
+        PG2_CUDA(cudaMalloc(&reset_count, 4 * sizeof(int)));
+        PG2_CUDA(cudaMemsetAsync(reset_count, 0, 4 * sizeof(int), stream));
+        PG2_CUDA(cudaMalloc(&pending, N));
+        PG2_CUDA(cudaMemsetAsync(pending, 0, N, stream));
+        overlap_reset = G::SLOW_RESET && auto_reset;
+        if (const char* o = getenv("PG2_OVERLAP_RESET")) overlap_reset = atoi(o) != 0 && auto_reset;
+        if (overlap_reset) {
+            PG2_CUDA(cudaStreamCreateWithFlags(&reset_stream, cudaStreamNonBlocking));
+            PG2_CUDA(cudaEventCreateWithFlags(&ev_stepped, cudaEventDisableTiming));
+            PG2_CUDA(cudaEventCreateWithFlags(&ev_reset_done, cudaEventDisableTiming));
+        }
         PG2_CUDA(cudaMallocHost(&actions_pinned, sizeof(int32_t) * N));
         // texture atlas: decode the game's textures from the packed blob, upload once
         int ntex = 0;
@@ -282,14 +326,14 @@ struct Engine : EngineBase {
         return ctas < num_sms * 4 ? (ctas < 1 ? 1 : ctas) : num_sms * 4;
     }
     void launch_reset_all() {
-        k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, nullptr, reset_count, N);
+        k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, nullptr, nullptr, N);
         launches++;
     }
-    void launch_render() {
+    void launch_render(int mode, int* ticket, cudaStream_t on) {
         int per_sm = 8;
         if (const char* o = getenv("PG2_RENDER_CTAS_PER_SM")) per_sm = atoi(o) > 0 ? atoi(o) : per_sm;
         int grid = N < num_sms * per_sm ? N : num_sms * per_sm;
-        k_render<G><<<grid, RENDER_THREADS, 0, stream>>>(st, common, texinfo, atlas, obs, reset_count, N);
+        k_render<G><<<grid, RENDER_THREADS, 0, on>>>(st, common, texinfo, atlas, obs, ticket, mode, reset_list, reset_count + parity, pending, N);
         launches++;
     }
 
@@ -302,7 +346,8 @@ struct Engine : EngineBase {
             launches++;
         }
         launch_reset_all();
-        launch_render();
+        PG2_CUDA(cudaMemsetAsync(reset_count + 2, 0, 2 * sizeof(int), stream));
+        launch_render(0, reset_count + 2, stream);
         PG2_CUDA(cudaMemsetAsync(reward, 0, sizeof(float) * N, stream));
         PG2_CUDA(cudaMemsetAsync(terminated, 0, N, stream));
         PG2_CUDA(cudaMemsetAsync(truncated, 0, N, stream));
@@ -310,26 +355,40 @@ struct Engine : EngineBase {
         return 0;
     }
 
+    // One step = k_step -> k_reset (finished envs) -> k_render. With overlap_reset the level generation of the few
+    // finished envs runs on a second stream WHILE the main stream renders all other envs; a short tail render
+    // of the reset envs follows. Timing marks: [0] k_step, [1] exposed reset (+ tail render), [2] (main) render.
     int step_device(const int32_t* actions_dev) override {
-        if (profiling) {
-            if (prof_events.size() >= 4096) prof_collect();
-            prof_mark();
-            k_step<G><<<step_grid(), 128, 0, stream>>>(st, common, actions_dev, reward, terminated, truncated, reset_list,
-                                                         reset_count, N, max_episode_steps, auto_reset, step_epw);
-            prof_mark();
-            k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count, N);
-            prof_mark();
-            launches += 2;
-            launch_render();
-            prof_mark();
-            PG2_CUDA(cudaGetLastError());
-            return 0;
+        parity ^= 1;
+        const bool prof = profiling;
+        if (prof && prof_events.size() >= 4096) prof_collect();
+        if (prof) prof_mark();
+        k_step<G><<<step_grid(), 128, 0, stream>>>(st, common, actions_dev, reward, terminated, truncated, reset_list, pending,
+                                                     reset_count, parity, N, max_episode_steps, auto_reset, step_epw);
+        launches++;
+        if (prof) prof_mark();
+        if (overlap_reset) {
+            // k_reset stays on the main stream (first in line after k_step, so its few long-running CTAs get their
+            // shared memory before the render fills the SMs); the render of all OTHER envs runs on the second stream
+            PG2_CUDA(cudaEventRecord(ev_stepped, stream));
+            PG2_CUDA(cudaStreamWaitEvent(reset_stream, ev_stepped, 0));
+            k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count + parity, N);
+            if (prof) prof_mark();
+            if (prof) prof_mark_on(reset_stream);
+            launch_render(1, reset_count + 2, reset_stream);
+            if (prof) prof_mark_on(reset_stream);
+            PG2_CUDA(cudaEventRecord(ev_reset_done, reset_stream));   // = main render done
+            PG2_CUDA(cudaStreamWaitEvent(stream, ev_reset_done, 0));
+            launch_render(2, reset_count + 3, stream);
+            launches++;
+            if (prof) prof_mark();
+        } else {
+            k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count + parity, N);
+            launches++;
+            if (prof) prof_mark();
+            launch_render(0, reset_count + 2, stream);
+            if (prof) prof_mark();
         }
-        k_step<G><<<step_grid(), 128, 0, stream>>>(st, common, actions_dev, reward, terminated, truncated, reset_list,
-                                                     reset_count, N, max_episode_steps, auto_reset, step_epw);
-        k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count, N);
-        launches += 2;
-        launch_render();
         PG2_CUDA(cudaGetLastError());
         return 0;
     }

@@ -49,6 +49,7 @@ struct BossFight {
     static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
     static constexpr int MAX_POST = 112;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = true;     // some blits are rotated
+    static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int TILE_CLASSES = 1;
     static constexpr int MB = 64, NEX = 8, AB = 32, MAX_BAR = 4;
     enum Tex {

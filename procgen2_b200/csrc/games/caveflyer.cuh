@@ -45,6 +45,7 @@ struct CaveFlyer {
     static constexpr bool LANE_AWARE = false;   // step() supports warp-per-env (ctx) but measures faster thread-per-env (r01j)
     static constexpr int MAX_POST = 112;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = true;     // some blits are rotated
+    static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int TILE_CLASSES = 1;
     enum Obj { O_NONE = 0, O_OBSTACLE, O_TARGET, O_ENEMY };
     enum Tex { T_WALL = 0, T_GOAL, T_TARGET, T_OBSTACLE, T_ENEMY, T_BULLET, T_SHIP, T_PARTICLE, T_EXPL0, T_BG0 = 13, NUM_BG = 13, NUM_TEX = 26 };

@@ -45,6 +45,7 @@ struct Chaser {
     static constexpr bool LANE_AWARE = true;    // step(): the point loop is strided over ctx's lanes, the rest is uniform
     static constexpr int MAX_POST = 80;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
+    static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int TILE_CLASSES = 1;
     static constexpr int TILE_STRIDE = 128, FREE_STRIDE = 64;
     enum Kind { K_NONE = 0, K_ORB, K_MOB, K_POINT };

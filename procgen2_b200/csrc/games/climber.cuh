@@ -43,6 +43,7 @@ struct Climber {
     static constexpr bool LANE_AWARE = true;    // step(): per-entity loops are strided over ctx's lanes
     static constexpr int MAX_POST = 48;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
+    static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int TILE_CLASSES = 2;   // wall_mid textures are 64x64, one wall_top texture is 64x53
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID };
     enum Ent { E_NONE = 0, E_MOB, E_POINT };

@@ -43,6 +43,7 @@ struct Jumper {
     static constexpr bool LANE_AWARE = false;   // step() supports warp-per-env (ctx) but measures faster thread-per-env (r01j)
     static constexpr int MAX_POST = 80;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = true;     // some blits are rotated
+    static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int TILE_CLASSES = 2;
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID, SPIKE };
     enum Tex {

@@ -34,6 +34,7 @@ struct Maze {
     static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
     static constexpr int MAX_POST = 4;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
+    static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int TILE_CLASSES = 1;
     static constexpr int TILE_STRIDE = 640;
     enum Tex { T_WALL = 0, T_CHEESE = 1, T_MOUSE = 2, T_BG0 = 3, NUM_BG = 9, NUM_TEX = 12 };
