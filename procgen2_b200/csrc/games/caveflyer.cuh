@@ -251,10 +251,7 @@ struct CaveFlyer {
         USet<MAX_OBJ + 8, 128>* us = w.alloc<USet<MAX_OBJ + 8, 128>>(1);
         bool fault = false;
 
-        for (int i = 0; i < W * H; i++) {
-            float r = w.rng.uniform_real(0.0f, 1.0f);
-            if (lane == 0) rg.grid[i] = r < 0.5f ? 1 : 0;
-        }
+        w.rng.bernoulli_fill(rg.grid, W * H, [](int) { return 0.5f; });   // grid[i] = dist01(rng) < 0.5f ? 1 : 0
         rg.update(w);
         rg.update(w);
         int nroom = rg.find_best_room(w);
@@ -273,13 +270,7 @@ struct CaveFlyer {
         __syncwarp();
         for (int i = lane; i < plen; i += WARP_LANES) tiles[rg.path[i]] = 2;
         __syncwarp();
-        int nfree = 0;
-        if (lane == 0) {
-            for (int i = 0; i < W * H; i++) if (tiles[i] == 0) free_cells[nfree++] = (uint16_t)i;
-            rg.res[2] = nfree;
-        }
-        __syncwarp();
-        nfree = rg.res[2];
+        const int nfree = warp_compact(w, W * H, [&](int i) { return tiles[i] == 0; }, free_cells);
 
         const int chunk = nfree / 80;
         int num_objects = 3 * chunk;

@@ -237,12 +237,10 @@ struct Jumper {
         USet<MAX_SPIKES + 8, 128>* us = w.alloc<USet<MAX_SPIKES + 8, 128>>(1);
         Map map{ tiles };
 
-        for (int i = 0; i < W * H; i++) {
+        w.rng.bernoulli_fill(rg.grid, W * H, [&](int i) {   // wall with probability 0.8 under a maze wall, else 0.2
             int obj = mg.grid[((i % H) / maze_scale + 1) + mg.ah * ((i / H) / maze_scale + 1)];
-            float prob = obj == 1 ? 0.8f : 0.2f;
-            float r = w.rng.uniform_real(0.0f, 1.0f);
-            if (lane == 0) rg.grid[i] = r < prob ? 1 : 0;
-        }
+            return obj == 1 ? 0.8f : 0.2f;
+        });
         rg.update(w);
         rg.update(w);
         for (int i = lane; i < W; i += WARP_LANES) {
@@ -257,17 +255,7 @@ struct Jumper {
         __syncwarp();
         const int goal_cell = rg.order[w.rng.uniform_int(0, nroom - 1)];
 
-        int ncand = 0;
-        if (lane == 0) {
-            for (int x = 0; x < W; x++)
-                for (int y = 0; y < H; y++) {
-                    int i = y + H * x;
-                    if (map.space_on_ground(x, y) && i != goal_cell) cand[ncand++] = (uint16_t)i;
-                }
-            rg.res[2] = ncand;
-        }
-        __syncwarp();
-        ncand = rg.res[2];
+        int ncand = warp_compact(w, W * H, [&](int i) { return map.space_on_ground(i / H, i % H) && i != goal_cell; }, cand);
         if (ncand <= 0) { fault = true; ncand = 1; if (lane == 0) cand[0] = rg.order[0]; __syncwarp(); }   // Q20
         const int agent_cell = cand[w.rng.uniform_int(0, ncand - 1)];
         __syncwarp();
@@ -280,14 +268,22 @@ struct Jumper {
         const float goal_x = __fadd_rn((float)(goal_cell / H), 0.5f), goal_y = __fadd_rn((float)(H - 1 - goal_cell % H), 0.5f);
 
         // spikes, then wall thinning: scans whose writes feed later tests, RNG draws inside -> uniform serial code
-        for (int x = 0; x < W; x++)
-            for (int y = 0; y < H; y++)
+        {   // a spike only turns EMPTY cells non-empty, which can only falsify later tests: the cells passing the test on
+            // the spike-free map (lane-parallel scan, x-major order kept) are a superset; re-check those in order
+            uint16_t* sc = rg.queue;
+            int nsc = warp_compact(w, W * H, [&](int i) {
+                int x = i / H, y = i % H;
+                return map.space_on_ground(x, y) && map.space_on_ground(x - 1, y) && map.space_on_ground(x + 1, y); }, sc);
+            for (int k = 0; k < nsc; k++) {
+                int x = sc[k] / H, y = sc[k] % H;
                 if (map.space_on_ground(x, y) && map.space_on_ground(x - 1, y) && map.space_on_ground(x + 1, y)) {
                     bool put = w.rng.uniform_real(0.0f, 1.0f) < 0.2f;
                     __syncwarp();
                     if (put) map.set(x, y, SPIKE);
                     __syncwarp();
                 }
+            }
+        }
         for (int x = 0; x < W; x++)
             for (int y = 0; y < H; y++) {
                 if (map.left_wall(x, y) && map.left_wall(x, y + 1) && map.left_wall(x, y + 2)) {
@@ -305,22 +301,12 @@ struct Jumper {
             }
         const float agent_x = __fadd_rn((float)(agent_cell / H), 0.5f), agent_y = (float)(H - 1 - (agent_cell % H));
 
-        int nspikes = 0;
-        if (lane == 0) {
-            rg.res[3] = 0;
-            for (int i = 0; i < W * H; i++)
-                if (tiles[i] == SPIKE) {
-                    tiles[i] = EMPTY;
-                    if (i != agent_cell && i != goal_cell) {
-                        if (nspikes < MAX_SPIKES) spikes[nspikes++] = (uint16_t)i;
-                        else rg.res[3] = 1;
-                    }
-                }
-            rg.res[2] = nspikes;
-        }
+        int nspikes = warp_compact(w, W * H, [&](int i) { return tiles[i] == SPIKE && i != agent_cell && i != goal_cell; }, rg.queue);
+        if (nspikes > MAX_SPIKES) { fault = true; nspikes = MAX_SPIKES; }
+        for (int k = lane; k < nspikes; k += WARP_LANES) spikes[k] = rg.queue[k];
         __syncwarp();
-        nspikes = rg.res[2];
-        if (rg.res[3]) fault = true;
+        for (int i = lane; i < W * H; i += WARP_LANES) if (tiles[i] == SPIKE) tiles[i] = EMPTY;
+        __syncwarp();
         // tops (order-insensitive: a cell turned into wall_top is neither wall_mid nor empty for its neighbours' tests)
         for (int i = lane; i < W * H; i += WARP_LANES) rg.tmp[i] = map.top_wall(i / H, i % H) ? 1 : 0;
         __syncwarp();

@@ -99,6 +99,30 @@ struct WarpMt {
         idx = 0;
     }
 
+    // n consecutive uniform_real_distribution<float>(0,1) draws compared against per-draw thresholds, spread over the
+    // lanes: out[i] = draw_i < thr(i). Identical stream consumption to n calls of canonical() (one word per draw).
+    template <class Thr>
+    PG2_DEV_NOINLINE void bernoulli_fill(uint8_t* out, int n, Thr thr) {
+        int done = 0;
+        while (done < n) {
+            if (idx >= MT_N) twist();
+            int m = min(MT_N - idx, n - done);
+            __syncwarp();
+            for (int j = lane; j < m; j += WARP_LANES) {
+                uint32_t y = mt[idx + j];
+                y ^= (y >> 11);
+                y ^= (y << 7) & 0x9d2c5680u;
+                y ^= (y << 15) & 0xefc60000u;
+                y ^= (y >> 18);
+                float r = __fdiv_rn(__uint2float_rn(y), 4294967296.0f);
+                if (r >= 1.0f) r = 0.99999994f;
+                out[done + j] = r < thr(done + j) ? 1 : 0;
+            }
+            __syncwarp();
+            idx += m; done += m;
+        }
+    }
+
     PG2_DEV uint32_t next() {
         if (idx >= MT_N) twist();
         uint32_t y = mt[idx++];

@@ -18,6 +18,19 @@ namespace pg2 {
 constexpr int ROOM_DIM = 40, ROOM_CELLS = ROOM_DIM * ROOM_DIM;
 using RoomSet = USet<ROOM_CELLS, 2400>;
 
+// Atomically claim a byte flag (0 -> 1); true for the one thread that claimed it.
+PG2_DEV bool claim_cell(uint8_t* p) {
+#ifdef PG2_HOSTSIM
+    if (*p) return false;
+    *p = 1;
+    return true;
+#else
+    uint32_t* word = (uint32_t*)((size_t)p & ~(size_t)3);
+    uint32_t bit = 1u << (8u * (uint32_t)((size_t)p & 3));
+    return (atomicOr(word, bit) & (0xffu << (8u * (uint32_t)((size_t)p & 3)))) == 0u;
+#endif
+}
+
 struct RoomGen {
     int W, H;
     uint8_t* grid;        // [y + H * x]: 1 wall, 0 space
@@ -61,33 +74,44 @@ struct RoomGen {
 
     // Room_Generator::find_best_room -> order[0 .. n) = iteration order of best_room; returns n
     PG2_DEV_NOINLINE int find_best_room(WarpCtx& w) {
+        // pass 1 (lane-parallel, order-insensitive): size of every room in scan order. A one-cell room yields an
+        // EMPTY set (its start cell is never re-discovered); the first room always replaces the initial
+        // best_room_size of -1.
+        const int cells = W * H;
         __syncwarp();
-        if (w.lane == 0) {
-            const int cells = W * H;
-            for (int i = 0; i < cells; i++) mark[i] = 0;
-            // pass 1: size of every room in scan order; a one-cell room yields an EMPTY set (its start cell is
-            // never re-discovered), the first room always replaces the initial best_room_size of -1
-            int best_start = -1, best_size = -1;
-            for (int i = 0; i < cells; i++) {
-                if (grid[i] != 0 || mark[i]) continue;
-                int head = 0, tail = 0;
-                queue[tail++] = (uint16_t)i; mark[i] = 1;
-                while (head < tail) {
-                    int cur = queue[head++], x = cur / H, y = cur % H;
+        for (int i = w.lane; i < cells; i += WARP_LANES) mark[i] = 0;
+        __syncwarp();
+        int best_start = -1, best_size = -1;
+        for (int i = 0; i < cells; i++) {
+            if (grid[i] != 0 || mark[i]) continue;          // uniform: every lane reads the same cell
+            __syncwarp();
+            if (w.lane == 0) { mark[i] = 1; queue[0] = (uint16_t)i; res[2] = 1; }
+            __syncwarp();
+            int head = 0, tail = 1;
+            while (head < tail) {                            // one BFS level chunk per iteration
+                for (int q = head + w.lane; q < tail; q += WARP_LANES) {
+                    int cur = queue[q], x = cur / H, y = cur % H;
                     const int nx[4] = { x - 1, x, x, x + 1 }, ny[4] = { y, y - 1, y + 1, y };
                     for (int k = 0; k < 4; k++) {
                         if (nx[k] < 0 || ny[k] < 0 || nx[k] >= W || ny[k] >= H) continue;
                         int nxt = ny[k] + H * nx[k];
-                        if (!mark[nxt] && grid[nxt] == 0) { mark[nxt] = 1; queue[tail++] = (uint16_t)nxt; }
+                        if (grid[nxt] == 0 && claim_cell(&mark[nxt])) queue[atomicAdd(&res[2], 1)] = (uint16_t)nxt;
                     }
                 }
-                int size = tail >= 2 ? tail : 0;
-                if (size > best_size) { best_size = size; best_start = i; }
+                __syncwarp();
+                head = tail; tail = res[2];
+                __syncwarp();
             }
-            // pass 2: the winning room again, exactly as build_room inserts it
+            int size = tail >= 2 ? tail : 0;
+            if (size > best_size) { best_size = size; best_start = i; }
+        }
+        __syncwarp();
+        for (int i = w.lane; i < cells; i += WARP_LANES) mark[i] = 0;
+        __syncwarp();
+        if (w.lane == 0) {
+            // pass 2 (ordered): the winning room again, exactly as build_room inserts it
             int n = 0;
             if (best_size > 0) {
-                for (int i = 0; i < cells; i++) mark[i] = 0;
                 set->init(1);
                 int head = 0, tail = 0;
                 queue[tail++] = (uint16_t)best_start;
@@ -97,7 +121,7 @@ struct RoomGen {
                     for (int k = 0; k < 4; k++) {
                         if (nx[k] < 0 || ny[k] < 0 || nx[k] >= W || ny[k] >= H) continue;
                         int nxt = ny[k] + H * nx[k];
-                        if (!mark[nxt] && grid[nxt] == 0) { mark[nxt] = 1; queue[tail++] = (uint16_t)nxt; set->insert(nxt); }
+                        if (!mark[nxt] && grid[nxt] == 0) { mark[nxt] = 1; queue[tail++] = (uint16_t)nxt; set->insert_new(nxt); }
                     }
                 }
                 n = set->order(order);
@@ -111,11 +135,11 @@ struct RoomGen {
     // Room_Generator::find_path -> path[0 .. len) from src to dst; returns len (0: none)
     PG2_DEV_NOINLINE int find_path(WarpCtx& w, int src, int dst) {
         __syncwarp();
+        for (int i = w.lane; i < W * H; i += WARP_LANES) mark[i] = 0;   // `covered` (does not contain src)
+        __syncwarp();
         if (w.lane == 0) {
             int len = 0;
             if (grid[src] == 0) {
-                const int cells = W * H;
-                for (int i = 0; i < cells; i++) mark[i] = 0;   // `covered` (does not contain src)
                 int count = 0, search = 0;
                 queue[count] = (uint16_t)src; parents[count] = 0xffff; count++;
                 while (search < count) {

@@ -20,6 +20,15 @@ struct USet {
     int16_t bucket[MAXB];
     int16_t head;
     int nb, count, next_resize;
+    uint32_t nb_magic;   // ceil(2^32 / nb): mod(key) without a hardware divide (keys and nb < 2^16)
+
+    PG2_DEV void set_nb(int n) { nb = n; nb_magic = (uint32_t)(0xffffffffu / (uint32_t)n) + 1u; }
+    PG2_DEV int mod(int key) const {
+        if (nb == 1) return 0;
+        uint32_t q = (uint32_t)(((uint64_t)(uint32_t)key * nb_magic) >> 32);
+        int r = key - (int)q * nb;
+        return r >= nb ? r - nb : (r < 0 ? r + nb : r);
+    }
 
     PG2_DEV_NOINLINE static int next_bkt(int n, int* next_resize) {
         const unsigned char fast[14] = { 2, 2, 2, 3, 5, 5, 7, 7, 11, 11, 11, 11, 13, 13 };
@@ -41,7 +50,7 @@ struct USet {
 
     // Fresh set: persisted_nb = 1. After clear(): the bucket count seen last.
     PG2_DEV_NOINLINE void init(int persisted_nb) {
-        nb = persisted_nb < 1 ? 1 : persisted_nb;
+        set_nb(persisted_nb < 1 ? 1 : persisted_nb);
         next_resize = nb == 1 ? 0 : nb;
         count = 0;
         head = END;
@@ -51,14 +60,22 @@ struct USet {
     PG2_DEV int16_t next_of(int16_t node) const { return node == BEFORE ? head : next[node]; }
     PG2_DEV void set_next(int16_t node, int16_t v) { if (node == BEFORE) head = v; else next[node] = v; }
 
+    PG2_DEV static int mod_by(int key, int n, uint32_t magic) {
+        if (n == 1) return 0;
+        uint32_t q = (uint32_t)(((uint64_t)(uint32_t)key * magic) >> 32);
+        int r = key - (int)q * n;
+        return r >= n ? r - n : (r < 0 ? r + n : r);
+    }
+
     PG2_DEV_NOINLINE void rehash(int newnb) {
+        const uint32_t newmagic = (uint32_t)(0xffffffffu / (uint32_t)newnb) + 1u;
         for (int i = 0; i < newnb && i < MAXB; i++) bucket[i] = NONE;
         int16_t p = head;
         head = END;
         int bbegin_bkt = 0;
         while (p != END) {
             int16_t nxt = next[p];
-            int bkt = p % newnb;
+            int bkt = mod_by(p, newnb, newmagic);
             if (bucket[bkt] == NONE) {
                 next[p] = head;
                 head = p;
@@ -72,19 +89,24 @@ struct USet {
             }
             p = nxt;
         }
-        nb = newnb;
+        set_nb(newnb);
     }
 
     PG2_DEV_NOINLINE bool contains(int key) const {
-        int16_t prev = bucket[key % nb];
+        int16_t prev = bucket[mod(key)];
         if (prev == NONE) return false;
-        for (int16_t p = next_of(prev); p != END && (p % nb) == (key % nb); p = next[p])
+        for (int16_t p = next_of(prev); p != END && (mod(p)) == (mod(key)); p = next[p])
             if (p == key) return true;
         return false;
     }
 
     PG2_DEV_NOINLINE void insert(int key) {
         if (count > 0 && contains(key)) return;
+        insert_new(key);
+    }
+
+    // insert a key the caller knows to be absent
+    PG2_DEV_NOINLINE void insert_new(int key) {
         if (count + 1 > next_resize) {
             int min_bkts = (count + 1 > (next_resize ? 0 : 11)) ? count + 1 : (next_resize ? 0 : 11);   // load factor 1.0
             if (min_bkts >= nb) {
@@ -94,7 +116,7 @@ struct USet {
                 next_resize = nb;
             }
         }
-        int bkt = key % nb;
+        int bkt = mod(key);
         if (bucket[bkt] != NONE) {
             int16_t prev = bucket[bkt];
             next[key] = next_of(prev);
@@ -102,7 +124,7 @@ struct USet {
         } else {
             next[key] = head;
             head = (int16_t)key;
-            if (next[key] != END) bucket[next[key] % nb] = (int16_t)key;
+            if (next[key] != END) bucket[mod(next[key])] = (int16_t)key;
             bucket[bkt] = BEFORE;
         }
         count++;
@@ -110,12 +132,12 @@ struct USet {
 
     PG2_DEV_NOINLINE void erase(int key) {
         if (count == 0) return;
-        int bkt = key % nb;
+        int bkt = mod(key);
         int16_t prev = bucket[bkt];
         if (prev == NONE) return;
         int16_t p = next_of(prev);
         while (p != END && p != key) {
-            if ((p % nb) != bkt) return;
+            if ((mod(p)) != bkt) return;
             prev = p;
             p = next[p];
         }
@@ -123,13 +145,13 @@ struct USet {
         int16_t nxt = next[p];
         if (prev == bucket[bkt]) {
             // _M_remove_bucket_begin
-            int next_bkt_i = nxt != END ? nxt % nb : 0;
+            int next_bkt_i = nxt != END ? mod(nxt) : 0;
             if (nxt == END || next_bkt_i != bkt) {
                 if (nxt != END) bucket[next_bkt_i] = bucket[bkt];
                 bucket[bkt] = NONE;
             }
         } else if (nxt != END) {
-            int next_bkt_i = nxt % nb;
+            int next_bkt_i = mod(nxt);
             if (next_bkt_i != bkt) bucket[next_bkt_i] = prev;
         }
         set_next(prev, nxt);

@@ -32,4 +32,20 @@ struct WarpCtx {
     }
 };
 
+// Ordered, lane-parallel stream compaction: out[0 .. n) = ascending indices i in [0, count) with pred(i). Returns n.
+template <class Pred, class T>
+PG2_DEV int warp_compact(WarpCtx& w, int count, Pred pred, T* out) {
+    int n = 0;
+    __syncwarp();
+    for (int base = 0; base < count; base += WARP_LANES) {
+        int i = base + w.lane;
+        bool p = i < count && pred(i);
+        uint32_t m = __ballot_sync(0xffffffffu, p);
+        if (p) out[n + __popc(m & ((1u << w.lane) - 1u))] = (T)i;
+        n += __popc(m);
+    }
+    __syncwarp();
+    return n;
+}
+
 }  // namespace pg2
