@@ -177,7 +177,8 @@ def workload_config(a, world):
     return {"workload": "BASELINE.json configs[1]: %s, %d envs per GPU, 64x64x3 uint8 obs, uniform-random actions, "
                         "auto-reset with per-episode level regeneration" % (a.game, a.envs_per_gpu),
             "game": a.game, "envs_per_gpu": a.envs_per_gpu, "global_envs": a.envs_per_gpu * world, "parallelism": "env-sharded x%d, no collective" % world,
-            "l2": "flushed between timed steps (256 MiB memset outside the event pairs)", "base_seed": BASE_SEED}
+            "l2": "flushed between timed steps (256 MiB memset outside the event pairs)", "base_seed": BASE_SEED,
+            "max_episode_steps": a.max_episode_steps}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -190,6 +191,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--game", default="coinrun")
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
+    ap.add_argument("--max-episode-steps", type=int, default=0,
+                    help="truncate episodes (engine extension; BASELINE configs[4] stresses level generation with short episodes)")
     ap.add_argument("--ref-inner", type=int, default=50, help="env steps per env per timed sample of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -218,7 +221,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     N = a.envs_per_gpu
-    env = BatchedEnv(a.game, N, seed=BASE_SEED, device=local_rank, first_env=rank * N)
+    env = BatchedEnv(a.game, N, seed=BASE_SEED, device=local_rank, first_env=rank * N, max_episode_steps=a.max_episode_steps)
     env.reset()
     env.sync()
     total_steps = a.warmup + a.steps

@@ -15,6 +15,12 @@ constexpr int WARP_LANES = 32;
 __device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 __device__ __forceinline__ int warp_bcast(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+// atomicAdd on a counter known to live in shared memory (a generic-address atomic costs an address-space dispatch)
+__device__ __forceinline__ int smem_atomic_inc(int* p) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return old;
+}
 __device__ __forceinline__ float warp_bcast(float v) { return __shfl_sync(0xffffffffu, v, 0); }
 }
 #else
@@ -54,6 +60,7 @@ inline int warp_bcast(int v) { return v; }
 inline float warp_bcast(float v) { return v; }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
+inline int smem_atomic_inc(int* p) { return (*p)++; }
 using std::max;
 using std::min;
 }

@@ -410,7 +410,7 @@ PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas) 
     for (;;) {
       // blocks are handed out dynamically: a warp that drew cheap blocks (no sprites) simply takes more of them
       int block = 0;
-      if (lane == 0) block = atomicAdd(&f.next_block, 1);
+      if (lane == 0) block = smem_atomic_inc(&f.next_block);
       block = warp_bcast(block);
       if (block >= 128) break;
       for (int l = lane; l < 32; l += WARP_LANES) {
