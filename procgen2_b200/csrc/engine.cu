@@ -118,18 +118,19 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render(typename G::State s, 
     const int count = mode == 2 ? *list_count : N;
     frame_init_tiletex<G>(f, tex);
     for (;;) {
+        __syncthreads();   // every warp is done with the previous frame (bands are stored per warp, without a CTA barrier)
         if (threadIdx.x == 0) {
             int t = atomicAdd(ticket, 1);
             if (mode == 1) while (t < count && pending[t]) t = atomicAdd(ticket, 1);
             s_env = t < count ? (mode == 2 ? list[t] : t) : -1;
-            f.npre = 0; f.npost = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1;
         }
+        frame_begin(f);
         __syncthreads();
         const int env = s_env;
         if (env < 0) break;
         render_body<G>(s, c, env, f, tex, atlas, obs, false);
     }
-    if (threadIdx.x == 0) frame_store_wait();
+    if ((threadIdx.x & 31) == 0) frame_store_wait();   // every warp issued bulk stores of its own
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -375,18 +375,9 @@ struct CaveFlyer {
             for (int k = 0; k < nobj + 1; k++) nlive += sprite_alive(s.sprite_order[k * N + env]);
         const int num_bullets = s.num_bullets[env], next_bullet = s.next_bullet[env];
         const int o_spr = NPART, o_bul = o_spr + nlive, o_ship = o_bul + num_bullets;
-        // tile layer first, on the CTA's LAST threads: it overlaps the blit construction of the first warps below
-        const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_WALL].w);
-        for (int t = (int)blockDim.x - 1 - tid; t < ncol + nrow; t += blockDim.x) {
-            if (t < ncol) f.col[0][t] = make_axis(__fmul_rn((float)(lx + t), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tex[T_WALL].w, tscale, false, false);
-            else f.row[0][t - ncol] = make_axis(__fmul_rn((float)(ly + t - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, tex[T_WALL].h, tscale, false, true);
-        }
         const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
-        for (int t = (int)blockDim.x - 1 - tid; t < ncol * nrow; t += blockDim.x) {
-            int cx = t % ncol, ry = t / ncol;
-            int id = get(tiles, lx + cx, H - 1 - (ly + ry));
-            f.tile_tex[ry * MAX_WIN + cx] = id == 1 ? (uint8_t)T_WALL : NO_TILE;
-        }
+        build_tile_layer(f, cam, tex, 1, lx, ly, ncol, nrow, [](int) { return (int)T_WALL; },
+                         [&](int x, int y) { return get(tiles, x, H - 1 - y) == 1 ? (int)T_WALL : (int)NO_TILE; });
         emit_post_blits(f, o_ship + 1, [&](int k, Blit& b, BlitRot& rot) {
             if (k < o_spr) {   // System_Particles::render
                 int pi = k * N + env;

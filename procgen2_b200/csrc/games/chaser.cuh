@@ -371,18 +371,9 @@ struct Chaser {
         int nlive = 0;
         if (sprites)
             for (int k = 0; k < nents; k++) nlive += s.ent_kind[s.sprite_order[k * N + env] * N + env] != K_NONE;
-        // tile layer first, on the CTA's LAST threads: it overlaps the blit construction of the first warps below
-        const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_WALL].w);
-        for (int t = (int)blockDim.x - 1 - tid; t < ncol + nrow; t += blockDim.x) {
-            if (t < ncol) f.col[0][t] = make_axis(__fmul_rn((float)(lx + t), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tex[T_WALL].w, tscale, false, false);
-            else f.row[0][t - ncol] = make_axis(__fmul_rn((float)(ly + t - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, tex[T_WALL].h, tscale, false, true);
-        }
         const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
-        for (int t = (int)blockDim.x - 1 - tid; t < ncol * nrow; t += blockDim.x) {
-            int cx = t % ncol, ry = t / ncol;
-            int id = get(tiles, lx + cx, H - 1 - (ly + ry));
-            f.tile_tex[ry * MAX_WIN + cx] = id == 1 ? (uint8_t)T_WALL : NO_TILE;
-        }
+        build_tile_layer(f, cam, tex, 1, lx, ly, ncol, nrow, [](int) { return (int)T_WALL; },
+                         [&](int x, int y) { return get(tiles, x, H - 1 - y) == 1 ? (int)T_WALL : (int)NO_TILE; });
         emit_post_blits(f, nlive + 1, [&](int k, Blit& b, BlitRot&) {
             if (k < nlive) {
                 int want = sort_perm(nlive, k), e = 0;

@@ -467,30 +467,17 @@ struct CoinRun {
             f.npre = 1;
         }
         (void)nmobs;
-        // post blits: particles (set order x slot), sprites (std::sort order), agent
-        // tile layer first, on the CTA's LAST threads: it overlaps the blit construction of the first warps below
         // tile layer: every tile texture is 128x128
-        const int tw = tex[T_WALL_MID0].w, th = tex[T_WALL_MID0].h;
-        const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tw);
-        for (int t = (int)blockDim.x - 1 - tid; t < ncol + nrow; t += blockDim.x) {
-            if (t < ncol) f.col[0][t] = make_axis(__fmul_rn((float)(lx + t), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tw, tscale, false, false);
-            else f.row[0][t - ncol] = make_axis(__fmul_rn((float)(ly + t - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, th, tscale, false, true);
-        }
         const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
         const int theme = s.map_theme[env];
-        for (int t = (int)blockDim.x - 1 - tid; t < ncol * nrow; t += blockDim.x) {
-            int cx = t % ncol, ry = t / ncol;
-            int x = lx + cx, y = H - 1 - (ly + ry);
-            int raw = (x < 0 || y < 0 || x >= W || y >= H) ? WALL_MID : tiles[y + x * H];
-            int id = raw & 15;
-            uint8_t tt = NO_TILE;
-            if (id == WALL_MID) tt = (uint8_t)(T_WALL_MID0 + theme);
-            else if (id == WALL_TOP) tt = (uint8_t)(T_WALL_TOP0 + theme);
-            else if (id == LAVA_MID) tt = T_LAVA_MID;
-            else if (id == LAVA_TOP) tt = T_LAVA_TOP;
-            else if (id == CRATE) tt = (uint8_t)(T_CRATE0 + (raw >> 4));
-            f.tile_tex[ry * MAX_WIN + cx] = tt;
-        }
+        build_tile_layer(f, cam, tex, 1, lx, ly, ncol, nrow, [](int) { return (int)T_WALL_MID0; }, [&](int x, int yr) {
+            const int y = H - 1 - yr;
+            const int raw = (x < 0 || y < 0 || x >= W || y >= H) ? WALL_MID : tiles[y + x * H];
+            const int id = raw & 15;
+            return id == WALL_MID ? T_WALL_MID0 + theme : id == WALL_TOP ? T_WALL_TOP0 + theme : id == LAVA_MID ? (int)T_LAVA_MID
+                 : id == LAVA_TOP ? (int)T_LAVA_TOP : id == CRATE ? T_CRATE0 + (raw >> 4) : (int)NO_TILE;
+        });
+        // post blits: particles (set order x slot), sprites (std::sort order), agent
         emit_post_blits(f, npart_slots + nsprite + 1, [&](int k, Blit& b, BlitRot&) {
             if (k < npart_slots) {
                 int e = s.mob_order[(k / NPART) * N + env], i = k % NPART;

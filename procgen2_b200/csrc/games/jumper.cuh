@@ -369,23 +369,12 @@ struct Jumper {
             f.npre = 1;
         }
         const int o_spr = NPART, o_agent = o_spr + nspr, o_hud = o_agent + 1;
-        // tile layer first, on the CTA's LAST threads: it overlaps the blit construction of the first warps below
-        for (int t = (int)blockDim.x - 1 - tid; t < 2 * (ncol + nrow); t += blockDim.x) {
-            int cls = t / (ncol + nrow), u = t % (ncol + nrow);
-            int ti = (cls ? T_WALL_TOP0 : T_WALL_MID0) + theme;
-            float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[ti].w);
-            if (u < ncol) f.col[cls][u] = make_axis(__fmul_rn((float)(lx + u), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tex[ti].w, tscale, false, false);
-            else f.row[cls][u - ncol] = make_axis(__fmul_rn((float)(ly + u - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, tex[ti].h, tscale, false, true);
-        }
+        // tile layer: class 0 = wall_mid texture of the theme, class 1 = wall_top texture
         const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
-        for (int t = (int)blockDim.x - 1 - tid; t < ncol * nrow; t += blockDim.x) {
-            int cx = t % ncol, ry = t / ncol;
-            int id = get(tiles, lx + cx, H - 1 - (ly + ry));
-            uint8_t tt = NO_TILE;
-            if (id == WALL_MID) tt = (uint8_t)(T_WALL_MID0 + theme);
-            else if (id == WALL_TOP) tt = (uint8_t)(T_WALL_TOP0 + theme);
-            f.tile_tex[ry * MAX_WIN + cx] = tt;
-        }
+        build_tile_layer(f, cam, tex, 2, lx, ly, ncol, nrow, [&](int cls) { return (cls ? T_WALL_TOP0 : T_WALL_MID0) + theme; }, [&](int x, int y) {
+            const int id = get(tiles, x, H - 1 - y);
+            return id == WALL_MID ? T_WALL_MID0 + theme : id == WALL_TOP ? T_WALL_TOP0 + theme : (int)NO_TILE;
+        });
         emit_post_blits(f, o_hud + 3, [&](int k, Blit& b, BlitRot& rot) {
             if (k < o_spr) {   // System_Particles::render
                 int pi = k * N + env;

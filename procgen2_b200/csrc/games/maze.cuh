@@ -173,19 +173,10 @@ struct Maze {
             f.npre = 1;
         }
         const int ncheese = c.sprites_valid[env] ? 1 : 0;
-        // tile layer first, on the CTA's LAST threads: it overlaps the blit construction of the first warps below
         // tile layer (tilemap.cpp:111-131)
-        const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_WALL].w);
-        for (int t = (int)blockDim.x - 1 - tid; t < ncol + nrow; t += blockDim.x) {
-            if (t < ncol) f.col[0][t] = make_axis(__fmul_rn((float)(lx + t), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, tex[T_WALL].w, tscale, false, false);
-            else f.row[0][t - ncol] = make_axis(__fmul_rn((float)(ly + t - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, tex[T_WALL].h, tscale, false, true);
-        }
         const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
-        for (int t = (int)blockDim.x - 1 - tid; t < ncol * nrow; t += blockDim.x) {
-            int cx = t % ncol, ry = t / ncol;
-            int id = get(tiles, lx + cx, WORLD - 1 - (ly + ry));
-            f.tile_tex[ry * MAX_WIN + cx] = id ? (uint8_t)T_WALL : NO_TILE;
-        }
+        build_tile_layer(f, cam, tex, 1, lx, ly, ncol, nrow, [](int) { return (int)T_WALL; },
+                         [&](int x, int y) { return get(tiles, x, WORLD - 1 - y) ? (int)T_WALL : (int)NO_TILE; });
         emit_post_blits(f, ncheese + 1, [&](int k, Blit& b, BlitRot&) {
             if (k < ncheese) {   // cheese (tilemap.cpp:95-98, common_systems.cpp:41-63)
                 float gx = __fmul_rn(__fadd_rn(s.goal_x[env], -0.48f), UNIT_TO_PIXELS);

@@ -66,16 +66,15 @@ using FrameOf = FrameT<G::MAX_POST, G::ROTATES>;
 // render_game(true) + RGBA->RGB pack for one env by one CTA (f.tiletex filled by frame_init_tiletex before)
 template <class G>
 PG2_DEV void render_body(const typename G::State& s, const CommonState& c, int env, FrameOf<G>& f, const TexInfo* __restrict__ tex,
-                         const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs, bool init_and_sync = true) {
-    if (init_and_sync) {
-        if (threadIdx.x == 0) { f.npre = 0; f.npost = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1; }
+                         const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs, bool begin_and_sync = true) {
+    if (begin_and_sync) {
+        frame_begin(f);
         __syncthreads();
     }
     G::build_frame(s, c, env, f, tex);
     __syncthreads();
     frame_finalize<G>(f);
-    frame_rasterise<G>(f, atlas);
-    frame_store(f, obs + (size_t)env * OBS_BYTES);
+    frame_rasterise<G>(f, atlas, obs + (size_t)env * OBS_BYTES);
 }
 
 }  // namespace pg2

@@ -22,6 +22,12 @@ __device__ __forceinline__ int smem_atomic_inc(int* p) {
     return old;
 }
 __device__ __forceinline__ float warp_bcast(float v) { return __shfl_sync(0xffffffffu, v, 0); }
+// Ballot written so that it also works when one thread walks the 32 "virtual lanes" in a loop (host-sim):
+// on the GPU the loop body runs once and the result is the ballot; simulated, bit `vlane` is returned and OR-ed up.
+__device__ __forceinline__ uint32_t lane_ballot(bool p, int /*vlane*/) { return __ballot_sync(0xffffffffu, p); }
+// index of the most significant set bit (0xffffffff for 0)
+__device__ __forceinline__ uint32_t bfind(uint32_t v) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
+__device__ __forceinline__ uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 }
 #else
 #include <math.h>
@@ -61,6 +67,16 @@ inline float warp_bcast(float v) { return v; }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 inline int smem_atomic_inc(int* p) { return (*p)++; }
+inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
+inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+inline uint32_t lane_ballot(bool p, int vlane) { return p ? 1u << vlane : 0u; }
+inline uint32_t bfind(uint32_t v) { return v ? 31u - (uint32_t)__builtin_clz(v) : 0xffffffffu; }
+inline uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+    uint64_t v = (uint64_t)b << 32 | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 255u) << (8 * i);
+    return r;
+}
 using std::max;
 using std::min;
 }

@@ -3,16 +3,23 @@
 // Replaces render_game() (games/coinrun/coinrun.cpp:443-470 and its six siblings) together with
 // the SDL3 software blits it issues (SDL_RenderTextureRotated, renderer.cpp:78/97) and the
 // RGBA->RGB pack loop (coinrun.cpp:377-388). Draw order is the reference's painter's order:
-//   clear(0,0,0) -> "pre" blits (background) -> tile layer (y-major, x-minor; tilemap.cpp:303-320)
+//   clear(0,0,0) -> "pre" blit (background) -> tile layer (y-major, x-minor; tilemap.cpp:303-320)
 //   -> "post" blits (particles, sprites, agent, HUD) in submission order.
-// Instead of executing blits one after another over a framebuffer, every output pixel gathers
-// the layers that cover it, in that order, and blends them in registers; the finished frame is
-// staged in shared memory and leaves the SM as ONE 12 288-byte TMA bulk store
-// (cp.async.bulk.global.shared::cta), i.e. fully coalesced 128-bit+ writes.
+//
+// The frame is drawn in shared memory by row bands (8 bands x 8 rows, handed out to the CTA's warps):
+//   base pass   every thread owns a run of 4 pixels of one row. Background + tile layer are a GATHER: per pixel
+//               the top-most tile candidate is found from per-row tile presence bitmaps (no walk over empty
+//               cells), ONE texel is fetched (four independent fetches in flight per thread), an opaque texel
+//               decides the pixel; a transparent / translucent one sends that pixel to the ordered slow path.
+//               Four finished pixels are packed into three 32-bit words with byte permutes and stored.
+//   post pass   the same warp then draws the post blits that touch its band, blit by blit in submission order
+//               (lanes = an 8x4 patch of the blit's destination rectangle), straight onto the packed RGB rows.
+//   store       the band leaves the SM as one 1 536-byte TMA bulk store (cp.async.bulk.global.shared::cta).
 //
 // The tile layer exploits that render_texture() is separable: a tile's destination columns only
 // depend on its x index and its rows only on its y index, so a frame needs <= 32 column and <= 32
-// row descriptors instead of up to 27x27 blit records.
+// row descriptors instead of up to 27x27 blit records; per screen column / row the (at most two) covering
+// tile columns / rows and their source texel indices are tabulated once per frame (ColDesc / RowDesc).
 #pragma once
 #include "pg2_common.cuh"
 
@@ -20,12 +27,12 @@ namespace pg2 {
 
 constexpr int MAX_WIN = 32;        // tile window extent per axis (maze: 27)
 constexpr int MAX_PRE = 2;
-constexpr int MAX_POST = 192;      // visible post blits (coinrun: 10 particles per visible mob)
 #ifndef PG2_RENDER_THREADS
 #define PG2_RENDER_THREADS 128
 #endif
 constexpr int RENDER_THREADS = PG2_RENDER_THREADS;
 constexpr uint8_t NO_TILE = 0xff;
+constexpr int BAND_ROWS = 8, NUM_BANDS = OBS_H / BAND_ROWS, BAND_BYTES = BAND_ROWS * OBS_W * 3;
 
 // std::sort permutation table. System_Sprite_Render::update sorts (z, entity) pairs
 // by z with std::sort (common_systems.cpp:36-38); every sprite of a game has the same z, so the
@@ -54,38 +61,52 @@ struct alignas(16) FastBlit {
 struct TileTex { uint32_t offset; uint16_t w; uint8_t blend, cls; };   // tile textures: ids < MAX_TILE_TEX
 constexpr int MAX_TILE_TEX = 32;
 
+// Tile layer + background under one screen column: clo = first covering tile column of the window; per texture
+// shape class (textures of one class share width and height) and candidate j (tile column clo + j) a validity bit
+// and the source texel x. vc masks are in "candidate index" form (candidate q = jr * 2 + jc): 0b0101 for jc = 0,
+// 0b1010 for jc = 1, so that (cw & rw) >> (8 + 4 * cls) is the set of candidates whose class-cls axes cover the pixel.
+struct alignas(16) ColDesc {
+    uint32_t cw;       // clo | vc[0] << 8 | vc[1] << 12
+    uint32_t csx;      // sx[cls][j] in byte cls * 2 + j
+    int32_t pre_sx;    // background: source x under this column, -1: not covered
+    uint32_t pad;
+};
+// Same for one screen row, plus the tile presence bitmaps of the two candidate tile rows (bit = tile column).
+struct alignas(16) RowDesc {
+    uint32_t rw;       // rlo | vr[0] << 8 | vr[1] << 12   (0b0011 for jr = 0, 0b1100 for jr = 1)
+    int32_t pre_row;   // background: tex_offset + sy * tex_w under this row, -1: not covered
+    uint32_t syw[2];   // [cls]: (sy * tex_w) of candidate row 0 | candidate row 1 << 16
+    uint32_t rm[2][2]; // [cls][jr]: presence bitmap of class-cls tiles in tile row rlo + jr
+};
+
 // Frame description of ONE environment, in shared memory. MAXP = capacity of the post-blit list (per game),
 // ROT = whether the game ever rotates a blit (bossfight, caveflyer, jumper HUD).
 template <int MAXP, bool ROT>
 struct FrameT {
-    static constexpr int MAX_POST = MAXP, WORDS = (MAXP + 31) / 32, NROT = ROT ? MAXP : 1;
+    static constexpr int MAX_POST = MAXP, NROT = ROT ? MAXP : 1;
     static constexpr bool ROTATES = ROT;
-    Blit pre[MAX_PRE];
-    FastBlit fpre[MAX_PRE];
+    alignas(16) uint8_t rgb[OBS_BYTES];         // the frame, packed RGB rows
+    ColDesc cold[OBS_W];
+    RowDesc rowd[OBS_H];
     FastBlit fpost[MAXP];
+    FastBlit fpre[MAX_PRE];
     BlitRot post_rot[NROT];
+    Blit pre[MAX_PRE];
     int npre, npost;
-    // tile layer: window origin (tile coordinates, y in render space), extents, descriptors per
-    // texture shape class (textures of one class share width and height)
+    // tile layer: window origin (tile coordinates, y in render space), extents, descriptors per texture shape class
     int tx0, ty0, ncol, nrow, nclass;
     Axis col[2][MAX_WIN];
     Axis row[2][MAX_WIN];
-    uint8_t tile_tex[MAX_WIN * MAX_WIN];        // tile texture id per window cell or NO_TILE
-    uint8_t col_lo[OBS_W], col_hi[OBS_W];       // per screen column: range of tile columns covering it
-    uint8_t row_lo[OBS_H], row_hi[OBS_H];       // (lo > hi: none)
-    // for every screen column / row and class: source texel index under the (at most two) covering tiles
-    int16_t col_sx[2][2][OBS_W];                // [class][candidate][X] -> source x, -1: not covered
-    int16_t row_sy[2][2][OBS_H];
-    int32_t pre_sx[MAX_PRE][OBS_W];             // pre blits (backgrounds), resolved per column / row:
-    int32_t pre_row[MAX_PRE][OBS_H];            //   texel index = pre_row[k][Y] + pre_sx[k][X], -1: not covered
+    uint8_t tile_tex[(MAX_WIN + 1) * MAX_WIN];  // tile texture id per window cell or NO_TILE (+1 row: branch-free reads)
+    uint32_t rowmask[2][MAX_WIN + 1];           // [cls][tile row]: bit cx set = a class-cls tile at window column cx
+    int cov_lo[2 * OBS_W], cov_hi[2 * OBS_W];   // [0,64): per screen column, [64,128): per screen row: covering tile range
+    uint8_t bandmask[MAXP];                     // post blit k touches band b <=> bit b
     int wcount[RENDER_THREADS / 32];            // emit_post_blits: visible blits per warp
-    int next_block;                             // frame_rasterise: dynamic hand-out of the 128 pixel blocks to warps
-    int wide;                                   // some column / row is covered by more than two tiles (never observed)
-    // post-blit binning: 8x4-pixel blocks (one warp's pixels) x MAXP blits
-    uint32_t bin[128][WORDS];
-    uint8_t bin_any[128];
+    int next_band;                              // dynamic hand-out of the row bands to warps
+    int wide;                                   // the frame needs the general ordered path for every pixel (never observed)
+    int pre_blend;                              // background texture carries alpha
+    int class_w[2];                             // texture width of the tile shape classes
     TileTex tiletex[MAX_TILE_TEX];              // per CTA (filled once): atlas offset / stride / blend / class
-    alignas(16) uint8_t rgb[OBS_BYTES];         // staged output frame
 };
 
 // Deterministic sin/cos in degrees, mirrored operation by operation from oracle/raster.c
@@ -207,6 +228,18 @@ PG2_DEV FastBlit make_fast(const Blit& b) {
     return fb;
 }
 
+// Bands (8 rows each) a blit can touch; a rotated rect is bounded by centre +- half diagonal.
+PG2_DEV uint32_t blit_bands(const FastBlit& fb) {
+    int y0 = fb.y0, y1 = fb.y0 + fb.h - 1;
+    if (fb.flags & 2u) {
+        int rad = ((int)fb.w + (int)fb.h) / 2 + 2, cy = fb.y0 + fb.h / 2;
+        y0 = cy - rad; y1 = cy + rad;
+    }
+    if (y1 < 0 || y0 >= OBS_H) return 0u;
+    int b0 = max(y0, 0) / BAND_ROWS, b1 = min(y1, OBS_H - 1) / BAND_ROWS;
+    return ((2u << b1) - 1u) & ~((1u << b0) - 1u);
+}
+
 // Ordered, compacting append of post blits by the whole CTA: candidate k (in the reference's
 // submission order) is evaluated by thread k % blockDim; only visible blits are stored, order
 // preserved through a warp ballot + a prefix over the warps' counts. make(k, blit, rot) fills the blit.
@@ -222,6 +255,8 @@ PG2_DEV void emit_post_blits(F& f, int ncand, MakeFn make) {
         b.ax.visible = 0; b.rotated = 0; rot.s = 0.0; rot.c = 1.0;
         if (k < ncand) make(k, b, rot);
         bool vis = k < ncand && b.ax.visible;
+        FastBlit fb;
+        if (vis) { fb = make_fast(b); vis = !(fb.flags & 4u); }
         uint32_t m = __ballot_sync(0xffffffffu, vis);
         if (lane == 0) f.wcount[warp] = __popc(m);
         __syncthreads();
@@ -230,7 +265,8 @@ PG2_DEV void emit_post_blits(F& f, int ncand, MakeFn make) {
         if (vis) {
             int idx = n + before + __popc(m & ((1u << lane) - 1u));
             if (idx < F::MAX_POST) {
-                f.fpost[idx] = make_fast(b);
+                f.fpost[idx] = fb;
+                f.bandmask[idx] = (uint8_t)blit_bands(fb);
                 if (F::ROTATES) f.post_rot[idx] = rot;
             }
         }
@@ -253,81 +289,127 @@ PG2_DEV void tile_window(const Camera& cam, int* lower_x, int* lower_y, int* upp
     *upper_y = f2i(ceilf(__fadd_rn(ay, aw)));
 }
 
+// Start of a frame (every thread; followed by a __syncthreads() before the game's frame builder runs).
+template <class F>
+PG2_DEV void frame_begin(F& f) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { f.npre = 0; f.npost = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1; f.wide = 0; f.next_band = 0; f.pre_blend = 0; }
+    for (int k = tid; k < 2 * OBS_W; k += blockDim.x) { f.cov_lo[k] = 255; f.cov_hi[k] = -1; }
+}
+
+// Tile layer of a frame (System_Tilemap::render, tilemap.cpp:294-320), called by every thread of the CTA from the
+// game's frame builder: the window's column / row axes per texture shape class (class_tex(cls) = a texture of that
+// class), the window's tile texture ids (tile_at(x, y) with x = window column + lx, y = render-space tile row) and the
+// per-row presence bitmaps. Every axis also registers itself in the covering range of the screen columns / rows it
+// touches (cov_lo / cov_hi, initialised by frame_begin).
+template <class F, class ClassTex, class TileAt>
+PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int nclass, int lx, int ly, int ncol, int nrow,
+                              ClassTex class_tex, TileAt tile_at) {
+    const int tid = threadIdx.x, lane = tid % WARP_LANES, warp = tid / WARP_LANES;
+    const int nwarps = ((int)blockDim.x + WARP_LANES - 1) / WARP_LANES;
+    const int per = ncol + nrow;
+    for (int t = tid; t < nclass * per; t += blockDim.x) {
+        const int cls = t >= per ? 1 : 0, u = t - cls * per;
+        const TexInfo ti = tex[class_tex(cls)];
+        const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)ti.w);
+        const bool is_row = u >= ncol;
+        Axis a;
+        if (!is_row) a = make_axis(__fmul_rn((float)(lx + u), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, ti.w, tscale, false, false);
+        else a = make_axis(__fmul_rn((float)(ly + u - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, ti.h, tscale, false, true);
+        const int idx = is_row ? u - ncol : u;
+        if (is_row) f.row[cls][idx] = a; else f.col[cls][idx] = a;
+        if (a.visible && a.d0 > -65536 && a.d0 < 65536 && a.dlen < 65536) {   // register in the covering ranges
+            const int p0 = max(a.d0, 0), p1 = min(a.d0 + a.dlen - 1, OBS_W - 1), o = is_row ? OBS_W : 0;
+            for (int pp = p0; pp <= p1; pp++) { atomicMin(&f.cov_lo[o + pp], idx); atomicMax(&f.cov_hi[o + pp], idx); }
+        }
+    }
+    for (int cls = tid; cls < nclass; cls += blockDim.x) f.class_w[cls] = tex[class_tex(cls)].w;
+    // window cells: one warp per tile row, lanes = tile columns
+    for (int ry = warp; ry <= MAX_WIN; ry += nwarps) {
+        uint32_t m0 = 0u, m1 = 0u;
+        for (int cx = lane; cx < MAX_WIN; cx += WARP_LANES) {
+            uint8_t tt = (ry < nrow && cx < ncol) ? (uint8_t)tile_at(lx + cx, ly + ry) : NO_TILE;
+            f.tile_tex[ry * MAX_WIN + cx] = tt;
+            const bool c1 = tt != NO_TILE && f.tiletex[tt & (MAX_TILE_TEX - 1)].cls != 0;
+            m0 |= lane_ballot(tt != NO_TILE && !c1, cx);
+            m1 |= lane_ballot(c1, cx);
+        }
+        if (lane == 0) { f.rowmask[0][ry] = m0; f.rowmask[1][ry] = m1; }
+    }
+}
+
 // ---- per-pixel evaluation ---------------------------------------------------------------------
 
-// After the game's frame builder filled pre/post blits, the tile window, col/row descriptors and tile_tex
-// (and __syncthreads()'d): per-column / per-row lookup tables of the tile layer, post-blit bins.
+// After the game's frame builder (and a __syncthreads()): ColDesc / RowDesc of every screen column / row.
 template <class G, class F>
 PG2_DEV_NOINLINE void frame_finalize(F& f) {
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 128 * F::WORDS; i += blockDim.x) (&f.bin[0][0])[i] = 0u;
-    for (int i = tid; i < 128; i += blockDim.x) f.bin_any[i] = 0;
-    if (tid == 0) { f.wide = 0; f.next_block = 0; }
-    // covering ranges: k < 64 -> screen column k, 64..127 -> screen row k-64
-    for (int k = tid; k < 128; k += blockDim.x) {
-        bool is_row = k >= 64;
-        int p = k & 63;
-        int n = is_row ? f.nrow : f.ncol;
-        int lo = 255, hi = 0;
-        for (int cls = 0; cls < f.nclass; cls++) {
-            const Axis* ax = is_row ? f.row[cls] : f.col[cls];
-            for (int t = 0; t < n; t++) {
-                Axis a = ax[t];
-                if (a.visible && (unsigned)(p - a.d0) < (unsigned)a.dlen) { lo = min(lo, t); hi = max(hi, t); }
+    const int tid = threadIdx.x, lane = tid % WARP_LANES;
+    const int npre = f.npre, nclass = f.nclass;
+    // the fast path handles ONE un-rotated background with alpha_mod 255
+    const bool pre_ok = npre == 0 || (npre == 1 && !f.pre[0].rotated && f.pre[0].alpha_mod == 255);
+    if (tid == 0) {
+        if (!pre_ok) f.wide = 1;
+        f.pre_blend = npre >= 1 ? f.pre[npre - 1].blend : 0;
+    }
+    for (int k = tid; k < npre; k += blockDim.x) f.fpre[k] = make_fast(f.pre[k]);
+    for (int k = tid; k < 2 * OBS_W; k += blockDim.x) {
+        const bool is_row = k >= OBS_W;
+        const int p = k & (OBS_W - 1);
+        const int lo = f.cov_lo[k], hi = f.cov_hi[k];
+        uint32_t word = 0u, smp[2] = { 0u, 0u };
+        if (lo <= hi) {
+            word = (uint32_t)lo;
+            if (hi - lo > 1) f.wide = 1;
+            for (int cls = 0; cls < nclass; cls++)
+                for (int j = 0; j < 2; j++) {
+                    if (lo + j > hi) continue;
+                    const Axis& a = is_row ? f.row[cls][lo + j] : f.col[cls][lo + j];
+                    if (!a.visible || (unsigned)(p - a.d0) >= (unsigned)a.dlen) continue;
+                    const uint32_t v = (uint32_t)axis_sample(a, p, false);
+                    if (is_row) {
+                        const uint32_t w = (uint32_t)f.class_w[cls];
+                        if (v * w > 0xffffu) f.wide = 1;
+                        smp[cls] |= ((v * w) & 0xffffu) << (16 * j);
+                        word |= (j ? 0xcu : 0x3u) << (8 + 4 * cls);
+                    } else {
+                        if (v > 0xffu) f.wide = 1;
+                        smp[0] |= (v & 0xffu) << (8 * (cls * 2 + j));
+                        word |= (j ? 0xau : 0x5u) << (8 + 4 * cls);
+                    }
+                }
+        }
+        int32_t pv = -1;
+        if (npre >= 1 && pre_ok) {
+            const Blit& b = f.pre[0];
+            const Axis& a = is_row ? b.ay : b.ax;
+            if (b.ax.visible && (unsigned)(p - a.d0) < (unsigned)a.dlen) {
+                int s = axis_sample(a, p, is_row ? false : (b.flip_h != 0));
+                pv = is_row ? (int32_t)(b.tex_offset + (uint32_t)s * b.tex_w) : s;
             }
         }
-        if (is_row) { f.row_lo[p] = (uint8_t)lo; f.row_hi[p] = (uint8_t)hi; }
-        else        { f.col_lo[p] = (uint8_t)lo; f.col_hi[p] = (uint8_t)hi; }
-    }
-    for (int k = tid; k < f.npre; k += blockDim.x) f.fpre[k] = make_fast(f.pre[k]);
-    for (int k = tid; k < f.npre * 128; k += blockDim.x) {
-        const Blit& b = f.pre[k >> 7];
-        int p = k & 63, is_row = (k >> 6) & 1;
-        const Axis& a = is_row ? b.ay : b.ax;
-        int32_t v = -1;
-        if (b.ax.visible && !b.rotated && (unsigned)(p - a.d0) < (unsigned)a.dlen) {
-            int smp = axis_sample(a, p, is_row ? false : (b.flip_h != 0));
-            v = is_row ? (int32_t)(b.tex_offset + (uint32_t)smp * b.tex_w) : smp;
+        if (is_row) {
+            RowDesc rd;
+            rd.rw = word; rd.pre_row = pv; rd.syw[0] = smp[0]; rd.syw[1] = smp[1];
+            const int r0 = lo <= hi ? lo : MAX_WIN;       // row MAX_WIN is always empty
+            const int r1 = lo < hi ? lo + 1 : MAX_WIN;
+            rd.rm[0][0] = f.rowmask[0][r0]; rd.rm[0][1] = f.rowmask[0][r1];
+            rd.rm[1][0] = f.rowmask[1][r0]; rd.rm[1][1] = f.rowmask[1][r1];
+            f.rowd[p] = rd;
+        } else {
+            ColDesc cd;
+            cd.cw = word; cd.csx = smp[0]; cd.pre_sx = pv; cd.pad = 0u;
+            f.cold[p] = cd;
         }
-        if (is_row) f.pre_row[k >> 7][p] = v; else f.pre_sx[k >> 7][p] = v;
     }
-    __syncthreads();
-    // per screen column / row and class: source texel of the (at most two) covering tiles
-    for (int k = tid; k < 128 * 2 * 2; k += blockDim.x) {
-        int p = k & 63, is_row = (k >> 6) & 1, j = (k >> 7) & 1, cls = k >> 8;
-        int lo = is_row ? f.row_lo[p] : f.col_lo[p], hi = is_row ? f.row_hi[p] : f.col_hi[p];
-        int16_t v = -1;
-        if (cls < f.nclass && lo + j <= hi) {
-            const Axis& a = is_row ? f.row[cls][lo + j] : f.col[cls][lo + j];
-            if (a.visible && (unsigned)(p - a.d0) < (unsigned)a.dlen) v = (int16_t)axis_sample(a, p, false);
-        }
-        if (is_row) f.row_sy[cls][j][p] = v; else f.col_sx[cls][j][p] = v;
-        if (j == 0 && cls == 0 && lo <= hi && hi - lo > 1) f.wide = 1;
-    }
-    for (int k = tid; k < f.npost; k += blockDim.x) {
-        const FastBlit fb = f.fpost[k];
-        if (fb.flags & 4u) continue;
-        int x0 = fb.x0, y0 = fb.y0, x1 = fb.x0 + fb.w - 1, y1 = fb.y0 + fb.h - 1;
-        if (fb.flags & 2u) {   // conservative bounds of a rotated rect: centre +- half diagonal
-            int rad = ((int)fb.w + (int)fb.h) / 2 + 2;
-            int cx = fb.x0 + fb.w / 2, cy = fb.y0 + fb.h / 2;
-            x0 = cx - rad; x1 = cx + rad; y0 = cy - rad; y1 = cy + rad;
-        }
-        if (x1 < 0 || y1 < 0 || x0 > 63 || y0 > 63) continue;
-        x0 = max(x0, 0) >> 3; y0 = max(y0, 0) >> 2; x1 = min(x1, 63) >> 3; y1 = min(y1, 63) >> 2;
-        for (int by = y0; by <= y1; by++)
-            for (int bx = x0; bx <= x1; bx++) { atomicOr(&f.bin[by * 8 + bx][k >> 5], 1u << (k & 31)); f.bin_any[by * 8 + bx] = 1; }
-    }
-    if (tid == 0) frame_store_wait();   // the previous frame's bulk store has read f.rgb
+    if (lane == 0) frame_store_wait();   // this warp's bulk stores of the previous frame have read f.rgb
     __syncthreads();
 }
 
 // Texel of a blit under pixel (X, Y); false when the pixel is not covered.
-PG2_DEV bool fast_texel(const FastBlit& fbr, const BlitRot* rot, const uint32_t* __restrict__ atlas, int X, int Y, uint32_t* texel) {
-    const FastBlit fb = fbr;
+template <bool ROT>
+PG2_DEV bool fast_texel(const FastBlit& fb, const BlitRot* rot, const uint32_t* __restrict__ atlas, int X, int Y, uint32_t* texel) {
     uint32_t i, j;
-    if (fb.flags & 6u) {
-        if (fb.flags & 4u) return false;
+    if (ROT && (fb.flags & 2u)) {
         // rotated: inverse-map the pixel centre into the un-rotated destination rect (oracle/raster.c step 4)
         double hw = __dmul_rn((double)fb.w, 0.5), hh = __dmul_rn((double)fb.h, 0.5);
         double cx = __dadd_rn((double)fb.x0, hw), cy = __dadd_rn((double)fb.y0, hh);
@@ -365,145 +447,228 @@ PG2_DEV uint32_t blend_packed(uint32_t color, uint32_t texel, uint32_t blend, ui
     return r | g << 8 | b << 16;
 }
 
-// clear -> pre -> tiles of one pixel in reference (bottom-up) order; `general` walks the whole covering range
-// (frames where more than two tiles cover a column / row), else the two-candidate tables are used.
-template <class F>
-PG2_DEV_NOINLINE uint32_t shade_base_ordered(const F& f, const uint32_t* __restrict__ atlas, int X, int Y, bool general) {
+// Tile candidates of a pixel as a 4-bit set (candidate q = jr * 2 + jc <=> tile (rlo + jr, clo + jc)): a tile is
+// there and the axes of its shape class cover the pixel. Painter's order = ascending q.
+template <int NCLASS>
+PG2_DEV uint32_t tile_candidates(const RowDesc& rd, uint32_t cw) {
+    const uint32_t clo = cw & 31u, v = cw & rd.rw;
+    uint32_t p = (((rd.rm[0][0] >> clo) & 3u) | ((rd.rm[0][1] >> clo) & 3u) << 2) & (v >> 8);
+    if (NCLASS > 1) p |= (((rd.rm[1][0] >> clo) & 3u) | ((rd.rm[1][1] >> clo) & 3u) << 2) & (v >> 12);
+    return p & 15u;
+}
+
+// Atlas index + blend flag of tile candidate q under a pixel.
+template <int NCLASS, class F>
+PG2_DEV uint32_t tile_texel_index(const F& f, const RowDesc& rd, const ColDesc& cd, uint32_t q, uint32_t* blend) {
+    const uint32_t jr = q >> 1, jc = q & 1u;
+    const uint32_t t = f.tile_tex[((rd.rw & 31u) + jr) * MAX_WIN + (cd.cw & 31u) + jc];
+    const TileTex tt = f.tiletex[t & (MAX_TILE_TEX - 1)];
+    const uint32_t cls = NCLASS > 1 ? tt.cls : 0u;
+    const uint32_t sx = (cd.csx >> ((cls * 2u + jc) * 8u)) & 255u;
+    const uint32_t syw = ((cls ? rd.syw[1] : rd.syw[0]) >> (jr * 16u)) & 0xffffu;
+    *blend = tt.blend;
+    return tt.offset + syw + sx;
+}
+
+// clear -> pre -> tiles of one pixel in reference (bottom-up) order with full blending: the path of pixels whose
+// top-most layer is translucent, and of every pixel of a `wide` frame (more than two tiles cover a column / row,
+// or a background the tables do not describe), which walks the covering ranges with the axes themselves.
+template <class G, class F>
+PG2_DEV_NOINLINE uint32_t shade_base_ordered(const F& f, const uint32_t* __restrict__ atlas, int X, int Y) {
     uint32_t color = 0u, texel;   // SDL_RenderClear(0,0,0,255)
-    for (int k = 0; k < f.npre; k++)
-        if (fast_texel(f.fpre[k], nullptr, atlas, X, Y, &texel)) color = blend_packed(color, texel, f.fpre[k].flags & 1u, f.fpre[k].alpha_mod);
-    const int rlo = f.row_lo[Y], rhi = f.row_hi[Y], clo = f.col_lo[X], chi = f.col_hi[X];
+    for (int k = 0; k < f.npre; k++) {
+        const FastBlit fb = f.fpre[k];
+        BlitRot rot{ 0.0, 1.0 };
+        if (!(fb.flags & 4u) && fast_texel<false>(fb, &rot, atlas, X, Y, &texel)) color = blend_packed(color, texel, fb.flags & 1u, fb.alpha_mod);
+    }
+    if (!f.wide) {
+        const RowDesc rd = f.rowd[Y];
+        const ColDesc cd = f.cold[X];
+        uint32_t p = tile_candidates<G::TILE_CLASSES>(rd, cd.cw);
+        for (uint32_t q = 0; q < 4u; q++)
+            if (p >> q & 1u) {
+                uint32_t blend;
+                texel = __ldg(atlas + tile_texel_index<G::TILE_CLASSES>(f, rd, cd, q, &blend));
+                color = blend_packed(color, texel, blend, 255u);
+            }
+        return color;
+    }
+    const int rlo = f.cov_lo[OBS_W + Y], rhi = f.cov_hi[OBS_W + Y], clo = f.cov_lo[X], chi = f.cov_hi[X];
     for (int ry = rlo; ry <= rhi; ry++)
         for (int cx = clo; cx <= chi; cx++) {
             uint32_t t = f.tile_tex[ry * MAX_WIN + cx];
             if (t == NO_TILE) continue;
             const TileTex tt = f.tiletex[t];
-            int sx, sy;
-            if (general) {
-                const Axis& ax = f.col[tt.cls][cx];
-                const Axis& ay = f.row[tt.cls][ry];
-                if (!ax.visible || !ay.visible) continue;
-                if ((unsigned)(X - ax.d0) >= (unsigned)ax.dlen || (unsigned)(Y - ay.d0) >= (unsigned)ay.dlen) continue;
-                sx = axis_sample(ax, X, false); sy = axis_sample(ay, Y, false);
-            } else {
-                sx = f.col_sx[tt.cls][cx - clo][X]; sy = f.row_sy[tt.cls][ry - rlo][Y];
-                if ((sx | sy) < 0) continue;
-            }
+            const Axis& ax = f.col[tt.cls][cx];
+            const Axis& ay = f.row[tt.cls][ry];
+            if (!ax.visible || !ay.visible) continue;
+            if ((unsigned)(X - ax.d0) >= (unsigned)ax.dlen || (unsigned)(Y - ay.d0) >= (unsigned)ay.dlen) continue;
+            int sx = axis_sample(ax, X, false), sy = axis_sample(ay, Y, false);
             texel = __ldg(atlas + tt.offset + (uint32_t)sy * tt.w + (uint32_t)sx);
             color = blend_packed(color, texel, tt.blend, 255u);
         }
     return color;
 }
 
-// Shade all 4096 pixels into f.rgb. A warp owns 8x4-pixel blocks (lane = pixel); loop trip counts are uniform over
-// the warp (<= 2x2 candidate tiles, the block's post-blit bin) and lanes whose pixel is not covered are predicated
-// off, so a warp never serialises different pixels' layer lists.
-//   base colour: tile candidates TOP-DOWN ((hi,hi) .. (lo,lo) = reverse painter's order), then the pre blits; the
-//     first opaque texel decides the pixel (alpha 255 replaces, alpha 0 is the identity — exact). A partially
-//     transparent texel met on the way sends that pixel through shade_base_ordered (reference order) instead.
-//   post blits: bottom-up in submission order on top of the base colour.
+// A pixel whose top-most tile texel turned out transparent: keep walking its candidates top-down (then the
+// background); the first opaque texel decides, a translucent one hands the pixel to shade_base_ordered.
 template <class G, class F>
-PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas) {
-    const bool wide = f.wide != 0;
-    const int npre = f.npre;
-    const int lane = threadIdx.x % WARP_LANES;
-    for (;;) {
-      // blocks are handed out dynamically: a warp that drew cheap blocks (no sprites) simply takes more of them
-      int block = 0;
-      if (lane == 0) block = smem_atomic_inc(&f.next_block);
-      block = warp_bcast(block);
-      if (block >= 128) break;
-      for (int l = lane; l < 32; l += WARP_LANES) {
-        const int X = ((block & 7) << 3) + (l & 7), Y = ((block >> 3) << 2) + (l >> 3);
-        uint32_t color = 0u, texel;
-        bool resolved = false, semi = wide;
-        if (!wide) {
-            const int rlo = f.row_lo[Y], nr = (int)f.row_hi[Y] - rlo + 1;
-            const int clo = f.col_lo[X], nc = (int)f.col_hi[X] - clo + 1;
-            // every lane walks ITS candidates from the topmost one: candidate index q = jr * ncc + jc, descending
-            const int nrr = min(max(nr, 0), 2), ncc = min(max(nc, 0), 2);
-            int q = nrr * ncc - 1;
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                bool act = !resolved && q >= 0;
-                if (!warp_any(act)) break;
-                if (act) {
-                    const int jr = ncc == 2 ? q >> 1 : q, jc = ncc == 2 ? q & 1 : 0;
-                    uint32_t tid = f.tile_tex[(rlo + jr) * MAX_WIN + clo + jc];
-                    if (tid != NO_TILE) {
-                        const TileTex tt = f.tiletex[tid];
-                        int sx = f.col_sx[tt.cls][jc][X], sy = f.row_sy[tt.cls][jr][Y];
-                        if ((sx | sy) >= 0) {
-                            texel = __ldg(atlas + tt.offset + (uint32_t)sy * tt.w + (uint32_t)sx);
-                            uint32_t a = tt.blend ? texel >> 24 : 255u;
-                            if (a == 255u) { color = texel; resolved = true; }
-                            else if (a != 0u) { semi = true; resolved = true; }
-                        }
-                    }
-                    q--;
-                }
-            }
-            if (warp_any(!resolved)) {
-                for (int k = npre - 1; k >= 0; k--) {
-                    const int cx = f.pre_sx[k][X], ro = f.pre_row[k][Y];
-                    if (!resolved && (cx | ro) >= 0) {
-                        texel = __ldg(atlas + (uint32_t)ro + (uint32_t)cx);
-                        uint32_t a = layer_alpha(texel, f.fpre[k].flags & 1u, f.fpre[k].alpha_mod);
-                        if (a == 255u) { color = texel; resolved = true; }
-                        else if (a != 0u) { semi = true; resolved = true; }
-                    }
-                }
-            }
-        }
-        if (semi) color = shade_base_ordered(f, atlas, X, Y, wide);
-        if (f.bin_any[block]) {
-            const uint32_t* bins = f.bin[block];
-#pragma unroll
-            for (int w = 0; w < F::WORDS; w++) {
-                uint32_t m = bins[w];
-                while (m) {
-                    int k = w * 32 + __ffs(m) - 1;
-                    m &= m - 1;
-                    if (fast_texel(f.fpost[k], &f.post_rot[F::ROTATES ? k : 0], atlas, X, Y, &texel))
-                        color = blend_packed(color, texel, f.fpost[k].flags & 1u, f.fpost[k].alpha_mod);
-                }
-            }
-        }
-        uint8_t* out = f.rgb + 3 * (Y * OBS_W + X);
-        out[0] = (uint8_t)color; out[1] = (uint8_t)(color >> 8); out[2] = (uint8_t)(color >> 16);
-      }
+PG2_DEV_NOINLINE uint32_t shade_base_continue(const F& f, const uint32_t* __restrict__ atlas, int X, int Y, uint32_t p) {
+    const RowDesc rd = f.rowd[Y];
+    const ColDesc cd = f.cold[X];
+    while (p) {
+        const uint32_t q = bfind(p);
+        p &= ~(1u << q);
+        uint32_t blend;
+        const uint32_t texel = __ldg(atlas + tile_texel_index<G::TILE_CLASSES>(f, rd, cd, q, &blend));
+        const uint32_t a = blend ? texel >> 24 : 255u;
+        if (a == 255u) return texel;
+        if (a != 0u) return shade_base_ordered<G>(f, atlas, X, Y);
     }
+    if ((rd.pre_row | cd.pre_sx) < 0) return 0u;
+    const uint32_t texel = __ldg(atlas + (uint32_t)rd.pre_row + (uint32_t)cd.pre_sx);
+    const uint32_t a = f.pre_blend ? texel >> 24 : 255u;
+    if (a == 255u) return texel;
+    return a ? shade_base_ordered<G>(f, atlas, X, Y) : 0u;
 }
 
-// The finished frame leaves the SM as ONE 12 288-byte TMA bulk store shared -> global (async proxy). The copy is
-// only ISSUED here; the CTA goes on with the next frame's description and waits (frame_store_wait) right before
-// it overwrites f.rgb again, so the drain of the staging buffer overlaps useful work.
+// Base pass of one band: clear + background + tile layer of 8 rows, packed into f.rgb.
+template <class G, class F>
+PG2_DEV void raster_band_base(F& f, const uint32_t* __restrict__ atlas, int band, int lane) {
+    constexpr int NCLASS = G::TILE_CLASSES;
+    const bool wide = f.wide != 0;
+    const uint32_t pre_blend = (uint32_t)f.pre_blend;
+    for (int it = 0; it < BAND_ROWS / 2; it++)
+        for (int l = lane; l < 32; l += WARP_LANES) {
+            const int Y = band * BAND_ROWS + it * 2 + (l >> 4), X0 = (l & 15) * 4;
+            uint32_t color[4];
+            if (!wide) {
+                const RowDesc rd = f.rowd[Y];
+                uint32_t cand[4], texel[4], blend[4];
+                bool fetched[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const ColDesc cd = f.cold[X0 + i];
+                    const uint32_t p = tile_candidates<NCLASS>(rd, cd.cw);
+                    cand[i] = p;
+                    uint32_t tb;
+                    const uint32_t tidx = tile_texel_index<NCLASS>(f, rd, cd, bfind(p | 1u), &tb);
+                    const bool bg_ok = (rd.pre_row | cd.pre_sx) >= 0;
+                    const uint32_t idx = p ? tidx : (uint32_t)rd.pre_row + (uint32_t)cd.pre_sx;
+                    blend[i] = p ? tb : pre_blend;
+                    fetched[i] = p || bg_ok;
+                    texel[i] = fetched[i] ? __ldg(atlas + idx) : 0u;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t a = (blend[i] && fetched[i]) ? texel[i] >> 24 : 255u;
+                    color[i] = texel[i];
+                    if (a != 255u) {   // transparent: next candidate below; translucent: blend in reference order
+                        if (a != 0u) color[i] = shade_base_ordered<G>(f, atlas, X0 + i, Y);
+                        else color[i] = cand[i] ? shade_base_continue<G>(f, atlas, X0 + i, Y, cand[i] & ~(1u << bfind(cand[i]))) : 0u;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) color[i] = shade_base_ordered<G>(f, atlas, X0 + i, Y);
+            }
+            uint32_t* out = (uint32_t*)(f.rgb + 3 * (Y * OBS_W + X0));
+            out[0] = byte_perm(color[0], color[1], 0x4210u);
+            out[1] = byte_perm(color[1], color[2], 0x5421u);
+            out[2] = byte_perm(color[2], color[3], 0x6542u);
+        }
+}
+
+// One post blit onto the rows [Y0, Y0 + 8) of f.rgb: lanes = an 8x4 patch of the destination rectangle.
 template <class F>
-PG2_DEV void frame_store(F& f, uint8_t* __restrict__ dst) {
+PG2_DEV void draw_blit_band(F& f, const uint32_t* __restrict__ atlas, int k, int Y0, int lane) {
+    const FastBlit fb = f.fpost[k];
+    const BlitRot* rot = &f.post_rot[F::ROTATES ? k : 0];
+    int x0 = fb.x0, y0 = fb.y0, x1 = fb.x0 + fb.w - 1, y1 = fb.y0 + fb.h - 1;
+    if (F::ROTATES && (fb.flags & 2u)) {   // conservative bounds of a rotated rect: centre +- half diagonal
+        int rad = ((int)fb.w + (int)fb.h) / 2 + 2;
+        int cx = fb.x0 + fb.w / 2, cy = fb.y0 + fb.h / 2;
+        x0 = cx - rad; x1 = cx + rad; y0 = cy - rad; y1 = cy + rad;
+    }
+    x0 = max(x0, 0); x1 = min(x1, OBS_W - 1); y0 = max(y0, Y0); y1 = min(y1, Y0 + BAND_ROWS - 1);
+    const uint32_t blend = fb.flags & 1u, alpha_mod = fb.alpha_mod;
+    for (int yb = y0; yb <= y1; yb += 4)
+        for (int xb = x0; xb <= x1; xb += 8)
+            for (int l = lane; l < 32; l += WARP_LANES) {
+                const int X = xb + (l & 7), Y = yb + (l >> 3);
+                uint32_t texel;
+                if (X <= x1 && Y <= y1 && fast_texel<F::ROTATES>(fb, rot, atlas, X, Y, &texel)) {
+                    const uint32_t a = layer_alpha(texel, blend, alpha_mod);
+                    uint8_t* px = f.rgb + 3 * (Y * OBS_W + X);
+                    if (a == 255u) { px[0] = (uint8_t)texel; px[1] = (uint8_t)(texel >> 8); px[2] = (uint8_t)(texel >> 16); }
+                    else if (a != 0u) {
+                        uint32_t r = px[0], g = px[1], b = px[2];
+                        blend_texel(r, g, b, texel, blend, alpha_mod);
+                        px[0] = (uint8_t)r; px[1] = (uint8_t)g; px[2] = (uint8_t)b;
+                    }
+                }
+            }
+    __syncwarp();
+}
+
+// The finished band leaves the SM as one 1 536-byte TMA bulk store shared -> global (async proxy). The copy is only
+// ISSUED here (by the warp that drew the band); the warp waits (frame_store_wait) right before the CTA starts to
+// overwrite f.rgb with the next frame, so the drain of the staging buffer overlaps useful work.
+template <class F>
+PG2_DEV void band_store(F& f, uint8_t* __restrict__ dst, int band, int lane) {
 #ifdef PG2_HOSTSIM
-    memcpy(dst, f.rgb, OBS_BYTES);
-    return;
+    memcpy(dst + band * BAND_BYTES, f.rgb + band * BAND_BYTES, BAND_BYTES);
 #else
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t src = (uint32_t)__cvta_generic_to_shared(f.rgb);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "n"(OBS_BYTES) : "memory");
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t src = (uint32_t)__cvta_generic_to_shared(f.rgb + band * BAND_BYTES);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + band * BAND_BYTES), "r"(src), "n"(BAND_BYTES) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
 #endif
 }
 
+// Draw the frame: warps take bands from a ticket counter (a warp that drew cheap bands simply takes more of them),
+// per band: base pass, post blits in submission order, bulk store.
+template <class G, class F>
+PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas, uint8_t* __restrict__ dst) {
+    const int lane = threadIdx.x % WARP_LANES;
+    const int npost = f.npost;
+    for (;;) {
+        int band = 0;
+        if (lane == 0) band = smem_atomic_inc(&f.next_band);
+        band = warp_bcast(band);
+        if (band >= NUM_BANDS) break;
+        raster_band_base<G>(f, atlas, band, lane);
+        __syncwarp();
+        for (int base = 0; base < npost; base += 32) {
+            uint32_t m = 0u;
+            for (int l = lane; l < 32; l += WARP_LANES) {
+                const int k = base + l;
+                m |= lane_ballot(k < npost && (f.bandmask[k < npost ? k : 0] >> band & 1u), l);
+            }
+            while (m) {
+                const int k = base + __ffs(m) - 1;
+                m &= m - 1u;
+                draw_blit_band(f, atlas, k, band * BAND_ROWS, lane);
+            }
+        }
+        band_store(f, dst, band, lane);
+    }
+}
+
 // Per-CTA table of the game's tile textures (ids < MAX_TILE_TEX), filled once before the first frame.
 template <class G, class F>
 PG2_DEV void frame_init_tiletex(F& f, const TexInfo* __restrict__ tex) {
-    int ntex = 0;
-    (void)ntex;
-    for (int t = threadIdx.x; t < MAX_TILE_TEX && t < G::NUM_TEX; t += blockDim.x) {
-        TexInfo ti = tex[t];
+    for (int t = threadIdx.x; t < MAX_TILE_TEX; t += blockDim.x) {
         TileTex tt;
-        tt.offset = ti.offset; tt.w = ti.w; tt.blend = ti.blend ? 1 : 0;
-        tt.cls = (uint8_t)((G::TILE_CLASSES > 1) ? G::tile_class((uint32_t)t) : 0);
+        tt.offset = 0; tt.w = 0; tt.blend = 0; tt.cls = 0;
+        if (t < G::NUM_TEX) {
+            TexInfo ti = tex[t];
+            tt.offset = ti.offset; tt.w = ti.w; tt.blend = ti.blend ? 1 : 0;
+            tt.cls = (uint8_t)((G::TILE_CLASSES > 1) ? G::tile_class((uint32_t)t) : 0);
+        }
         f.tiletex[t] = tt;
     }
     __syncthreads();
