@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::
 // more of them. mode 0: every env; mode 1: every env that is NOT being reset this step (k_reset runs concurrently
 // on a second stream); mode 2: exactly the envs of the reset list (after k_reset).
 template <class G>
-__global__ void __launch_bounds__(RENDER_THREADS) k_render(typename G::State s, CommonState c, const TexInfo* __restrict__ tex,
+__global__ void __launch_bounds__(RENDER_THREADS, 8) k_render(typename G::State s, CommonState c, const TexInfo* __restrict__ tex,
                                                            const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs,
                                                            int* __restrict__ ticket, int mode, const int* __restrict__ list,
                                                            const int* __restrict__ list_count, const uint8_t* __restrict__ pending, int N) {
@@ -117,17 +117,22 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render(typename G::State s, 
     __shared__ int s_env;
     const int count = mode == 2 ? *list_count : N;
     frame_init_tiletex<G>(f, tex);
+    auto take_ticket = [&]() {
+        int t = atomicAdd(ticket, 1);
+        if (mode == 1) while (t < count && pending[t]) t = atomicAdd(ticket, 1);
+        return t;
+    };
+    int next = 0;
+    if (threadIdx.x == 0) next = take_ticket();
     for (;;) {
         __syncthreads();   // every warp is done with the previous frame (bands are stored per warp, without a CTA barrier)
-        if (threadIdx.x == 0) {
-            int t = atomicAdd(ticket, 1);
-            if (mode == 1) while (t < count && pending[t]) t = atomicAdd(ticket, 1);
-            s_env = t < count ? (mode == 2 ? list[t] : t) : -1;
-        }
+        if (threadIdx.x == 0) s_env = next < count ? (mode == 2 ? list[next] : next) : -1;
         frame_begin(f);
         __syncthreads();
         const int env = s_env;
         if (env < 0) break;
+        // the next frame's ticket is taken now: the atomic's round trip overlaps this frame's work
+        if (threadIdx.x == 0) next = take_ticket();
         render_body<G>(s, c, env, f, tex, atlas, obs, false);
     }
     if ((threadIdx.x & 31) == 0) frame_store_wait();   // every warp issued bulk stores of its own

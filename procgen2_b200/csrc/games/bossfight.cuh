@@ -464,12 +464,11 @@ struct BossFight {
         const int N = s.N;
         const Camera cam{ 0.0f, 0.0f, 1.0f };
         const double PI = 3.14159265358979323846;
-        if (is_role(1)) {
-            f.tx0 = 0; f.ty0 = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1;
-            int bg = T_BG0 + s.bg_index[env];
-            float sc = __fdiv_rn(__fmul_rn(__fdiv_rn(1.0f, (float)tex[bg].h), 64.0f), 1.0f);
-            f.pre[0] = make_blit(tex, bg, __fmul_rn(__fdiv_rn(-64.0f, 1.0f), 0.5f), __fmul_rn(__fdiv_rn(-64.0f, 1.0f), 0.5f), cam, sc);
-            f.npre = 1;
+        {   // background only, no tile layer
+            const int bg = T_BG0 + s.bg_index[env];
+            const float sc = __fdiv_rn(__fmul_rn(__fdiv_rn(1.0f, (float)tex[bg].h), 64.0f), 1.0f);
+            const float half = __fmul_rn(__fdiv_rn(-64.0f, 1.0f), 0.5f);
+            build_tile_layer(f, cam, tex, 1, 0, 0, 0, 0, [](int) { return 0; }, [](int, int) { return (int)NO_TILE; }, bg, half, half, sc);
         }
         const int m_num = s.m_num_bullets[env], m_next = s.m_next_bullet[env];
         const int e_num = s.m_num_expl[env], e_next = s.m_next_expl[env];
@@ -480,7 +479,7 @@ struct BossFight {
         // submission order: boss bullets, boss, shield, explosions, barrier sprites, agent bullets, ship
         const int o_boss = m_num, o_shield = o_boss + 1, o_expl = o_shield + 1, o_spr = o_expl + e_num,
                   o_ab = o_spr + nspr, o_ship = o_ab + a_num;
-        emit_post_blits(f, o_ship + 1, [&](int k, Blit& b, BlitRot& rot) {
+        emit_post_blits(f, tex, o_ship + 1, [&](int k, BlitReq& b, BlitRot& rot) {
             if (k < o_boss) {
                 int bi = ((MB + m_next - 1 - k) % MB) * N + env;
                 float frame = s.mb_frame[bi];
@@ -490,14 +489,14 @@ struct BossFight {
                 float x = __fsub_rn(__fmul_rn(s.mb_x[bi], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[t].w), 0.5f));
                 float y = __fsub_rn(__fmul_rn(s.mb_y[bi], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[t].h), 0.5f));
                 float rotation = (float)__dadd_rn((double)s.mb_rot[bi], __dmul_rn(PI, 0.5));
-                b = make_blit_rotated(tex, t, x, y, cam, rotation, size, 1.0f, &rot);
+                b.rotated(t, x, y, cam, rotation, size, 1.0f, &rot);
             } else if (k == o_boss || k == o_shield) {
                 if (k == o_shield && !shield) return;
                 int t = k == o_boss ? T_BOSS0 + s.m_ship[env] : T_SHIELD;
                 const float size = 0.25f;
                 float x = __fsub_rn(__fmul_rn(bx, UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[t].w), 0.5f));
                 float y = __fsub_rn(__fmul_rn(by, UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[t].h), 0.5f));
-                b = make_blit(tex, t, x, y, cam, size, k == o_boss ? 1.0f : 0.7f);
+                b.plain(t, x, y, cam, size, k == o_boss ? 1.0f : 0.7f);
             } else if (k < o_spr) {
                 int ei = ((NEX + e_next - 1 - (k - o_expl)) % NEX) * N + env;
                 float frame = s.ex_frame[ei];
@@ -506,14 +505,14 @@ struct BossFight {
                 const float size = 0.3f;
                 float x = __fsub_rn(__fmul_rn(s.ex_x[ei], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[t].w), 0.5f));
                 float y = __fsub_rn(__fmul_rn(s.ex_y[ei], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[t].h), 0.5f));
-                b = make_blit(tex, t, x, y, cam, size);
+                b.plain(t, x, y, cam, size);
             } else if (k < o_ab) {
                 int id = s.sprite_order[sort_perm(nspr, k - o_spr) * N + env] - 2;
                 int t = T_BARRIER0 + s.bar_tex[id * N + env];
                 float x = __fmul_rn(__fadd_rn(s.bar_x[id * N + env], -0.15f), UNIT_TO_PIXELS);
                 float y = __fmul_rn(__fadd_rn(s.bar_y[id * N + env], -0.15f), UNIT_TO_PIXELS);
                 float sc = __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 0.3f), UNIT_TO_PIXELS), (float)tex[t].w);
-                b = make_blit(tex, t, x, y, cam, sc);
+                b.plain(t, x, y, cam, sc);
             } else if (k < o_ship) {
                 int bi = ((AB + a_next - 1 - (k - o_ab)) % AB) * N + env;
                 float frame = s.ab_frame[bi];
@@ -522,16 +521,15 @@ struct BossFight {
                 const float size = 0.05f;
                 float x = __fsub_rn(__fmul_rn(s.ab_x[bi], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[t].w), 0.5f));
                 float y = __fsub_rn(__fmul_rn(s.ab_y[bi], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[t].h), 0.5f));
-                b = make_blit(tex, t, x, y, cam, size);
+                b.plain(t, x, y, cam, size);
             } else {
                 int t = T_PLAYER0 + s.a_ship[env];
                 const float size = 0.05f;
                 float x = __fsub_rn(__fmul_rn(s.px[env], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[t].w), 0.5f));
                 float y = __fsub_rn(__fmul_rn(s.py[env], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[t].h), 0.5f));
-                b = make_blit(tex, t, x, y, cam, size);
+                b.plain(t, x, y, cam, size);
             }
         });
-        __syncthreads();
     }
 };
 

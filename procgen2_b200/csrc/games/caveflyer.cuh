@@ -360,15 +360,11 @@ struct CaveFlyer {
         const int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);
         const int nobj = s.num_obj[env];
         const bool sprites = c.sprites_valid[env] != 0;
-        if (is_role(1)) {
-            f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = 1;
-            int bg = T_BG0 + s.bg_index[env];
-            TexInfo bt = tex[bg];
-            float extra = __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f);
-            f.pre[0] = make_blit(tex, bg, __fmul_rn(-s.bg_offset[env], extra), 0.0f, cam,
-                                 __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h));
-            f.npre = 1;
-        }
+        // background (e.g. maze.cpp:402-408): the blit itself is built by build_tile_layer below
+        const int bg = T_BG0 + s.bg_index[env];
+        const TexInfo bt = tex[bg];
+        const float bg_x = __fmul_rn(-s.bg_offset[env], __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f));
+        const float bg_scale = __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h);
         auto sprite_alive = [&](int sp) { return sp == 0 || s.obj_type[(sp - 1) * N + env] != O_NONE; };
         int nlive = 0;
         if (sprites)
@@ -377,8 +373,8 @@ struct CaveFlyer {
         const int o_spr = NPART, o_bul = o_spr + nlive, o_ship = o_bul + num_bullets;
         const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
         build_tile_layer(f, cam, tex, 1, lx, ly, ncol, nrow, [](int) { return (int)T_WALL; },
-                         [&](int x, int y) { return get(tiles, x, H - 1 - y) == 1 ? (int)T_WALL : (int)NO_TILE; });
-        emit_post_blits(f, o_ship + 1, [&](int k, Blit& b, BlitRot& rot) {
+                         [&](int x, int y) { return get(tiles, x, H - 1 - y) == 1 ? (int)T_WALL : (int)NO_TILE; }, bg, bg_x, 0.0f, bg_scale);
+        emit_post_blits(f, tex, o_ship + 1, [&](int k, BlitReq& b, BlitRot& rot) {
             if (k < o_spr) {   // System_Particles::render
                 int pi = k * N + env;
                 float life = s.p_life[pi];
@@ -391,7 +387,7 @@ struct CaveFlyer {
                 float size = __fdiv_rn(__fmul_rn(scale, UNIT_TO_PIXELS), pw);
                 float x = __fsub_rn(__fmul_rn(__fadd_rn(s.p_x[pi], __fmul_rn(s.p_dx[pi], shift)), UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, pw), 0.5f));
                 float y = __fsub_rn(__fmul_rn(__fadd_rn(s.p_y[pi], __fmul_rn(s.p_dy[pi], shift)), UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, ph), 0.5f));
-                b = make_blit_rotated(tex, T_PARTICLE, x, y, cam, s.p_rot[pi], size, alpha, &rot);
+                b.rotated(T_PARTICLE, x, y, cam, s.p_rot[pi], size, alpha, &rot);
             } else if (k < o_bul) {
                 int want = sort_perm(nlive, k - o_spr), sp = 0;
                 for (int j = 0, seen = 0; j < nobj + 1; j++) {
@@ -408,7 +404,7 @@ struct CaveFlyer {
                 float px = __fmul_rn(__fadd_rn(x, -0.4f), UNIT_TO_PIXELS);
                 float py = __fmul_rn(__fadd_rn(y, -0.4f), UNIT_TO_PIXELS);
                 float sc = __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 0.8f), UNIT_TO_PIXELS), (float)tex[t].w);
-                b = make_blit(tex, t, px, py, cam, sc);
+                b.plain(t, px, py, cam, sc);
             } else if (k < o_ship) {
                 int bi = ((NB + next_bullet - 1 - (k - o_bul)) % NB) * N + env;
                 float frame = s.b_frame[bi];
@@ -418,16 +414,15 @@ struct CaveFlyer {
                 float x = __fsub_rn(__fmul_rn(s.b_x[bi], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[t].w), 0.5f));
                 float y = __fsub_rn(__fmul_rn(s.b_y[bi], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[t].h), 0.5f));
                 float rotation = (float)__dadd_rn((double)s.b_rot[bi], __dmul_rn(PI, 0.5));
-                b = make_blit_rotated(tex, t, x, y, cam, rotation, size, 1.0f, &rot);
+                b.rotated(t, x, y, cam, rotation, size, 1.0f, &rot);
             } else {
                 const float size = 0.15f;
                 float x = __fsub_rn(__fmul_rn(s.ax[env], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[T_SHIP].w), 0.5f));
                 float y = __fsub_rn(__fmul_rn(s.ay[env], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, (float)tex[T_SHIP].h), 0.5f));
                 float rotation = (float)__dadd_rn((double)s.arot[env], __dmul_rn(PI, 0.5));
-                b = make_blit_rotated(tex, T_SHIP, x, y, cam, rotation, size, 1.0f, &rot);
+                b.rotated(T_SHIP, x, y, cam, rotation, size, 1.0f, &rot);
             }
         });
-        __syncthreads();
     }
 };
 

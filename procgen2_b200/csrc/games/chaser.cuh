@@ -359,22 +359,18 @@ struct Chaser {
         const int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);
         const int nents = s.num_ents[env];
         const bool sprites = c.sprites_valid[env] != 0;
-        if (is_role(1)) {
-            f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = 1;
-            int bg = T_BG0 + s.bg_index[env];
-            TexInfo bt = tex[bg];
-            float extra = __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f);
-            f.pre[0] = make_blit(tex, bg, __fmul_rn(-s.bg_offset[env], extra), 0.0f, cam,
-                                 __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h));
-            f.npre = 1;
-        }
+        // background (e.g. maze.cpp:402-408): the blit itself is built by build_tile_layer below
+        const int bg = T_BG0 + s.bg_index[env];
+        const TexInfo bt = tex[bg];
+        const float bg_x = __fmul_rn(-s.bg_offset[env], __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f));
+        const float bg_scale = __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h);
         int nlive = 0;
         if (sprites)
             for (int k = 0; k < nents; k++) nlive += s.ent_kind[s.sprite_order[k * N + env] * N + env] != K_NONE;
         const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
         build_tile_layer(f, cam, tex, 1, lx, ly, ncol, nrow, [](int) { return (int)T_WALL; },
-                         [&](int x, int y) { return get(tiles, x, H - 1 - y) == 1 ? (int)T_WALL : (int)NO_TILE; });
-        emit_post_blits(f, nlive + 1, [&](int k, Blit& b, BlitRot&) {
+                         [&](int x, int y) { return get(tiles, x, H - 1 - y) == 1 ? (int)T_WALL : (int)NO_TILE; }, bg, bg_x, 0.0f, bg_scale);
+        emit_post_blits(f, tex, nlive + 1, [&](int k, BlitReq& b, BlitRot&) {
             if (k < nlive) {
                 int want = sort_perm(nlive, k), e = 0;
                 for (int j = 0, seen = 0; j < nents; j++) {
@@ -394,14 +390,13 @@ struct Chaser {
                 float px = __fmul_rn(__fadd_rn(x, -0.5f), UNIT_TO_PIXELS);
                 float py = __fmul_rn(__fadd_rn(y, -0.5f), UNIT_TO_PIXELS);
                 float sc = __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 1.0f), UNIT_TO_PIXELS), (float)tex[t].w);
-                b = make_blit(tex, t, px, py, cam, sc);
+                b.plain(t, px, py, cam, sc);
             } else {
                 float px = __fmul_rn(__fadd_rn(s.ax[env], -0.5f), UNIT_TO_PIXELS);
                 float py = __fmul_rn(__fadd_rn(s.ay[env], -0.5f), UNIT_TO_PIXELS);
-                b = make_blit(tex, T_AGENT, px, py, cam, __fmul_rn(__fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_AGENT].w), 1.0f));
+                b.plain(T_AGENT, px, py, cam, __fmul_rn(__fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_AGENT].w), 1.0f));
             }
         });
-        __syncthreads();
     }
 };
 

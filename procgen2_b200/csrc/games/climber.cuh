@@ -310,15 +310,11 @@ struct Climber {
         const int nents = s.num_ents[env];
         const bool sprites = c.sprites_valid[env] != 0;
         const int theme = s.map_theme[env];
-        if (is_role(1)) {
-            f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = 2;
-            int bg = T_BG0 + s.bg_index[env];
-            TexInfo bt = tex[bg];
-            float extra = __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f);
-            f.pre[0] = make_blit(tex, bg, __fmul_rn(-s.bg_offset[env], extra), 0.0f, cam,
-                                 __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h));
-            f.npre = 1;
-        }
+        // background (e.g. maze.cpp:402-408): the blit itself is built by build_tile_layer below
+        const int bg = T_BG0 + s.bg_index[env];
+        const TexInfo bt = tex[bg];
+        const float bg_x = __fmul_rn(-s.bg_offset[env], __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f));
+        const float bg_scale = __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h);
         // live sprites in set order; destroyed points simply drop out of the (order-preserving) set
         int nlive = 0;
         if (sprites)
@@ -328,8 +324,8 @@ struct Climber {
         build_tile_layer(f, cam, tex, 2, lx, ly, ncol, nrow, [&](int cls) { return (cls ? T_WALL_TOP0 : T_WALL_MID0) + theme; }, [&](int x, int y) {
             const int id = get(tiles, x, H - 1 - y);
             return id == WALL_MID ? T_WALL_MID0 + theme : id == WALL_TOP ? T_WALL_TOP0 + theme : (int)NO_TILE;
-        });
-        emit_post_blits(f, nlive + 1, [&](int k, Blit& b, BlitRot&) {
+        }, bg, bg_x, 0.0f, bg_scale);
+        emit_post_blits(f, tex, nlive + 1, [&](int k, BlitReq& b, BlitRot&) {
             if (k < nlive) {
                 int want = sort_perm(nlive, k), e = 0;
                 for (int j = 0, seen = 0; j < nents; j++) {
@@ -342,7 +338,7 @@ struct Climber {
                 float px = __fmul_rn(__fadd_rn(s.ent_x[e * N + env], off), UNIT_TO_PIXELS);
                 float py = __fmul_rn(__fadd_rn(s.ent_y[e * N + env], off), UNIT_TO_PIXELS);
                 float sc = __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 1.0f), UNIT_TO_PIXELS), (float)tex[t].w);
-                b = make_blit(tex, t, px, py, cam, sc, 1.0f, s.ent_flip[e * N + env] != 0);
+                b.plain(t, px, py, cam, sc, 1.0f, s.ent_flip[e * N + env] != 0);
             } else {
                 float avx = s.avx[env];
                 bool on_ground = s.on_ground[env] != 0;
@@ -350,10 +346,9 @@ struct Climber {
                 int t = T_AGENT0 + 4 * s.agent_theme[env] + pose;
                 float px = __fmul_rn(__fsub_rn(s.ax[env], 0.5f), UNIT_TO_PIXELS);
                 float py = __fmul_rn(__fsub_rn(s.ay[env], 1.0f), UNIT_TO_PIXELS);
-                b = make_blit(tex, t, px, py, cam, __fdiv_rn(__fmul_rn(0.8f, UNIT_TO_PIXELS), (float)tex[t].w), 1.0f, s.face_forward[env] == 0);
+                b.plain(t, px, py, cam, __fdiv_rn(__fmul_rn(0.8f, UNIT_TO_PIXELS), (float)tex[t].w), 1.0f, s.face_forward[env] == 0);
             }
         });
-        __syncthreads();
     }
 };
 

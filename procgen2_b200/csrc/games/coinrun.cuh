@@ -457,15 +457,11 @@ struct CoinRun {
         // a reset (life = 0), so nothing is emitted either way.
         const int npart_slots = s.num_mobs[env] * NPART;
         const int nsprite = sprites ? nents : 0;
-        if (is_role(1)) {
-            f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = 1;
-            int bg = T_BG0 + s.bg_index[env];
-            TexInfo bt = tex[bg];
-            float extra = __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f);
-            f.pre[0] = make_blit(tex, bg, __fmul_rn(-s.bg_offset[env], extra), 0.0f, cam,
-                                 __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h));
-            f.npre = 1;
-        }
+        // background (e.g. maze.cpp:402-408): the blit itself is built by build_tile_layer below
+        const int bg = T_BG0 + s.bg_index[env];
+        const TexInfo bt = tex[bg];
+        const float bg_x = __fmul_rn(-s.bg_offset[env], __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f));
+        const float bg_scale = __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h);
         (void)nmobs;
         // tile layer: every tile texture is 128x128
         const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
@@ -476,9 +472,9 @@ struct CoinRun {
             const int id = raw & 15;
             return id == WALL_MID ? T_WALL_MID0 + theme : id == WALL_TOP ? T_WALL_TOP0 + theme : id == LAVA_MID ? (int)T_LAVA_MID
                  : id == LAVA_TOP ? (int)T_LAVA_TOP : id == CRATE ? T_CRATE0 + (raw >> 4) : (int)NO_TILE;
-        });
+        }, bg, bg_x, 0.0f, bg_scale);
         // post blits: particles (set order x slot), sprites (std::sort order), agent
-        emit_post_blits(f, npart_slots + nsprite + 1, [&](int k, Blit& b, BlitRot&) {
+        emit_post_blits(f, tex, npart_slots + nsprite + 1, [&](int k, BlitReq& b, BlitRot&) {
             if (k < npart_slots) {
                 int e = s.mob_order[(k / NPART) * N + env], i = k % NPART;
                 int pi = (e * NPART + i) * N + env;
@@ -491,7 +487,7 @@ struct CoinRun {
                     float pw = (float)tex[T_PARTICLE].w, ph = (float)tex[T_PARTICLE].h;
                     float px = __fsub_rn(__fmul_rn(s.part_x[pi], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(0.5f, pw), scale));
                     float py = __fsub_rn(__fmul_rn(__fadd_rn(s.part_y[pi], offset_y), UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(0.5f, ph), scale));
-                    b = make_blit(tex, T_PARTICLE, px, py, cam, __fdiv_rn(__fmul_rn(scale, UNIT_TO_PIXELS), pw), alpha);
+                    b.plain(T_PARTICLE, px, py, cam, __fdiv_rn(__fmul_rn(scale, UNIT_TO_PIXELS), pw), alpha);
                 }
             } else if (k < npart_slots + nsprite) {
                 int j = k - npart_slots;
@@ -502,7 +498,7 @@ struct CoinRun {
                 float px = __fmul_rn(__fadd_rn(s.ent_x[e * N + env], -0.5f), UNIT_TO_PIXELS);
                 float py = __fmul_rn(__fadd_rn(s.ent_y[e * N + env], -0.5f), UNIT_TO_PIXELS);
                 float sc = __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 1.0f), UNIT_TO_PIXELS), (float)tex[t].w);
-                b = make_blit(tex, t, px, py, cam, sc, 1.0f, s.ent_flip[e * N + env] != 0);
+                b.plain(t, px, py, cam, sc, 1.0f, s.ent_flip[e * N + env] != 0);
             } else {
                 // agent (common_systems.cpp:254-278)
                 float avx = s.avx[env];
@@ -511,10 +507,9 @@ struct CoinRun {
                 int t = T_AGENT0 + 4 * s.agent_theme[env] + pose;
                 float px = __fmul_rn(__fsub_rn(s.ax[env], 0.5f), UNIT_TO_PIXELS);
                 float py = __fmul_rn(__fsub_rn(s.ay[env], 2.0f), UNIT_TO_PIXELS);
-                b = make_blit(tex, t, px, py, cam, __fdiv_rn(UNIT_TO_PIXELS, (float)tex[t].w), 1.0f, s.face_forward[env] == 0);
+                b.plain(t, px, py, cam, __fdiv_rn(UNIT_TO_PIXELS, (float)tex[t].w), 1.0f, s.face_forward[env] == 0);
             }
         });
-        __syncthreads();
     }
 };
 

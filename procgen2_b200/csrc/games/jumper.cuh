@@ -359,23 +359,19 @@ struct Jumper {
         const int nspikes = s.num_spikes[env];
         const int nspr = c.sprites_valid[env] ? nspikes + 1 : 0;
         const int theme = s.map_theme[env];
-        if (is_role(1)) {
-            f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = 2;
-            int bg = T_BG0 + s.bg_index[env];
-            TexInfo bt = tex[bg];
-            float extra = __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f);
-            f.pre[0] = make_blit(tex, bg, __fmul_rn(-s.bg_offset[env], extra), 0.0f, cam,
-                                 __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h));
-            f.npre = 1;
-        }
+        // background (e.g. maze.cpp:402-408): the blit itself is built by build_tile_layer below
+        const int bg = T_BG0 + s.bg_index[env];
+        const TexInfo bt = tex[bg];
+        const float bg_x = __fmul_rn(-s.bg_offset[env], __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f));
+        const float bg_scale = __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h);
         const int o_spr = NPART, o_agent = o_spr + nspr, o_hud = o_agent + 1;
         // tile layer: class 0 = wall_mid texture of the theme, class 1 = wall_top texture
         const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
         build_tile_layer(f, cam, tex, 2, lx, ly, ncol, nrow, [&](int cls) { return (cls ? T_WALL_TOP0 : T_WALL_MID0) + theme; }, [&](int x, int y) {
             const int id = get(tiles, x, H - 1 - y);
             return id == WALL_MID ? T_WALL_MID0 + theme : id == WALL_TOP ? T_WALL_TOP0 + theme : (int)NO_TILE;
-        });
-        emit_post_blits(f, o_hud + 3, [&](int k, Blit& b, BlitRot& rot) {
+        }, bg, bg_x, 0.0f, bg_scale);
+        emit_post_blits(f, tex, o_hud + 3, [&](int k, BlitReq& b, BlitRot& rot) {
             if (k < o_spr) {   // System_Particles::render
                 int pi = k * N + env;
                 float life = s.p_life[pi];
@@ -387,19 +383,19 @@ struct Jumper {
                 float pw = (float)tex[T_PARTICLE].w, ph = (float)tex[T_PARTICLE].h;
                 float px = __fsub_rn(__fmul_rn(s.p_x[pi], UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(0.5f, pw), scale));
                 float py = __fsub_rn(__fmul_rn(__fadd_rn(s.p_y[pi], offset_y), UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(0.5f, ph), scale));
-                b = make_blit(tex, T_PARTICLE, px, py, cam, __fdiv_rn(__fmul_rn(scale, UNIT_TO_PIXELS), pw), alpha);
+                b.plain(T_PARTICLE, px, py, cam, __fdiv_rn(__fmul_rn(scale, UNIT_TO_PIXELS), pw), alpha);
             } else if (k < o_agent) {
                 int sp = s.sprite_order[sort_perm(nspr, k - o_spr) * N + env];
                 if (sp == 0) {
                     float px = __fmul_rn(__fadd_rn(s.goal_x[env], -0.5f), UNIT_TO_PIXELS);
                     float py = __fmul_rn(__fadd_rn(s.goal_y[env], -0.5f), UNIT_TO_PIXELS);
-                    b = make_blit(tex, T_CARROT, px, py, cam, __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 1.0f), UNIT_TO_PIXELS), (float)tex[T_CARROT].w));
+                    b.plain(T_CARROT, px, py, cam, __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 1.0f), UNIT_TO_PIXELS), (float)tex[T_CARROT].w));
                 } else {
                     int cell = s.spike_cell[(sp - 1) * N + env];
                     float sx = __fadd_rn((float)(cell / H), 0.5f), sy = __fadd_rn((float)(H - 1 - cell % H), 0.5f);
                     float px = __fmul_rn(__fadd_rn(sx, -0.25f), UNIT_TO_PIXELS);
                     float py = __fmul_rn(__fadd_rn(sy, -0.25f), UNIT_TO_PIXELS);
-                    b = make_blit(tex, T_SPIKE, px, py, cam, __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 0.4f), UNIT_TO_PIXELS), (float)tex[T_SPIKE].w));
+                    b.plain(T_SPIKE, px, py, cam, __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 0.4f), UNIT_TO_PIXELS), (float)tex[T_SPIKE].w));
                 }
             } else if (k == o_agent) {   // System_Agent::render
                 float avx = s.avx[env];
@@ -412,13 +408,13 @@ struct Jumper {
                 float posx = __fsub_rn(s.ax[env], 0.25f), posy = __fsub_rn(s.ay[env], 1.0f);
                 float px = __fmul_rn(__fadd_rn(posx, off_x), UNIT_TO_PIXELS);
                 float py = __fmul_rn(__fadd_rn(posy, off_y), UNIT_TO_PIXELS);
-                b = make_blit(tex, t, px, py, cam, __fmul_rn(__fdiv_rn(UNIT_TO_PIXELS, (float)tex[t].w), agent_scale), 1.0f, s.face_forward[env] == 0);
+                b.plain(t, px, py, cam, __fmul_rn(__fdiv_rn(UNIT_TO_PIXELS, (float)tex[t].w), agent_scale), 1.0f, s.face_forward[env] == 0);
             } else {   // compass HUD (jumper.cpp:474-509), obs target: width = 64, game_zoom = 0.3
                 const float compass_size = 200.0f, off_x = -32.0f, off_y = 32.0f, width = 64.0f;
                 const float tgx = s.to_goal_x[env], tgy = s.to_goal_y[env];
                 float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(tgx, tgx), __fmul_rn(tgy, tgy)));
                 if (k == o_hud) {
-                    b = make_blit_rect(tex, T_CIRCLE, __fadd_rn(__fsub_rn(width, __fmul_rn(compass_size, zoom)), __fmul_rn(off_x, zoom)),
+                    b.rect(T_CIRCLE, __fadd_rn(__fsub_rn(width, __fmul_rn(compass_size, zoom)), __fmul_rn(off_x, zoom)),
                                        __fmul_rn(off_y, zoom), __fmul_rn(compass_size, zoom), __fmul_rn(compass_size, zoom), 0.0, &rot);
                 } else if (k == o_hud + 1) {
                     float angle = (float)__ddiv_rn((double)__fmul_rn(glibc_atan2f(tgy, tgx), 180.0f), 3.14159265358979323846);
@@ -428,17 +424,16 @@ struct Jumper {
                     float y = __fadd_rn(__fmul_rn(__fmul_rn(compass_size, 0.5f), zoom), __fmul_rn(off_y, zoom));
                     x = __fadd_rn(x, __fmul_rn(__fmul_rn(__fmul_rn(compass_size, 0.25f), dir_x), zoom));
                     y = __fadd_rn(y, __fmul_rn(__fmul_rn(__fmul_rn(compass_size, 0.25f), dir_y), zoom));
-                    b = make_blit_rect(tex, T_NEEDLE, x, y, __fmul_rn(__fmul_rn(compass_size, 0.5f), zoom),
+                    b.rect(T_NEEDLE, x, y, __fmul_rn(__fmul_rn(compass_size, 0.5f), zoom),
                                        __fmul_rn(__fmul_rn(compass_size, 0.1f), zoom), (double)angle, &rot);
                 } else {
                     float ratio = fminf(1.0f, __fdiv_rn(dist, __fmul_rn((float)W, 1.414f)));
-                    b = make_blit_rect(tex, T_BAR, __fadd_rn(__fsub_rn(width, __fmul_rn(compass_size, zoom)), __fmul_rn(off_x, zoom)),
+                    b.rect(T_BAR, __fadd_rn(__fsub_rn(width, __fmul_rn(compass_size, zoom)), __fmul_rn(off_x, zoom)),
                                        __fadd_rn(__fmul_rn(compass_size, zoom), __fmul_rn(off_y, zoom)),
                                        __fmul_rn(__fmul_rn(compass_size, zoom), ratio), __fmul_rn(__fmul_rn(compass_size, 0.15f), zoom), 0.0, &rot);
                 }
             }
         });
-        __syncthreads();
     }
 };
 

@@ -161,36 +161,29 @@ struct Maze {
         int lx, ly, ux, uy;
         tile_window(cam, &lx, &ly, &ux, &uy);
         int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);
-        if (is_role(1)) {
-            f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = 1;
-            // background (maze.cpp:402-408)
-            int bg = T_BG0 + s.bg_index[env];
-            TexInfo bt = tex[bg];
-            float aspect = __fdiv_rn((float)bt.w, (float)bt.h);
-            float extra = __fsub_rn(aspect, 1.0f);
-            f.pre[0] = make_blit(tex, bg, __fmul_rn(-s.bg_offset[env], extra), 0.0f, cam,
-                                 __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h));
-            f.npre = 1;
-        }
+        // background (e.g. maze.cpp:402-408): the blit itself is built by build_tile_layer below
+        const int bg = T_BG0 + s.bg_index[env];
+        const TexInfo bt = tex[bg];
+        const float bg_x = __fmul_rn(-s.bg_offset[env], __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f));
+        const float bg_scale = __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h);
         const int ncheese = c.sprites_valid[env] ? 1 : 0;
         // tile layer (tilemap.cpp:111-131)
         const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
         build_tile_layer(f, cam, tex, 1, lx, ly, ncol, nrow, [](int) { return (int)T_WALL; },
-                         [&](int x, int y) { return get(tiles, x, WORLD - 1 - y) ? (int)T_WALL : (int)NO_TILE; });
-        emit_post_blits(f, ncheese + 1, [&](int k, Blit& b, BlitRot&) {
+                         [&](int x, int y) { return get(tiles, x, WORLD - 1 - y) ? (int)T_WALL : (int)NO_TILE; }, bg, bg_x, 0.0f, bg_scale);
+        emit_post_blits(f, tex, ncheese + 1, [&](int k, BlitReq& b, BlitRot&) {
             if (k < ncheese) {   // cheese (tilemap.cpp:95-98, common_systems.cpp:41-63)
                 float gx = __fmul_rn(__fadd_rn(s.goal_x[env], -0.48f), UNIT_TO_PIXELS);
                 float gy = __fmul_rn(__fadd_rn(s.goal_y[env], -0.5f), UNIT_TO_PIXELS);
                 float sc = __fdiv_rn(__fmul_rn(__fmul_rn(1.0f, 0.95f), UNIT_TO_PIXELS), (float)tex[T_CHEESE].w);
-                b = make_blit(tex, T_CHEESE, gx, gy, cam, sc);
+                b.plain(T_CHEESE, gx, gy, cam, sc);
             } else {             // agent (common_systems.cpp:138-151)
                 float ax = __fmul_rn(__fadd_rn(s.agent_x[env], -0.5f), UNIT_TO_PIXELS);
                 float ay = __fmul_rn(__fadd_rn(s.agent_y[env], -0.5f), UNIT_TO_PIXELS);
                 float sc = __fmul_rn(__fdiv_rn(UNIT_TO_PIXELS, (float)tex[T_MOUSE].w), 1.0f);
-                b = make_blit(tex, T_MOUSE, ax, ay, cam, sc, 1.0f, s.face_forward[env] != 0);
+                b.plain(T_MOUSE, ax, ay, cam, sc, 1.0f, s.face_forward[env] != 0);
             }
         });
-        __syncthreads();
     }
 };
 

@@ -83,7 +83,7 @@ struct Axis {
 // tex_len: texture extent on this axis, scale: render scale, flip: mirror the source rect
 // (horizontal flip only affects the x axis), y_axis selects the asymmetric cull test
 // (renderer.cpp:14: `dst.x > size.x || dst.y >= size.y`).
-PG2_DEV Axis make_axis(float pos, float cam, float cs, float size, int tex_len, float scale, bool flip, bool y_axis) {
+PG2_DEV_NOINLINE Axis make_axis(float pos, float cam, float cs, float size, int tex_len, float scale, bool flip, bool y_axis) {
     Axis a; a.visible = 0; a.d0 = 0; a.dlen = 0; a.s0 = 0; a.inc = 0;
     float src0 = 0.0f, srcl = (float)tex_len;
     float dst0 = __fadd_rn(__fmul_rn(__fsub_rn(pos, cam), cs), __fmul_rn(size, 0.5f));

@@ -72,7 +72,7 @@ PG2_DEV void render_body(const typename G::State& s, const CommonState& c, int e
         __syncthreads();
     }
     G::build_frame(s, c, env, f, tex);
-    __syncthreads();
+    __syncthreads();   // the only barrier between the frame builder's smem writes and their readers
     frame_finalize<G>(f);
     frame_rasterise<G>(f, atlas, obs + (size_t)env * OBS_BYTES);
 }

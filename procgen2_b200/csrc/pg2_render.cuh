@@ -65,12 +65,16 @@ constexpr int MAX_TILE_TEX = 32;
 // shape class (textures of one class share width and height) and candidate j (tile column clo + j) a validity bit
 // and the source texel x. vc masks are in "candidate index" form (candidate q = jr * 2 + jc): 0b0101 for jc = 0,
 // 0b1010 for jc = 1, so that (cw & rw) >> (8 + 4 * cls) is the set of candidates whose class-cls axes cover the pixel.
-struct alignas(16) ColDesc {
+// Stored as three word arrays indexed by col_slot(X), so that the 16 lanes of a row (lane l owns columns 4l .. 4l+3)
+// read consecutive words: no bank conflicts.
+struct ColDesc {
     uint32_t cw;       // clo | vc[0] << 8 | vc[1] << 12
     uint32_t csx;      // sx[cls][j] in byte cls * 2 + j
     int32_t pre_sx;    // background: source x under this column, -1: not covered
-    uint32_t pad;
 };
+PG2_DEV int col_slot(int X) { return (X >> 2) | (X & 3) << 4; }
+// Window cell: atlas offset of the tile's texture | blend << 28 | shape class << 29 | 1 << 31; 0 = no tile.
+constexpr uint32_t CELL_OFFSET_MASK = 0x0fffffffu, CELL_PRESENT = 0x80000000u;
 // Same for one screen row, plus the tile presence bitmaps of the two candidate tile rows (bit = tile column).
 struct alignas(16) RowDesc {
     uint32_t rw;       // rlo | vr[0] << 8 | vr[1] << 12   (0b0011 for jr = 0, 0b1100 for jr = 1)
@@ -86,7 +90,8 @@ struct FrameT {
     static constexpr int MAX_POST = MAXP, NROT = ROT ? MAXP : 1;
     static constexpr bool ROTATES = ROT;
     alignas(16) uint8_t rgb[OBS_BYTES];         // the frame, packed RGB rows
-    ColDesc cold[OBS_W];
+    uint32_t col_cw[OBS_W], col_csx[OBS_W];     // ColDesc fields, indexed by col_slot(X)
+    int32_t col_pre[OBS_W];
     RowDesc rowd[OBS_H];
     FastBlit fpost[MAXP];
     FastBlit fpre[MAX_PRE];
@@ -97,11 +102,11 @@ struct FrameT {
     int tx0, ty0, ncol, nrow, nclass;
     Axis col[2][MAX_WIN];
     Axis row[2][MAX_WIN];
-    uint8_t tile_tex[(MAX_WIN + 1) * MAX_WIN];  // tile texture id per window cell or NO_TILE (+1 row: branch-free reads)
+    uint32_t cell[(MAX_WIN + 1) * MAX_WIN];     // window cells (+1 row: branch-free reads)
     uint32_t rowmask[2][MAX_WIN + 1];           // [cls][tile row]: bit cx set = a class-cls tile at window column cx
     int cov_lo[2 * OBS_W], cov_hi[2 * OBS_W];   // [0,64): per screen column, [64,128): per screen row: covering tile range
     uint8_t bandmask[MAXP];                     // post blit k touches band b <=> bit b
-    int wcount[RENDER_THREADS / 32];            // emit_post_blits: visible blits per warp
+    int wcount[2][RENDER_THREADS / 32];         // emit_post_blits: visible blits per warp (double-buffered by round)
     int next_band;                              // dynamic hand-out of the row bands to warps
     int wide;                                   // the frame needs the general ordered path for every pixel (never observed)
     int pre_blend;                              // background texture carries alpha
@@ -240,28 +245,54 @@ PG2_DEV uint32_t blit_bands(const FastBlit& fb) {
     return ((2u << b1) - 1u) & ~((1u << b0) - 1u);
 }
 
+// What a game's frame builder asks for per post-blit candidate. The expensive part (make_blit and friends) is run by
+// emit_post_blits for all lanes of a warp TOGETHER, whatever kind of sprite each lane describes.
+struct BlitReq {
+    int mode;            // 0: nothing to draw, 1: render_texture, 2: render_texture_rotated, 3: explicit rect + angle
+    int tex_id;
+    float x, y, w, h;    // mode 1/2: world position in pixels (w, h unused); mode 3: float destination rect
+    float scale, alpha, rotation;
+    double angle_deg;
+    bool flip;
+    Camera cam;
+    PG2_DEV void plain(int t, float px, float py, const Camera& c, float sc, float al = 1.0f, bool fl = false) {
+        mode = 1; tex_id = t; x = px; y = py; cam = c; scale = sc; alpha = al; flip = fl;
+    }
+    PG2_DEV void rotated(int t, float px, float py, const Camera& c, float rot, float sc, float al, BlitRot*) {
+        mode = 2; tex_id = t; x = px; y = py; cam = c; rotation = rot; scale = sc; alpha = al; flip = false;
+    }
+    PG2_DEV void rect(int t, float dx, float dy, float dw, float dh, double ang, BlitRot*) {
+        mode = 3; tex_id = t; x = dx; y = dy; w = dw; h = dh; angle_deg = ang; flip = false;
+    }
+};
+
 // Ordered, compacting append of post blits by the whole CTA: candidate k (in the reference's
-// submission order) is evaluated by thread k % blockDim; only visible blits are stored, order
-// preserved through a warp ballot + a prefix over the warps' counts. make(k, blit, rot) fills the blit.
-// Must be called by every thread of the CTA, after a __syncthreads() that follows the frame's initialisation.
+// submission order) is described by thread k % blockDim (make(k, req, rot) fills the request or leaves it empty);
+// only visible blits are stored, order preserved through a warp ballot + a prefix over the warps' counts.
+// Must be called by every thread of the CTA, once per frame; ONE barrier per 128 candidates.
 template <class F, class MakeFn>
-PG2_DEV void emit_post_blits(F& f, int ncand, MakeFn make) {
+PG2_DEV void emit_post_blits(F& f, const TexInfo* tex, int ncand, MakeFn make) {
     const int tid = threadIdx.x, lane = tid % WARP_LANES, warp = tid / WARP_LANES;
     const int nwarps = ((int)blockDim.x + WARP_LANES - 1) / WARP_LANES;
-    int n = f.npost;
-    for (int base = 0; base < ncand; base += blockDim.x) {
+    int n = 0, round = 0;
+    for (int base = 0; base < ncand; base += blockDim.x, round ^= 1) {
         int k = base + tid;
-        Blit b; BlitRot rot;
-        b.ax.visible = 0; b.rotated = 0; rot.s = 0.0; rot.c = 1.0;
-        if (k < ncand) make(k, b, rot);
-        bool vis = k < ncand && b.ax.visible;
+        BlitReq req; BlitRot rot;
+        req.mode = 0; rot.s = 0.0; rot.c = 1.0;
+        if (k < ncand) make(k, req, rot);
+        Blit b;
+        b.ax.visible = 0;
+        if (req.mode == 1) b = make_blit(tex, req.tex_id, req.x, req.y, req.cam, req.scale, req.alpha, req.flip);
+        else if (req.mode == 2) b = make_blit_rotated(tex, req.tex_id, req.x, req.y, req.cam, req.rotation, req.scale, req.alpha, &rot);
+        else if (req.mode == 3) b = make_blit_rect(tex, req.tex_id, req.x, req.y, req.w, req.h, req.angle_deg, &rot);
+        bool vis = req.mode != 0 && b.ax.visible;
         FastBlit fb;
         if (vis) { fb = make_fast(b); vis = !(fb.flags & 4u); }
         uint32_t m = __ballot_sync(0xffffffffu, vis);
-        if (lane == 0) f.wcount[warp] = __popc(m);
+        if (lane == 0) f.wcount[round][warp] = __popc(m);
         __syncthreads();
         int before = 0, total = 0;
-        for (int w2 = 0; w2 < nwarps; w2++) { int cnt = f.wcount[w2]; if (w2 < warp) before += cnt; total += cnt; }
+        for (int w2 = 0; w2 < nwarps; w2++) { int cnt = f.wcount[round][w2]; if (w2 < warp) before += cnt; total += cnt; }
         if (vis) {
             int idx = n + before + __popc(m & ((1u << lane) - 1u));
             if (idx < F::MAX_POST) {
@@ -271,10 +302,8 @@ PG2_DEV void emit_post_blits(F& f, int ncand, MakeFn make) {
             }
         }
         n += total;
-        __syncthreads();
     }
     if (tid == 0) f.npost = n < F::MAX_POST ? n : F::MAX_POST;
-    __syncthreads();
 }
 
 // Tile window of System_Tilemap::render (tilemap.cpp:294-302): inclusive tile index range.
@@ -297,26 +326,41 @@ PG2_DEV void frame_begin(F& f) {
     for (int k = tid; k < 2 * OBS_W; k += blockDim.x) { f.cov_lo[k] = 255; f.cov_hi[k] = -1; }
 }
 
-// Tile layer of a frame (System_Tilemap::render, tilemap.cpp:294-320), called by every thread of the CTA from the
-// game's frame builder: the window's column / row axes per texture shape class (class_tex(cls) = a texture of that
-// class), the window's tile texture ids (tile_at(x, y) with x = window column + lx, y = render-space tile row) and the
-// per-row presence bitmaps. Every axis also registers itself in the covering range of the screen columns / rows it
-// touches (cov_lo / cov_hi, initialised by frame_begin).
+// Background + tile layer of a frame (the "pre" blit of render_game and System_Tilemap::render, tilemap.cpp:294-320),
+// called by every thread of the CTA from the game's frame builder:
+//   - the two axes of the background blit (texture bg_tex at world pixel position (bg_x, bg_y), scale bg_scale) and the
+//     window's column / row axes per texture shape class (class_tex(cls) = a texture of that class) are independent
+//     make_axis jobs: one job per thread, counted down from the CTA's LAST thread (the first warps build post blits
+//     meanwhile), all running the same instruction stream;
+//   - the window's cells (tile_at(x, y): tile texture id or NO_TILE; x = window column + lx, y = render-space tile row)
+//     and the per-row presence bitmaps, one warp per tile row.
+// Every tile axis also registers itself in the covering range of the screen columns / rows it touches
+// (cov_lo / cov_hi, initialised by frame_begin).
 template <class F, class ClassTex, class TileAt>
 PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int nclass, int lx, int ly, int ncol, int nrow,
-                              ClassTex class_tex, TileAt tile_at) {
+                              ClassTex class_tex, TileAt tile_at, int bg_tex, float bg_x, float bg_y, float bg_scale) {
     const int tid = threadIdx.x, lane = tid % WARP_LANES, warp = tid / WARP_LANES;
     const int nwarps = ((int)blockDim.x + WARP_LANES - 1) / WARP_LANES;
-    const int per = ncol + nrow;
-    for (int t = tid; t < nclass * per; t += blockDim.x) {
-        const int cls = t >= per ? 1 : 0, u = t - cls * per;
-        const TexInfo ti = tex[class_tex(cls)];
-        const float tscale = __fdiv_rn(UNIT_TO_PIXELS, (float)ti.w);
-        const bool is_row = u >= ncol;
-        Axis a;
-        if (!is_row) a = make_axis(__fmul_rn((float)(lx + u), UNIT_TO_PIXELS), cam.x, cam.scale, 64.0f, ti.w, tscale, false, false);
-        else a = make_axis(__fmul_rn((float)(ly + u - ncol), UNIT_TO_PIXELS), cam.y, cam.scale, 64.0f, ti.h, tscale, false, true);
+    const int per = ncol + nrow, njobs = 2 + nclass * per;
+    if (tid == 0) { f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = nclass; f.npre = 1; }
+    for (int job = (int)blockDim.x - 1 - tid; job < njobs; job += blockDim.x) {
+        const bool bg = job < 2;
+        const int t = job - 2, cls = (!bg && t >= per) ? 1 : 0, u = bg ? 0 : t - cls * per;
+        const bool is_row = bg ? job == 1 : u >= ncol;
         const int idx = is_row ? u - ncol : u;
+        const TexInfo ti = tex[bg ? bg_tex : class_tex(cls)];
+        const float scale = bg ? bg_scale : __fdiv_rn(UNIT_TO_PIXELS, (float)ti.w);
+        const float pos = bg ? (is_row ? bg_y : bg_x) : __fmul_rn((float)((is_row ? ly : lx) + idx), UNIT_TO_PIXELS);
+        const Axis a = make_axis(pos, is_row ? cam.y : cam.x, cam.scale, 64.0f, is_row ? ti.h : ti.w, scale, false, is_row);
+        if (bg) {
+            if (is_row) f.pre[0].ay = a;
+            else {   // the x-axis job also fills the rest of the blit (make_blit, alpha 1, no flip)
+                f.pre[0].ax = a;
+                f.pre[0].tex_offset = ti.offset; f.pre[0].tex_w = ti.w; f.pre[0].blend = (uint8_t)ti.blend;
+                f.pre[0].alpha_mod = 255; f.pre[0].flip_h = 0; f.pre[0].rotated = 0;
+            }
+            continue;
+        }
         if (is_row) f.row[cls][idx] = a; else f.col[cls][idx] = a;
         if (a.visible && a.d0 > -65536 && a.d0 < 65536 && a.dlen < 65536) {   // register in the covering ranges
             const int p0 = max(a.d0, 0), p1 = min(a.d0 + a.dlen - 1, OBS_W - 1), o = is_row ? OBS_W : 0;
@@ -328,9 +372,10 @@ PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int n
     for (int ry = warp; ry <= MAX_WIN; ry += nwarps) {
         uint32_t m0 = 0u, m1 = 0u;
         for (int cx = lane; cx < MAX_WIN; cx += WARP_LANES) {
-            uint8_t tt = (ry < nrow && cx < ncol) ? (uint8_t)tile_at(lx + cx, ly + ry) : NO_TILE;
-            f.tile_tex[ry * MAX_WIN + cx] = tt;
-            const bool c1 = tt != NO_TILE && f.tiletex[tt & (MAX_TILE_TEX - 1)].cls != 0;
+            const uint8_t tt = (ry < nrow && cx < ncol) ? (uint8_t)tile_at(lx + cx, ly + ry) : NO_TILE;
+            const TileTex ti = f.tiletex[tt & (MAX_TILE_TEX - 1)];
+            f.cell[ry * MAX_WIN + cx] = tt != NO_TILE ? (ti.offset | (uint32_t)ti.blend << 28 | (uint32_t)ti.cls << 29 | CELL_PRESENT) : 0u;
+            const bool c1 = tt != NO_TILE && ti.cls != 0;
             m0 |= lane_ballot(tt != NO_TILE && !c1, cx);
             m1 |= lane_ballot(c1, cx);
         }
@@ -351,7 +396,11 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
         if (!pre_ok) f.wide = 1;
         f.pre_blend = npre >= 1 ? f.pre[npre - 1].blend : 0;
     }
-    for (int k = tid; k < npre; k += blockDim.x) f.fpre[k] = make_fast(f.pre[k]);
+    for (int k = tid; k < npre; k += blockDim.x) {
+        Blit b = f.pre[k];
+        if (!b.ay.visible) b.ax.visible = 0;   // make_blit's rule (the two axes were built by different threads)
+        f.fpre[k] = make_fast(b);
+    }
     for (int k = tid; k < 2 * OBS_W; k += blockDim.x) {
         const bool is_row = k >= OBS_W;
         const int p = k & (OBS_W - 1);
@@ -382,7 +431,7 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
         if (npre >= 1 && pre_ok) {
             const Blit& b = f.pre[0];
             const Axis& a = is_row ? b.ay : b.ax;
-            if (b.ax.visible && (unsigned)(p - a.d0) < (unsigned)a.dlen) {
+            if (b.ax.visible && b.ay.visible && (unsigned)(p - a.d0) < (unsigned)a.dlen) {
                 int s = axis_sample(a, p, is_row ? false : (b.flip_h != 0));
                 pv = is_row ? (int32_t)(b.tex_offset + (uint32_t)s * b.tex_w) : s;
             }
@@ -396,9 +445,8 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
             rd.rm[1][0] = f.rowmask[1][r0]; rd.rm[1][1] = f.rowmask[1][r1];
             f.rowd[p] = rd;
         } else {
-            ColDesc cd;
-            cd.cw = word; cd.csx = smp[0]; cd.pre_sx = pv; cd.pad = 0u;
-            f.cold[p] = cd;
+            const int slot = col_slot(p);
+            f.col_cw[slot] = word; f.col_csx[slot] = smp[0]; f.col_pre[slot] = pv;
         }
     }
     if (lane == 0) frame_store_wait();   // this warp's bulk stores of the previous frame have read f.rgb
@@ -457,17 +505,24 @@ PG2_DEV uint32_t tile_candidates(const RowDesc& rd, uint32_t cw) {
     return p & 15u;
 }
 
+template <class F>
+PG2_DEV ColDesc load_col(const F& f, int X) {
+    const int slot = col_slot(X);
+    ColDesc cd;
+    cd.cw = f.col_cw[slot]; cd.csx = f.col_csx[slot]; cd.pre_sx = f.col_pre[slot];
+    return cd;
+}
+
 // Atlas index + blend flag of tile candidate q under a pixel.
 template <int NCLASS, class F>
 PG2_DEV uint32_t tile_texel_index(const F& f, const RowDesc& rd, const ColDesc& cd, uint32_t q, uint32_t* blend) {
     const uint32_t jr = q >> 1, jc = q & 1u;
-    const uint32_t t = f.tile_tex[((rd.rw & 31u) + jr) * MAX_WIN + (cd.cw & 31u) + jc];
-    const TileTex tt = f.tiletex[t & (MAX_TILE_TEX - 1)];
-    const uint32_t cls = NCLASS > 1 ? tt.cls : 0u;
+    const uint32_t w = f.cell[((rd.rw & 31u) + jr) * MAX_WIN + (cd.cw & 31u) + jc];
+    const uint32_t cls = NCLASS > 1 ? (w >> 29) & 1u : 0u;
     const uint32_t sx = (cd.csx >> ((cls * 2u + jc) * 8u)) & 255u;
     const uint32_t syw = ((cls ? rd.syw[1] : rd.syw[0]) >> (jr * 16u)) & 0xffffu;
-    *blend = tt.blend;
-    return tt.offset + syw + sx;
+    *blend = (w >> 28) & 1u;
+    return (w & CELL_OFFSET_MASK) + syw + sx;
 }
 
 // clear -> pre -> tiles of one pixel in reference (bottom-up) order with full blending: the path of pixels whose
@@ -483,7 +538,7 @@ PG2_DEV_NOINLINE uint32_t shade_base_ordered(const F& f, const uint32_t* __restr
     }
     if (!f.wide) {
         const RowDesc rd = f.rowd[Y];
-        const ColDesc cd = f.cold[X];
+        const ColDesc cd = load_col(f, X);
         uint32_t p = tile_candidates<G::TILE_CLASSES>(rd, cd.cw);
         for (uint32_t q = 0; q < 4u; q++)
             if (p >> q & 1u) {
@@ -496,16 +551,16 @@ PG2_DEV_NOINLINE uint32_t shade_base_ordered(const F& f, const uint32_t* __restr
     const int rlo = f.cov_lo[OBS_W + Y], rhi = f.cov_hi[OBS_W + Y], clo = f.cov_lo[X], chi = f.cov_hi[X];
     for (int ry = rlo; ry <= rhi; ry++)
         for (int cx = clo; cx <= chi; cx++) {
-            uint32_t t = f.tile_tex[ry * MAX_WIN + cx];
-            if (t == NO_TILE) continue;
-            const TileTex tt = f.tiletex[t];
-            const Axis& ax = f.col[tt.cls][cx];
-            const Axis& ay = f.row[tt.cls][ry];
+            const uint32_t w = f.cell[ry * MAX_WIN + cx];
+            if (!w) continue;
+            const uint32_t cls = (w >> 29) & 1u;
+            const Axis& ax = f.col[cls][cx];
+            const Axis& ay = f.row[cls][ry];
             if (!ax.visible || !ay.visible) continue;
             if ((unsigned)(X - ax.d0) >= (unsigned)ax.dlen || (unsigned)(Y - ay.d0) >= (unsigned)ay.dlen) continue;
             int sx = axis_sample(ax, X, false), sy = axis_sample(ay, Y, false);
-            texel = __ldg(atlas + tt.offset + (uint32_t)sy * tt.w + (uint32_t)sx);
-            color = blend_packed(color, texel, tt.blend, 255u);
+            texel = __ldg(atlas + (w & CELL_OFFSET_MASK) + (uint32_t)sy * (uint32_t)f.class_w[cls] + (uint32_t)sx);
+            color = blend_packed(color, texel, (w >> 28) & 1u, 255u);
         }
     return color;
 }
@@ -515,7 +570,7 @@ PG2_DEV_NOINLINE uint32_t shade_base_ordered(const F& f, const uint32_t* __restr
 template <class G, class F>
 PG2_DEV_NOINLINE uint32_t shade_base_continue(const F& f, const uint32_t* __restrict__ atlas, int X, int Y, uint32_t p) {
     const RowDesc rd = f.rowd[Y];
-    const ColDesc cd = f.cold[X];
+    const ColDesc cd = load_col(f, X);
     while (p) {
         const uint32_t q = bfind(p);
         p &= ~(1u << q);
@@ -548,7 +603,8 @@ PG2_DEV void raster_band_base(F& f, const uint32_t* __restrict__ atlas, int band
                 bool fetched[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const ColDesc cd = f.cold[X0 + i];
+                    ColDesc cd;   // col_slot(X0 + i) = (l & 15) + 16 * i
+                    cd.cw = f.col_cw[(l & 15) + 16 * i]; cd.csx = f.col_csx[(l & 15) + 16 * i]; cd.pre_sx = f.col_pre[(l & 15) + 16 * i];
                     const uint32_t p = tile_candidates<NCLASS>(rd, cd.cw);
                     cand[i] = p;
                     uint32_t tb;
