@@ -83,7 +83,7 @@ struct Axis {
 // tex_len: texture extent on this axis, scale: render scale, flip: mirror the source rect
 // (horizontal flip only affects the x axis), y_axis selects the asymmetric cull test
 // (renderer.cpp:14: `dst.x > size.x || dst.y >= size.y`).
-PG2_DEV_NOINLINE Axis make_axis(float pos, float cam, float cs, float size, int tex_len, float scale, bool flip, bool y_axis) {
+PG2_DEV Axis make_axis_inl(float pos, float cam, float cs, float size, int tex_len, float scale, bool flip, bool y_axis) {
     Axis a; a.visible = 0; a.d0 = 0; a.dlen = 0; a.s0 = 0; a.inc = 0;
     float src0 = 0.0f, srcl = (float)tex_len;
     float dst0 = __fadd_rn(__fmul_rn(__fsub_rn(pos, cam), cs), __fmul_rn(size, 0.5f));
@@ -122,6 +122,18 @@ PG2_DEV_NOINLINE Axis make_axis(float pos, float cam, float cs, float size, int 
     a.inc = fixed_inc(sl, dl);
     a.visible = 1;
     return a;
+}
+
+PG2_DEV_NOINLINE Axis make_axis(float pos, float cam, float cs, float size, int tex_len, float scale, bool flip, bool y_axis) {
+    return make_axis_inl(pos, cam, cs, size, tex_len, scale, flip, y_axis);
+}
+
+// Both axes of Renderer::render_texture in one function body: the two chains are independent, so their long
+// dependent float sequences interleave (twice the instruction-level parallelism of two make_axis calls).
+PG2_DEV_NOINLINE void make_axis_xy(float px, float py, float cam_x, float cam_y, float cs, int tex_w, int tex_h, float scale,
+                                   bool flip_h, Axis* ax, Axis* ay) {
+    *ax = make_axis_inl(px, cam_x, cs, 64.0f, tex_w, scale, flip_h, false);
+    *ay = make_axis_inl(py, cam_y, cs, 64.0f, tex_h, scale, false, true);
 }
 
 // Axis of a blit whose float destination rect is given directly and whose source is the whole

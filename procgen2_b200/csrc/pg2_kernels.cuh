@@ -61,7 +61,7 @@ PG2_DEV void reset_body(const typename G::State& s, const CommonState& c, int en
 }
 
 template <class G>
-using FrameOf = FrameT<G::MAX_POST, G::ROTATES>;
+using FrameOf = FrameT<G::MAX_POST, G::ROTATES, G::TILE_CLASSES>;
 
 // render_game(true) + RGBA->RGB pack for one env by one CTA (f.tiletex filled by frame_init_tiletex before)
 template <class G>

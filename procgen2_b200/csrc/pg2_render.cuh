@@ -58,7 +58,6 @@ struct alignas(16) FastBlit {
     uint16_t tex_w; uint8_t flags, alpha_mod;   // flags: 1 blend, 2 rotated, 4 invisible
 };
 
-struct TileTex { uint32_t offset; uint16_t w; uint8_t blend, cls; };   // tile textures: ids < MAX_TILE_TEX
 constexpr int MAX_TILE_TEX = 32;
 
 // Tile layer + background under one screen column: clo = first covering tile column of the window; per texture
@@ -85,11 +84,11 @@ struct alignas(16) RowDesc {
 
 // Frame description of ONE environment, in shared memory. MAXP = capacity of the post-blit list (per game),
 // ROT = whether the game ever rotates a blit (bossfight, caveflyer, jumper HUD).
-template <int MAXP, bool ROT>
+template <int MAXP, bool ROT, int NCLS>
 struct FrameT {
     static constexpr int MAX_POST = MAXP, NROT = ROT ? MAXP : 1;
     static constexpr bool ROTATES = ROT;
-    alignas(16) uint8_t rgb[OBS_BYTES];         // the frame, packed RGB rows
+    alignas(16) uint8_t band_rgb[RENDER_THREADS / 32][BAND_BYTES];   // per warp: the band it is drawing, packed RGB rows
     uint32_t col_cw[OBS_W], col_csx[OBS_W];     // ColDesc fields, indexed by col_slot(X)
     int32_t col_pre[OBS_W];
     RowDesc rowd[OBS_H];
@@ -100,8 +99,8 @@ struct FrameT {
     int npre, npost;
     // tile layer: window origin (tile coordinates, y in render space), extents, descriptors per texture shape class
     int tx0, ty0, ncol, nrow, nclass;
-    Axis col[2][MAX_WIN];
-    Axis row[2][MAX_WIN];
+    Axis col[NCLS][MAX_WIN];
+    Axis row[NCLS][MAX_WIN];
     uint32_t cell[(MAX_WIN + 1) * MAX_WIN];     // window cells (+1 row: branch-free reads)
     uint32_t rowmask[2][MAX_WIN + 1];           // [cls][tile row]: bit cx set = a class-cls tile at window column cx
     int cov_lo[2 * OBS_W], cov_hi[2 * OBS_W];   // [0,64): per screen column, [64,128): per screen row: covering tile range
@@ -111,7 +110,7 @@ struct FrameT {
     int wide;                                   // the frame needs the general ordered path for every pixel (never observed)
     int pre_blend;                              // background texture carries alpha
     int class_w[2];                             // texture width of the tile shape classes
-    TileTex tiletex[MAX_TILE_TEX];              // per CTA (filled once): atlas offset / stride / blend / class
+    uint32_t tileword[MAX_TILE_TEX];            // per CTA (filled once): window cell word of every tile texture id
 };
 
 // Deterministic sin/cos in degrees, mirrored operation by operation from oracle/raster.c
@@ -161,8 +160,7 @@ PG2_DEV Blit make_blit(const TexInfo* tex, int tex_id, float px, float py, const
                                           float scale, float alpha = 1.0f, bool flip_h = false) {
     TexInfo t = tex[tex_id];
     Blit b;
-    b.ax = make_axis(px, cam.x, cam.scale, 64.0f, t.w, scale, flip_h, false);
-    b.ay = make_axis(py, cam.y, cam.scale, 64.0f, t.h, scale, false, true);
+    make_axis_xy(px, py, cam.x, cam.y, cam.scale, t.w, t.h, scale, flip_h, &b.ax, &b.ay);
     if (!b.ay.visible) b.ax.visible = 0;
     b.tex_offset = t.offset; b.tex_w = t.w; b.blend = (uint8_t)t.blend;
     // `SDL_SetTextureAlphaMod(tex, 255 * alpha)`: float -> Uint8 truncation (renderer.cpp:57)
@@ -368,16 +366,16 @@ PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int n
         }
     }
     for (int cls = tid; cls < nclass; cls += blockDim.x) f.class_w[cls] = tex[class_tex(cls)].w;
-    // window cells: one warp per tile row, lanes = tile columns
-    for (int ry = warp; ry <= MAX_WIN; ry += nwarps) {
+    // window cells: one warp per tile row, lanes = tile columns (rows >= nrow are never referenced: the always-empty
+    // row MAX_WIN stands in for them, see frame_finalize)
+    for (int ry = warp; ry < nrow; ry += nwarps) {
         uint32_t m0 = 0u, m1 = 0u;
         for (int cx = lane; cx < MAX_WIN; cx += WARP_LANES) {
-            const uint8_t tt = (ry < nrow && cx < ncol) ? (uint8_t)tile_at(lx + cx, ly + ry) : NO_TILE;
-            const TileTex ti = f.tiletex[tt & (MAX_TILE_TEX - 1)];
-            f.cell[ry * MAX_WIN + cx] = tt != NO_TILE ? (ti.offset | (uint32_t)ti.blend << 28 | (uint32_t)ti.cls << 29 | CELL_PRESENT) : 0u;
-            const bool c1 = tt != NO_TILE && ti.cls != 0;
-            m0 |= lane_ballot(tt != NO_TILE && !c1, cx);
-            m1 |= lane_ballot(c1, cx);
+            const uint32_t tt = cx < ncol ? (uint32_t)tile_at(lx + cx, ly + ry) : (uint32_t)NO_TILE;
+            const uint32_t w = tt != NO_TILE ? f.tileword[tt & (MAX_TILE_TEX - 1)] : 0u;
+            f.cell[ry * MAX_WIN + cx] = w;
+            m0 |= lane_ballot(w != 0u && !(w >> 29 & 1u), cx);
+            m1 |= lane_ballot((w >> 29 & 1u) != 0u, cx);
         }
         if (lane == 0) { f.rowmask[0][ry] = m0; f.rowmask[1][ry] = m1; }
     }
@@ -388,7 +386,7 @@ PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int n
 // After the game's frame builder (and a __syncthreads()): ColDesc / RowDesc of every screen column / row.
 template <class G, class F>
 PG2_DEV_NOINLINE void frame_finalize(F& f) {
-    const int tid = threadIdx.x, lane = tid % WARP_LANES;
+    const int tid = threadIdx.x;
     const int npre = f.npre, nclass = f.nclass;
     // the fast path handles ONE un-rotated background with alpha_mod 255
     const bool pre_ok = npre == 0 || (npre == 1 && !f.pre[0].rotated && f.pre[0].alpha_mod == 255);
@@ -449,7 +447,6 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
             f.col_cw[slot] = word; f.col_csx[slot] = smp[0]; f.col_pre[slot] = pv;
         }
     }
-    if (lane == 0) frame_store_wait();   // this warp's bulk stores of the previous frame have read f.rgb
     __syncthreads();
 }
 
@@ -587,9 +584,9 @@ PG2_DEV_NOINLINE uint32_t shade_base_continue(const F& f, const uint32_t* __rest
     return a ? shade_base_ordered<G>(f, atlas, X, Y) : 0u;
 }
 
-// Base pass of one band: clear + background + tile layer of 8 rows, packed into f.rgb.
+// Base pass of one band: clear + background + tile layer of 8 rows, packed into the warp's band buffer.
 template <class G, class F>
-PG2_DEV void raster_band_base(F& f, const uint32_t* __restrict__ atlas, int band, int lane) {
+PG2_DEV void raster_band_base(F& f, const uint32_t* __restrict__ atlas, int band, int lane, uint8_t* buf) {
     constexpr int NCLASS = G::TILE_CLASSES;
     const bool wide = f.wide != 0;
     const uint32_t pre_blend = (uint32_t)f.pre_blend;
@@ -628,16 +625,16 @@ PG2_DEV void raster_band_base(F& f, const uint32_t* __restrict__ atlas, int band
 #pragma unroll
                 for (int i = 0; i < 4; i++) color[i] = shade_base_ordered<G>(f, atlas, X0 + i, Y);
             }
-            uint32_t* out = (uint32_t*)(f.rgb + 3 * (Y * OBS_W + X0));
+            uint32_t* out = (uint32_t*)(buf + 3 * ((it * 2 + (l >> 4)) * OBS_W + X0));
             out[0] = byte_perm(color[0], color[1], 0x4210u);
             out[1] = byte_perm(color[1], color[2], 0x5421u);
             out[2] = byte_perm(color[2], color[3], 0x6542u);
         }
 }
 
-// One post blit onto the rows [Y0, Y0 + 8) of f.rgb: lanes = an 8x4 patch of the destination rectangle.
+// One post blit onto the rows [Y0, Y0 + 8) (the band buffer): lanes = an 8x4 patch of the destination rectangle.
 template <class F>
-PG2_DEV void draw_blit_band(F& f, const uint32_t* __restrict__ atlas, int k, int Y0, int lane) {
+PG2_DEV void draw_blit_band(F& f, const uint32_t* __restrict__ atlas, int k, int Y0, int lane, uint8_t* buf) {
     const FastBlit fb = f.fpost[k];
     const BlitRot* rot = &f.post_rot[F::ROTATES ? k : 0];
     int x0 = fb.x0, y0 = fb.y0, x1 = fb.x0 + fb.w - 1, y1 = fb.y0 + fb.h - 1;
@@ -655,7 +652,7 @@ PG2_DEV void draw_blit_band(F& f, const uint32_t* __restrict__ atlas, int k, int
                 uint32_t texel;
                 if (X <= x1 && Y <= y1 && fast_texel<F::ROTATES>(fb, rot, atlas, X, Y, &texel)) {
                     const uint32_t a = layer_alpha(texel, blend, alpha_mod);
-                    uint8_t* px = f.rgb + 3 * (Y * OBS_W + X);
+                    uint8_t* px = buf + 3 * ((Y - Y0) * OBS_W + X);
                     if (a == 255u) { px[0] = (uint8_t)texel; px[1] = (uint8_t)(texel >> 8); px[2] = (uint8_t)(texel >> 16); }
                     else if (a != 0u) {
                         uint32_t r = px[0], g = px[1], b = px[2];
@@ -667,19 +664,18 @@ PG2_DEV void draw_blit_band(F& f, const uint32_t* __restrict__ atlas, int k, int
     __syncwarp();
 }
 
-// The finished band leaves the SM as one 1 536-byte TMA bulk store shared -> global (async proxy). The copy is only
-// ISSUED here (by the warp that drew the band); the warp waits (frame_store_wait) right before the CTA starts to
-// overwrite f.rgb with the next frame, so the drain of the staging buffer overlaps useful work.
-template <class F>
-PG2_DEV void band_store(F& f, uint8_t* __restrict__ dst, int band, int lane) {
+// The finished band leaves the SM as one 1 536-byte TMA bulk store shared -> global (async proxy), issued by the warp
+// that drew it; the warp waits for the copy to have READ its band buffer right before it draws into the buffer again,
+// so the drain overlaps the ticket / descriptor work in between.
+PG2_DEV void band_store(uint8_t* __restrict__ dst, const uint8_t* buf, int lane) {
 #ifdef PG2_HOSTSIM
-    memcpy(dst + band * BAND_BYTES, f.rgb + band * BAND_BYTES, BAND_BYTES);
+    memcpy(dst, buf, BAND_BYTES);
 #else
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
     __syncwarp();
     if (lane == 0) {
-        uint32_t src = (uint32_t)__cvta_generic_to_shared(f.rgb + band * BAND_BYTES);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + band * BAND_BYTES), "r"(src), "n"(BAND_BYTES) : "memory");
+        uint32_t src = (uint32_t)__cvta_generic_to_shared(buf);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "n"(BAND_BYTES) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
 #endif
@@ -690,13 +686,14 @@ PG2_DEV void band_store(F& f, uint8_t* __restrict__ dst, int band, int lane) {
 template <class G, class F>
 PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas, uint8_t* __restrict__ dst) {
     const int lane = threadIdx.x % WARP_LANES;
+    uint8_t* buf = f.band_rgb[threadIdx.x / WARP_LANES % (RENDER_THREADS / 32)];
     const int npost = f.npost;
     for (;;) {
         int band = 0;
-        if (lane == 0) band = smem_atomic_inc(&f.next_band);
+        if (lane == 0) { band = smem_atomic_inc(&f.next_band); frame_store_wait(); }   // the previous band has left the buffer
         band = warp_bcast(band);
         if (band >= NUM_BANDS) break;
-        raster_band_base<G>(f, atlas, band, lane);
+        raster_band_base<G>(f, atlas, band, lane, buf);
         __syncwarp();
         for (int base = 0; base < npost; base += 32) {
             uint32_t m = 0u;
@@ -707,26 +704,26 @@ PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas, 
             while (m) {
                 const int k = base + __ffs(m) - 1;
                 m &= m - 1u;
-                draw_blit_band(f, atlas, k, band * BAND_ROWS, lane);
+                draw_blit_band(f, atlas, k, band * BAND_ROWS, lane, buf);
             }
         }
-        band_store(f, dst, band, lane);
+        band_store(dst + band * BAND_BYTES, buf, lane);
     }
 }
 
-// Per-CTA table of the game's tile textures (ids < MAX_TILE_TEX), filled once before the first frame.
+// Per-CTA table of the game's tile textures (ids < MAX_TILE_TEX) as window cell words, filled once before the first frame.
 template <class G, class F>
 PG2_DEV void frame_init_tiletex(F& f, const TexInfo* __restrict__ tex) {
     for (int t = threadIdx.x; t < MAX_TILE_TEX; t += blockDim.x) {
-        TileTex tt;
-        tt.offset = 0; tt.w = 0; tt.blend = 0; tt.cls = 0;
+        uint32_t w = 0u;
         if (t < G::NUM_TEX) {
-            TexInfo ti = tex[t];
-            tt.offset = ti.offset; tt.w = ti.w; tt.blend = ti.blend ? 1 : 0;
-            tt.cls = (uint8_t)((G::TILE_CLASSES > 1) ? G::tile_class((uint32_t)t) : 0);
+            const TexInfo ti = tex[t];
+            const uint32_t cls = (G::TILE_CLASSES > 1) ? (uint32_t)G::tile_class((uint32_t)t) : 0u;
+            w = (ti.offset & CELL_OFFSET_MASK) | (ti.blend ? 1u << 28 : 0u) | cls << 29 | CELL_PRESENT;
         }
-        f.tiletex[t] = tt;
+        f.tileword[t] = w;
     }
+    for (int k = threadIdx.x; k < 2; k += blockDim.x) f.rowmask[k][MAX_WIN] = 0u;   // the always-empty tile row
     __syncthreads();
 }
 
