@@ -284,21 +284,27 @@ struct Jumper {
                 }
             }
         }
-        for (int x = 0; x < W; x++)
-            for (int y = 0; y < H; y++) {
-                if (map.left_wall(x, y) && map.left_wall(x, y + 1) && map.left_wall(x, y + 2)) {
-                    int d = w.rng.uniform_int(0, 2);
-                    __syncwarp();
-                    map.set(x, y + d, EMPTY);
-                    __syncwarp();
-                }
-                if (map.right_wall(x, y) && map.right_wall(x, y + 1) && map.right_wall(x, y + 2)) {
-                    int d = w.rng.uniform_int(0, 2);
-                    __syncwarp();
-                    map.set(x, y + d, EMPTY);
-                    __syncwarp();
-                }
+        // wall thinning (tilemap.cpp): cells in x-major order, per cell the left test then the right test, every hit
+        // draws from the RNG and clears a wall cell — which can enable as well as disable later tests. The warp tests
+        // 32 cells at a time on the CURRENT map, serves the first hit in order, and resumes right behind it.
+        {
+            int pos = 0, skip_left = 0;   // next cell to test; skip_left: its left test has been served already
+            while (pos < W * H) {
+                const int i = pos + lane, x = i / H, y = i % H;
+                const bool in = i < W * H;
+                const bool hl = in && !(lane == 0 && skip_left) && map.left_wall(x, y) && map.left_wall(x, y + 1) && map.left_wall(x, y + 2);
+                const bool hr = in && map.right_wall(x, y) && map.right_wall(x, y + 1) && map.right_wall(x, y + 2);
+                const uint32_t ml = lane_ballot(hl, lane), mr = lane_ballot(hr, lane);
+                if (!(ml | mr)) { pos += WARP_LANES; skip_left = 0; continue; }
+                const int l = __ffs(ml | mr) - 1, hit = pos + l, hx = hit / H, hy = hit % H;
+                const bool left = (ml >> l) & 1u;
+                int d = w.rng.uniform_int(0, 2);
+                __syncwarp();
+                map.set(hx, hy + d, EMPTY);
+                __syncwarp();
+                if (left) { pos = hit; skip_left = 1; } else { pos = hit + 1; skip_left = 0; }
             }
+        }
         const float agent_x = __fadd_rn((float)(agent_cell / H), 0.5f), agent_y = (float)(H - 1 - (agent_cell % H));
 
         int nspikes = warp_compact(w, W * H, [&](int i) { return tiles[i] == SPIKE && i != agent_cell && i != goal_cell; }, rg.queue);

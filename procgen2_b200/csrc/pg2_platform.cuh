@@ -28,6 +28,18 @@ __device__ __forceinline__ uint32_t lane_ballot(bool p, int /*vlane*/) { return 
 // index of the most significant set bit (0xffffffff for 0)
 __device__ __forceinline__ uint32_t bfind(uint32_t v) { uint32_t r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
 __device__ __forceinline__ uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+// Exclusive prefix sum of v over the warp's lanes; *total = the warp's sum. (Host-sim: one lane.)
+__device__ __forceinline__ int warp_excl_scan(int v, int* total) {
+    const int lane = threadIdx.x & 31;
+    int s = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, d); if (lane >= d) s += t; }
+    *total = __shfl_sync(0xffffffffu, s, 31);
+    return s - v;
+}
+// Lanes of the warp that hold the same key (the caller passes a lane-unique key for "no key").
+__device__ __forceinline__ uint32_t match_lanes(uint32_t key) { return __match_any_sync(0xffffffffu, key); }
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 }
 #else
 #include <math.h>
@@ -70,6 +82,9 @@ inline int smem_atomic_inc(int* p) { return (*p)++; }
 inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 inline uint32_t lane_ballot(bool p, int vlane) { return p ? 1u << vlane : 0u; }
+inline int warp_excl_scan(int v, int* total) { *total = v; return 0; }
+inline uint32_t match_lanes(uint32_t) { return 1u; }
+inline int lane_id() { return 0; }
 inline uint32_t bfind(uint32_t v) { return v ? 31u - (uint32_t)__builtin_clz(v) : 0xffffffffu; }
 inline uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
     uint64_t v = (uint64_t)b << 32 | a;

@@ -16,7 +16,7 @@
 namespace pg2 {
 
 constexpr int ROOM_DIM = 40, ROOM_CELLS = ROOM_DIM * ROOM_DIM;
-using RoomSet = USet<ROOM_CELLS, 2400>;
+constexpr int ROOM_MAX_BUCKETS = 2400;   // bucket count of a fresh unordered_set<int> holding <= 1600 keys: <= 2357
 
 // Atomically claim a byte flag (0 -> 1); true for the one thread that claimed it.
 PG2_DEV bool claim_cell(uint8_t* p) {
@@ -31,6 +31,105 @@ PG2_DEV bool claim_cell(uint8_t* p) {
 #endif
 }
 
+// ITERATION ORDER of a fresh std::unordered_set<int> (libstdc++ 13, see pg2_uset.cuh) after inserting the distinct
+// keys[0 .. n) in that order — computed by the whole warp instead of replaying n insertions.
+//   Both _M_insert_bucket_begin and _M_rehash_aux(unique) place a node at the BEGINNING of its bucket's group, or — for
+//   a bucket seen for the first time — at the very front of the list. Folding that rule over a sequence Q from an empty
+//   table with nb buckets therefore yields
+//       G(Q, nb) = groups by bucket (key % nb), groups in REVERSE order of first appearance in Q, each group in
+//                  REVERSE order of appearance,
+//   a rehash to nb' turns the list L into G(L, nb'), and the keys inserted until the next rehash extend that fold:
+//       L_i = G(L_{i-1} ++ batch_i, nb_i).
+//   For a fresh set every policy trigger is a rehash (load factor 1.0: 13, 29, 59, 127, 257, 541, 1109, 2357 buckets),
+//   so <= 9 regroupings, each a counting sort over positions (first position and size per bucket, a descending scan
+//   for the group offsets, a descending placement pass with in-warp ranking of equal buckets).
+// bufa / bufb: >= n keys each; first / cnt: >= ROOM_MAX_BUCKETS ints each. Returns the buffer holding the order.
+struct USetOrder {
+    PG2_DEV static int mod_by(int key, int n, uint32_t magic) {
+        if (n == 1) return 0;
+        uint32_t q = (uint32_t)(((uint64_t)(uint32_t)key * magic) >> 32);
+        int r = key - (int)q * n;
+        return r >= n ? r - n : (r < 0 ? r + n : r);
+    }
+
+    // out = G(q[0 .. n), nb)
+    PG2_DEV_NOINLINE static void regroup(WarpCtx& w, const uint16_t* q, int n, int nb, int* first, int* cnt, uint16_t* out) {
+        const int lane = w.lane;
+        const uint32_t magic = (uint32_t)(0xffffffffu / (uint32_t)nb) + 1u;
+        __syncwarp();
+        for (int b = lane; b < nb; b += WARP_LANES) { first[b] = 0x7fffffff; cnt[b] = 0; }
+        __syncwarp();
+        for (int j = lane; j < n; j += WARP_LANES) {
+            const int b = mod_by(q[j], nb, magic);
+            atomicMin(&first[b], j);
+            atomicAdd(&cnt[b], 1);
+        }
+        __syncwarp();
+        // group offsets: walk the positions downwards; a bucket's group starts where the groups of all buckets that
+        // first appear later end. Only the lane holding a bucket's first position touches cnt[b]: size -> offset in place.
+        int run = 0;
+        for (int base = n - 1; base >= 0; base -= WARP_LANES) {
+            const int j = base - lane;
+            const int b = j >= 0 ? mod_by(q[j], nb, magic) : 0;
+            const bool is_first = j >= 0 && first[b] == j;
+            int total;
+            const int excl = warp_excl_scan(is_first ? cnt[b] : 0, &total);
+            if (is_first) cnt[b] = run + excl;
+            run += total;
+        }
+        __syncwarp();
+        // placement, positions downwards again: cnt[b] = next free slot of the group
+        for (int base = n - 1; base >= 0; base -= WARP_LANES) {
+            const int j = base - lane;
+            const int b = j >= 0 ? mod_by(q[j], nb, magic) : 0;
+            const uint32_t same = match_lanes(j >= 0 ? (uint32_t)b : 0x80000000u | (uint32_t)lane);
+            const int rank = __popc(same & ((1u << lane) - 1u));   // lower lanes = later positions of the same bucket
+            const int slot = j >= 0 ? cnt[b] : 0;
+            __syncwarp();
+            if (j >= 0) {
+                out[slot + rank] = q[j];
+                if ((same >> lane) == 1u) cnt[b] = slot + rank + 1;   // the last lane of the bucket in this chunk
+            }
+            __syncwarp();
+        }
+    }
+
+    PG2_DEV_NOINLINE static uint16_t* order(WarpCtx& w, const uint16_t* keys, int n, uint16_t* bufa, uint16_t* bufb, int* first, int* cnt) {
+        uint16_t* cur = bufa;   // L_{i-1}, extended in place by the keys of the running batch
+        uint16_t* other = bufb;
+        int nb = 1, next_resize = 0, count = 0, listed = 0;   // listed = length of the grouped prefix of cur
+        int i = 0;
+        while (i < n) {
+            if (count + 1 > next_resize) {   // _Prime_rehash_policy::_M_need_rehash (load factor 1.0)
+                const int floor_bkts = next_resize ? 0 : 11;
+                const int min_bkts = count + 1 > floor_bkts ? count + 1 : floor_bkts;
+                if (min_bkts >= nb) {
+                    const int want = min_bkts + 1 > nb * 2 ? min_bkts + 1 : nb * 2;
+                    if (count > listed) {    // close the running batch under the old bucket count
+                        regroup(w, cur, count, nb, first, cnt, other);
+                        uint16_t* t = cur; cur = other; other = t;
+                    }
+                    listed = count;
+                    nb = USet<4, 4>::next_bkt(want, &next_resize);
+                } else {
+                    next_resize = nb;
+                }
+            }
+            int take = next_resize - count;
+            if (take > n - i) take = n - i;
+            __syncwarp();
+            for (int t = w.lane; t < take; t += WARP_LANES) cur[count + t] = keys[i + t];
+            __syncwarp();
+            i += take; count += take;
+        }
+        if (count > 0) {
+            regroup(w, cur, count, nb, first, cnt, other);
+            cur = other;
+        }
+        return cur;
+    }
+};
+
 struct RoomGen {
     int W, H;
     uint8_t* grid;        // [y + H * x]: 1 wall, 0 space
@@ -40,8 +139,10 @@ struct RoomGen {
     uint16_t* parents;
     uint16_t* order;      // best_room in unordered_set iteration order
     uint16_t* path;       // goal_path (src .. dst)
-    int* res;             // lane 0 -> all lanes: [0] best_room size, [1] path length
-    RoomSet* set;
+    uint16_t* seq;        // second key buffer of USetOrder
+    int* res;             // lane 0 -> all lanes: [0] best_room size, [1] path length, [2] BFS tail, [3] queue index of dst
+    int* claim;           // per cell: smallest (lane * 4 + neighbour) that wants it in the running BFS chunk
+    int* scratch;         // ROOM_MAX_BUCKETS ints (USetOrder)
 
     PG2_DEV_NOINLINE void init(WarpCtx& w, int width, int height) {
         W = width; H = height;
@@ -50,10 +151,12 @@ struct RoomGen {
         mark = w.alloc<uint8_t>(ROOM_CELLS);
         queue = w.alloc<uint16_t>(ROOM_CELLS + 64);
         parents = w.alloc<uint16_t>(ROOM_CELLS + 64);
-        order = w.alloc<uint16_t>(ROOM_CELLS);
+        order = w.alloc<uint16_t>(ROOM_CELLS + 64);
         path = w.alloc<uint16_t>(ROOM_CELLS + 64);
+        seq = w.alloc<uint16_t>(ROOM_CELLS + 64);
         res = w.alloc<int>(4);
-        set = w.alloc<RoomSet>(1);
+        claim = w.alloc<int>(ROOM_MAX_BUCKETS);     // ROOM_CELLS claims during a BFS, bucket table afterwards
+        scratch = w.alloc<int>(ROOM_MAX_BUCKETS);
     }
 
     PG2_DEV int get(int x, int y) const { return (x < 0 || y < 0 || x >= W || y >= H) ? 1 : grid[y + H * x]; }
@@ -72,98 +175,134 @@ struct RoomGen {
         __syncwarp();
     }
 
+    // The queue discipline of build_room / find_path (room_generator.cpp:38-78 / 80-141) by the whole warp:
+    // queue[0] = src, NOT marked (it re-enters the queue when a neighbour re-discovers it, Q19); 32 queued cells are
+    // expanded per round, a discovered cell goes to the expansion that comes first in the serial order (queue
+    // position, then neighbour order (x-1,y) (x,y-1) (x,y+1) (x+1,y)) through an atomicMin on claim[], and the
+    // winners are appended in exactly that order (prefix sum over the lanes' winner counts).
+    // Precondition: mark[] all 0. dst >= 0: stop once dst is queued (its parent chain is final), res[3] = its index.
+    // Returns the queue length; parents[] (if wanted) = queue index of the discoverer.
+    PG2_DEV_NOINLINE int bfs_ordered(WarpCtx& w, int src, int dst, bool with_parents) {
+        const int lane = w.lane, cells = W * H;
+        __syncwarp();
+        for (int i = lane; i < cells; i += WARP_LANES) claim[i] = 0x7fffffff;
+        if (lane == 0) { queue[0] = (uint16_t)src; parents[0] = 0xffff; res[3] = -1; }
+        __syncwarp();
+        int head = 0, tail = 1;
+        while (head < tail) {
+            const int chunk = tail - head < WARP_LANES ? tail - head : WARP_LANES;
+            const int q = head + lane;
+            const bool valid = lane < chunk;
+            const int cur = valid ? queue[q] : 0, x = cur / H, y = cur % H;
+            const int nx[4] = { x - 1, x, x, x + 1 }, ny[4] = { y, y - 1, y + 1, y };
+            int cell[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                cell[k] = -1;
+                if (valid && nx[k] >= 0 && ny[k] >= 0 && nx[k] < W && ny[k] < H) {
+                    const int nxt = ny[k] + H * nx[k];
+                    if (!mark[nxt] && grid[nxt] == 0) { cell[k] = nxt; atomicMin(&claim[nxt], lane * 4 + k); }
+                }
+            }
+            __syncwarp();
+            int wins = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (cell[k] >= 0 && claim[cell[k]] != lane * 4 + k) cell[k] = -1;
+                wins += cell[k] >= 0;
+            }
+            int total;
+            int pos = tail + warp_excl_scan(wins, &total);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (cell[k] >= 0) {
+                    queue[pos] = (uint16_t)cell[k];
+                    if (with_parents) parents[pos] = (uint16_t)q;
+                    mark[cell[k]] = 1;
+                    if (cell[k] == dst) res[3] = pos;
+                    pos++;
+                }
+            __syncwarp();
+            head += chunk; tail += total;
+            if (dst >= 0 && res[3] >= 0) break;
+        }
+        __syncwarp();
+        return tail;
+    }
+
     // Room_Generator::find_best_room -> order[0 .. n) = iteration order of best_room; returns n
     PG2_DEV_NOINLINE int find_best_room(WarpCtx& w) {
-        // pass 1 (lane-parallel, order-insensitive): size of every room in scan order. A one-cell room yields an
-        // EMPTY set (its start cell is never re-discovered); the first room always replaces the initial
-        // best_room_size of -1.
-        const int cells = W * H;
+        // pass 1 (order-insensitive): size of every room in scan order. A one-cell room yields an EMPTY set (its
+        // start cell is never re-discovered); the first room always replaces the initial best_room_size of -1.
+        const int cells = W * H, lane = w.lane;
         __syncwarp();
-        for (int i = w.lane; i < cells; i += WARP_LANES) mark[i] = 0;
+        for (int i = lane; i < cells; i += WARP_LANES) mark[i] = 0;
         __syncwarp();
         int best_start = -1, best_size = -1;
-        for (int i = 0; i < cells; i++) {
-            if (grid[i] != 0 || mark[i]) continue;          // uniform: every lane reads the same cell
-            __syncwarp();
-            if (w.lane == 0) { mark[i] = 1; queue[0] = (uint16_t)i; res[2] = 1; }
-            __syncwarp();
-            int head = 0, tail = 1;
-            while (head < tail) {                            // one BFS level chunk per iteration
-                for (int q = head + w.lane; q < tail; q += WARP_LANES) {
-                    int cur = queue[q], x = cur / H, y = cur % H;
-                    const int nx[4] = { x - 1, x, x, x + 1 }, ny[4] = { y, y - 1, y + 1, y };
-                    for (int k = 0; k < 4; k++) {
-                        if (nx[k] < 0 || ny[k] < 0 || nx[k] >= W || ny[k] >= H) continue;
-                        int nxt = ny[k] + H * nx[k];
-                        if (grid[nxt] == 0 && claim_cell(&mark[nxt])) queue[atomicAdd(&res[2], 1)] = (uint16_t)nxt;
+        for (int base = 0; base < cells; base += WARP_LANES) {
+            for (;;) {   // next unvisited space cell of this chunk, in scan order
+                const int i = base + lane;
+                const uint32_t m = lane_ballot(i < cells && grid[i] == 0 && !mark[i], lane);
+                if (!m) break;
+                const int start = base + __ffs(m) - 1;
+                __syncwarp();
+                if (lane == 0) { mark[start] = 1; queue[0] = (uint16_t)start; res[2] = 1; }
+                __syncwarp();
+                int head = 0, tail = 1;
+                while (head < tail) {                            // one BFS level chunk per iteration
+                    for (int q = head + lane; q < tail; q += WARP_LANES) {
+                        int cur = queue[q], x = cur / H, y = cur % H;
+                        const int nx[4] = { x - 1, x, x, x + 1 }, ny[4] = { y, y - 1, y + 1, y };
+                        for (int k = 0; k < 4; k++) {
+                            if (nx[k] < 0 || ny[k] < 0 || nx[k] >= W || ny[k] >= H) continue;
+                            int nxt = ny[k] + H * nx[k];
+                            if (grid[nxt] == 0 && claim_cell(&mark[nxt])) queue[atomicAdd(&res[2], 1)] = (uint16_t)nxt;
+                        }
                     }
+                    __syncwarp();
+                    head = tail; tail = res[2];
+                    __syncwarp();
                 }
-                __syncwarp();
-                head = tail; tail = res[2];
-                __syncwarp();
+                int size = tail >= 2 ? tail : 0;
+                if (size > best_size) { best_size = size; best_start = start; }
             }
-            int size = tail >= 2 ? tail : 0;
-            if (size > best_size) { best_size = size; best_start = i; }
         }
         __syncwarp();
-        for (int i = w.lane; i < cells; i += WARP_LANES) mark[i] = 0;
+        for (int i = lane; i < cells; i += WARP_LANES) mark[i] = 0;
         __syncwarp();
-        if (w.lane == 0) {
-            // pass 2 (ordered): the winning room again, exactly as build_room inserts it
-            int n = 0;
-            if (best_size > 0) {
-                set->init(1);
-                int head = 0, tail = 0;
-                queue[tail++] = (uint16_t)best_start;
-                while (head < tail) {
-                    int cur = queue[head++], x = cur / H, y = cur % H;
-                    const int nx[4] = { x - 1, x, x, x + 1 }, ny[4] = { y, y - 1, y + 1, y };
-                    for (int k = 0; k < 4; k++) {
-                        if (nx[k] < 0 || ny[k] < 0 || nx[k] >= W || ny[k] >= H) continue;
-                        int nxt = ny[k] + H * nx[k];
-                        if (!mark[nxt] && grid[nxt] == 0) { mark[nxt] = 1; queue[tail++] = (uint16_t)nxt; set->insert_new(nxt); }
-                    }
-                }
-                n = set->order(order);
-            }
-            res[0] = n;
+        // pass 2 (ordered): the winning room again, in the order build_room inserts it into the unordered_set
+        int n = 0;
+        if (best_size > 0) {
+            const int tail = bfs_ordered(w, best_start, -1, false);
+            n = tail - 1;                                        // every queued cell but the initial queue[0] was inserted
+            uint16_t* o = USetOrder::order(w, queue + 1, n, order, seq, claim, scratch);
+            __syncwarp();
+            if (o != order) for (int i = lane; i < n; i += WARP_LANES) order[i] = o[i];
+            __syncwarp();
         }
-        __syncwarp();
-        return res[0];
+        return n;
     }
 
     // Room_Generator::find_path -> path[0 .. len) from src to dst; returns len (0: none)
     PG2_DEV_NOINLINE int find_path(WarpCtx& w, int src, int dst) {
+        const int lane = w.lane;
         __syncwarp();
-        for (int i = w.lane; i < W * H; i += WARP_LANES) mark[i] = 0;   // `covered` (does not contain src)
+        for (int i = lane; i < W * H; i += WARP_LANES) mark[i] = 0;   // `covered` (does not contain src)
         __syncwarp();
-        if (w.lane == 0) {
-            int len = 0;
-            if (grid[src] == 0) {
-                int count = 0, search = 0;
-                queue[count] = (uint16_t)src; parents[count] = 0xffff; count++;
-                while (search < count) {
-                    int cur = queue[search];
-                    if (cur == dst) break;
-                    int x = cur / H, y = cur % H;
-                    const int nx[4] = { x - 1, x, x, x + 1 }, ny[4] = { y, y - 1, y + 1, y };
-                    for (int k = 0; k < 4; k++) {
-                        if (nx[k] < 0 || ny[k] < 0 || nx[k] >= W || ny[k] >= H) continue;
-                        int nxt = ny[k] + H * nx[k];
-                        if (!mark[nxt] && grid[nxt] == 0) {
-                            queue[count] = (uint16_t)nxt; parents[count] = (uint16_t)search; count++;
-                            mark[nxt] = 1;
-                        }
-                    }
-                    search++;
-                }
-                if (search < count && queue[search] == dst) {
-                    int k = search;
-                    while (k != 0xffff) { len++; k = parents[k]; }
-                    k = search;
-                    for (int j = len - 1; j >= 0; j--) { path[j] = queue[k]; k = parents[k]; }
-                }
-            }
+        if (grid[src] != 0) return 0;
+        int at = 0;                                                  // queue index of dst
+        if (src != dst) {
+            bfs_ordered(w, src, dst, true);
+            at = res[3];
+            if (at < 0) return 0;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int len = 0, k = at;
+            if (src == dst) { queue[0] = (uint16_t)src; parents[0] = 0xffff; }
+            while (k != 0xffff) { len++; k = parents[k]; }
+            k = at;
+            for (int j = len - 1; j >= 0; j--) { path[j] = queue[k]; k = parents[k]; }
             res[1] = len;
         }
         __syncwarp();

@@ -7,11 +7,15 @@
 // twists, tile-map fills, cellular-automaton passes, copies to HBM — by lane id.
 #pragma once
 #include "pg2_rng.cuh"
+#ifdef PG2_HOSTSIM
+#include <stdio.h>
+#include <stdlib.h>
+#endif
 
 namespace pg2 {
 
 constexpr int RESET_WARPS_PER_CTA = 2;
-constexpr int RESET_ARENA_BYTES = 40 * 1024;   // per-warp scratch
+constexpr int RESET_ARENA_BYTES = 52 * 1024;   // per-warp scratch
 
 struct WarpCtx {
     WarpMt rng;
@@ -23,6 +27,9 @@ struct WarpCtx {
     PG2_DEV_NOINLINE T* alloc(int count) {
         int off = (arena_off + 15) & ~15;
         arena_off = off + (int)sizeof(T) * count;
+#ifdef PG2_HOSTSIM
+        if (arena_off > RESET_ARENA_BYTES) { fprintf(stderr, "reset arena overflow: %d > %d\n", arena_off, RESET_ARENA_BYTES); abort(); }
+#endif
         return (T*)(arena + off);
     }
     template <class T>
