@@ -366,9 +366,9 @@ struct CaveFlyer {
         const float bg_x = __fmul_rn(-s.bg_offset[env], __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f));
         const float bg_scale = __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h);
         auto sprite_alive = [&](int sp) { return sp == 0 || s.obj_type[(sp - 1) * N + env] != O_NONE; };
-        int nlive = 0;
-        if (sprites)
-            for (int k = 0; k < nobj + 1; k++) nlive += sprite_alive(s.sprite_order[k * N + env]);
+        const int nlive = live_list(f, sprites ? nobj + 1 : 0, [&](int j) {
+            const int sp = s.sprite_order[j * N + env];
+            return sprite_alive(sp) ? sp : -1; });
         const int num_bullets = s.num_bullets[env], next_bullet = s.next_bullet[env];
         const int o_spr = NPART, o_bul = o_spr + nlive, o_ship = o_bul + num_bullets;
         const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
@@ -389,11 +389,7 @@ struct CaveFlyer {
                 float y = __fsub_rn(__fmul_rn(__fadd_rn(s.p_y[pi], __fmul_rn(s.p_dy[pi], shift)), UNIT_TO_PIXELS), __fmul_rn(__fmul_rn(size, ph), 0.5f));
                 b.rotated(T_PARTICLE, x, y, cam, s.p_rot[pi], size, alpha, &rot);
             } else if (k < o_bul) {
-                int want = sort_perm(nlive, k - o_spr), sp = 0;
-                for (int j = 0, seen = 0; j < nobj + 1; j++) {
-                    sp = s.sprite_order[j * N + env];
-                    if (sprite_alive(sp) && seen++ == want) break;
-                }
+                const int sp = f.live[sort_perm(nlive, k - o_spr)];
                 int t; float x, y;
                 if (sp == 0) { t = T_GOAL; x = s.goal_x[env]; y = s.goal_y[env]; }
                 else {

@@ -364,19 +364,15 @@ struct Chaser {
         const TexInfo bt = tex[bg];
         const float bg_x = __fmul_rn(-s.bg_offset[env], __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f));
         const float bg_scale = __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h);
-        int nlive = 0;
-        if (sprites)
-            for (int k = 0; k < nents; k++) nlive += s.ent_kind[s.sprite_order[k * N + env] * N + env] != K_NONE;
+        const int nlive = live_list(f, sprites ? nents : 0, [&](int j) {
+            const int e = s.sprite_order[j * N + env];
+            return s.ent_kind[e * N + env] != K_NONE ? e : -1; });
         const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
         build_tile_layer(f, cam, tex, 1, lx, ly, ncol, nrow, [](int) { return (int)T_WALL; },
                          [&](int x, int y) { return get(tiles, x, H - 1 - y) == 1 ? (int)T_WALL : (int)NO_TILE; }, bg, bg_x, 0.0f, bg_scale);
         emit_post_blits(f, tex, nlive + 1, [&](int k, BlitReq& b, BlitRot&) {
             if (k < nlive) {
-                int want = sort_perm(nlive, k), e = 0;
-                for (int j = 0, seen = 0; j < nents; j++) {
-                    e = s.sprite_order[j * N + env];
-                    if (s.ent_kind[e * N + env] != K_NONE && seen++ == want) break;
-                }
+                const int e = f.live[sort_perm(nlive, k)];
                 int kind = s.ent_kind[e * N + env];
                 int t; float x, y;
                 if (kind == K_MOB) {

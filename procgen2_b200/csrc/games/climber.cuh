@@ -112,7 +112,7 @@ struct Climber {
                 ax = __fadd_rn(ax, __fmul_rn(avx, dt));
                 ay = __fadd_rn(ay, __fmul_rn(avy, dt));
                 Rect world{ __fadd_rn(ax, -0.5f), __fadd_rn(ay, -1.0f), 1.0f, 1.0f };
-                CollisionResult cd = tile_collision(world, tile_at, wall);
+                CollisionResult cd = tile_collision(world, tile_at, wall, false, 0.0f, &ctx);
                 float dpx = __fsub_rn(cd.x, world.x), dpy = __fsub_rn(cd.y, world.y);
                 on_ground = dpy < 0.0f && cd.collided;
                 ax = __fsub_rn(cd.x, -0.5f);
@@ -316,9 +316,9 @@ struct Climber {
         const float bg_x = __fmul_rn(-s.bg_offset[env], __fsub_rn(__fdiv_rn((float)bt.w, (float)bt.h), 1.0f));
         const float bg_scale = __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h);
         // live sprites in set order; destroyed points simply drop out of the (order-preserving) set
-        int nlive = 0;
-        if (sprites)
-            for (int k = 0; k < nents; k++) nlive += s.ent_type[s.sprite_order[k * N + env] * N + env] != E_NONE;
+        const int nlive = live_list(f, sprites ? nents : 0, [&](int j) {
+            const int e = s.sprite_order[j * N + env];
+            return s.ent_type[e * N + env] != E_NONE ? e : -1; });
         // tile layer: class 0 = wall_mid texture of the theme, class 1 = wall_top texture
         const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
         build_tile_layer(f, cam, tex, 2, lx, ly, ncol, nrow, [&](int cls) { return (cls ? T_WALL_TOP0 : T_WALL_MID0) + theme; }, [&](int x, int y) {
@@ -327,11 +327,7 @@ struct Climber {
         }, bg, bg_x, 0.0f, bg_scale);
         emit_post_blits(f, tex, nlive + 1, [&](int k, BlitReq& b, BlitRot&) {
             if (k < nlive) {
-                int want = sort_perm(nlive, k), e = 0;
-                for (int j = 0, seen = 0; j < nents; j++) {
-                    e = s.sprite_order[j * N + env];
-                    if (s.ent_type[e * N + env] != E_NONE && seen++ == want) break;
-                }
+                const int e = f.live[sort_perm(nlive, k)];
                 int type = s.ent_type[e * N + env];
                 int t = type == E_POINT ? T_CRYSTAL : T_ENEMY0 + s.ent_frame[e * N + env];
                 float off = type == E_POINT ? -0.5f : -0.4f;

@@ -172,7 +172,7 @@ struct CoinRun {
                 Rect world{ __fadd_rn(ax, -0.5f), __fadd_rn(ay, -1.0f), 1.0f, 1.0f };
                 CollisionResult cd = tile_collision(world, tile_at,
                     [](int id) { return (id == WALL_MID || id == WALL_TOP) ? COLL_FULL : (id == CRATE ? COLL_DOWN_ONLY : COLL_NONE); },
-                    fallthrough, __fmul_rn(avy, dt));
+                    fallthrough, __fmul_rn(avy, dt), &ctx);
                 float dpx = __fsub_rn(cd.x, world.x), dpy = __fsub_rn(cd.y, world.y);
                 on_ground = dpy < 0.0f && cd.collided;
                 ax = __fsub_rn(cd.x, -0.5f);
@@ -200,7 +200,8 @@ struct CoinRun {
                 }
                 if (ctx.any(hit)) alive = false;
                 if (ctx.any(got)) achieved_goal = true;
-                CollisionResult lava = tile_collision(world, tile_at, [](int id) { return (id == LAVA_MID || id == LAVA_TOP) ? COLL_FULL : COLL_NONE; });
+                CollisionResult lava = tile_collision(world, tile_at, [](int id) { return (id == LAVA_MID || id == LAVA_TOP) ? COLL_FULL : COLL_NONE; },
+                                                      false, 0.0f, &ctx);
                 if (lava.collided) alive = false;
 
                 cam_x = __fmul_rn(ax, UNIT_TO_PIXELS);

@@ -40,6 +40,7 @@ __device__ __forceinline__ int warp_excl_scan(int v, int* total) {
 // Lanes of the warp that hold the same key (the caller passes a lane-unique key for "no key").
 __device__ __forceinline__ uint32_t match_lanes(uint32_t key) { return __match_any_sync(0xffffffffu, key); }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
 }
 #else
 #include <math.h>
@@ -85,6 +86,7 @@ inline uint32_t lane_ballot(bool p, int vlane) { return p ? 1u << vlane : 0u; }
 inline int warp_excl_scan(int v, int* total) { *total = v; return 0; }
 inline uint32_t match_lanes(uint32_t) { return 1u; }
 inline int lane_id() { return 0; }
+inline uint32_t warp_or(uint32_t v) { return v; }
 inline uint32_t bfind(uint32_t v) { return v ? 31u - (uint32_t)__builtin_clz(v) : 0xffffffffu; }
 inline uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
     uint64_t v = (uint64_t)b << 32 | a;

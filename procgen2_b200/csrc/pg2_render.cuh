@@ -105,6 +105,7 @@ struct FrameT {
     uint32_t rowmask[2][MAX_WIN + 1];           // [cls][tile row]: bit cx set = a class-cls tile at window column cx
     int cov_lo[2 * OBS_W], cov_hi[2 * OBS_W];   // [0,64): per screen column, [64,128): per screen row: covering tile range
     uint8_t bandmask[MAXP];                     // post blit k touches band b <=> bit b
+    uint8_t live[256];                          // live_list(): ids of the live sprites in set order
     int wcount[2][RENDER_THREADS / 32];         // emit_post_blits: visible blits per warp (double-buffered by round)
     int next_band;                              // dynamic hand-out of the row bands to warps
     int wide;                                   // the frame needs the general ordered path for every pixel (never observed)
@@ -304,6 +305,24 @@ PG2_DEV void emit_post_blits(F& f, const TexInfo* tex, int ncand, MakeFn make) {
     if (tid == 0) f.npost = n < F::MAX_POST ? n : F::MAX_POST;
 }
 
+// f.live[0 .. count) = the ids id_or_neg(j) >= 0, j < n, in order (the live members of an ECS set whose dead entries
+// are skipped by the reference's iteration). Every warp of the CTA computes the whole list redundantly — identical
+// values to identical addresses — so no CTA barrier is needed: a warp reads the list after its own __syncwarp().
+template <class F, class Fn>
+PG2_DEV int live_list(F& f, int n, Fn id_or_neg) {
+    const int lane = threadIdx.x % WARP_LANES;
+    int cnt = 0;
+    for (int base = 0; base < n; base += WARP_LANES) {
+        const int j = base + lane;
+        const int v = j < n ? id_or_neg(j) : -1;
+        const uint32_t m = lane_ballot(v >= 0, lane);
+        if (v >= 0 && cnt < 256) f.live[(cnt + __popc(m & ((1u << lane) - 1u))) & 255] = (uint8_t)v;
+        cnt += __popc(m);
+    }
+    __syncwarp();
+    return cnt;
+}
+
 // Tile window of System_Tilemap::render (tilemap.cpp:294-302): inclusive tile index range.
 PG2_DEV void tile_window(const Camera& cam, int* lower_x, int* lower_y, int* upper_x, int* upper_y) {
     float hx = __fdiv_rn(__fmul_rn(64.0f, 0.5f), cam.scale);
@@ -474,9 +493,9 @@ PG2_DEV bool fast_texel(const FastBlit& fb, const BlitRot* rot, const uint32_t* 
     return true;
 }
 
-// Effective alpha of a texel of a layer: 255 for opaque-copy textures, else A * alpha_mod / 255.
-PG2_DEV uint32_t layer_alpha(uint32_t texel, uint32_t blend, uint32_t alpha_mod) {
-    if (!blend) return 255u;
+// Effective alpha of a texel of a layer: A * alpha_mod / 255. Opaque-copy (RGB) textures are stored with A = 255 in
+// the atlas (assets.cpp), and SRC-over with alpha 255 IS the copy, so the blend flag never needs to be consulted.
+PG2_DEV uint32_t layer_alpha(uint32_t texel, uint32_t /*blend*/, uint32_t alpha_mod) {
     uint32_t ta = texel >> 24;
     return alpha_mod != 255u ? (ta * alpha_mod) / 255u : ta;
 }
@@ -510,15 +529,14 @@ PG2_DEV ColDesc load_col(const F& f, int X) {
     return cd;
 }
 
-// Atlas index + blend flag of tile candidate q under a pixel.
+// Atlas index of tile candidate q under a pixel.
 template <int NCLASS, class F>
-PG2_DEV uint32_t tile_texel_index(const F& f, const RowDesc& rd, const ColDesc& cd, uint32_t q, uint32_t* blend) {
+PG2_DEV uint32_t tile_texel_index(const F& f, const RowDesc& rd, const ColDesc& cd, uint32_t q) {
     const uint32_t jr = q >> 1, jc = q & 1u;
     const uint32_t w = f.cell[((rd.rw & 31u) + jr) * MAX_WIN + (cd.cw & 31u) + jc];
     const uint32_t cls = NCLASS > 1 ? (w >> 29) & 1u : 0u;
     const uint32_t sx = (cd.csx >> ((cls * 2u + jc) * 8u)) & 255u;
     const uint32_t syw = ((cls ? rd.syw[1] : rd.syw[0]) >> (jr * 16u)) & 0xffffu;
-    *blend = (w >> 28) & 1u;
     return (w & CELL_OFFSET_MASK) + syw + sx;
 }
 
@@ -539,9 +557,8 @@ PG2_DEV_NOINLINE uint32_t shade_base_ordered(const F& f, const uint32_t* __restr
         uint32_t p = tile_candidates<G::TILE_CLASSES>(rd, cd.cw);
         for (uint32_t q = 0; q < 4u; q++)
             if (p >> q & 1u) {
-                uint32_t blend;
-                texel = __ldg(atlas + tile_texel_index<G::TILE_CLASSES>(f, rd, cd, q, &blend));
-                color = blend_packed(color, texel, blend, 255u);
+                texel = __ldg(atlas + tile_texel_index<G::TILE_CLASSES>(f, rd, cd, q));
+                color = blend_packed(color, texel, 1u, 255u);
             }
         return color;
     }
@@ -557,7 +574,7 @@ PG2_DEV_NOINLINE uint32_t shade_base_ordered(const F& f, const uint32_t* __restr
             if ((unsigned)(X - ax.d0) >= (unsigned)ax.dlen || (unsigned)(Y - ay.d0) >= (unsigned)ay.dlen) continue;
             int sx = axis_sample(ax, X, false), sy = axis_sample(ay, Y, false);
             texel = __ldg(atlas + (w & CELL_OFFSET_MASK) + (uint32_t)sy * (uint32_t)f.class_w[cls] + (uint32_t)sx);
-            color = blend_packed(color, texel, (w >> 28) & 1u, 255u);
+            color = blend_packed(color, texel, 1u, 255u);
         }
     return color;
 }
@@ -571,15 +588,14 @@ PG2_DEV_NOINLINE uint32_t shade_base_continue(const F& f, const uint32_t* __rest
     while (p) {
         const uint32_t q = bfind(p);
         p &= ~(1u << q);
-        uint32_t blend;
-        const uint32_t texel = __ldg(atlas + tile_texel_index<G::TILE_CLASSES>(f, rd, cd, q, &blend));
-        const uint32_t a = blend ? texel >> 24 : 255u;
+        const uint32_t texel = __ldg(atlas + tile_texel_index<G::TILE_CLASSES>(f, rd, cd, q));
+        const uint32_t a = texel >> 24;
         if (a == 255u) return texel;
         if (a != 0u) return shade_base_ordered<G>(f, atlas, X, Y);
     }
     if ((rd.pre_row | cd.pre_sx) < 0) return 0u;
     const uint32_t texel = __ldg(atlas + (uint32_t)rd.pre_row + (uint32_t)cd.pre_sx);
-    const uint32_t a = f.pre_blend ? texel >> 24 : 255u;
+    const uint32_t a = texel >> 24;
     if (a == 255u) return texel;
     return a ? shade_base_ordered<G>(f, atlas, X, Y) : 0u;
 }
@@ -589,32 +605,27 @@ template <class G, class F>
 PG2_DEV void raster_band_base(F& f, const uint32_t* __restrict__ atlas, int band, int lane, uint8_t* buf) {
     constexpr int NCLASS = G::TILE_CLASSES;
     const bool wide = f.wide != 0;
-    const uint32_t pre_blend = (uint32_t)f.pre_blend;
     for (int it = 0; it < BAND_ROWS / 2; it++)
         for (int l = lane; l < 32; l += WARP_LANES) {
             const int Y = band * BAND_ROWS + it * 2 + (l >> 4), X0 = (l & 15) * 4;
             uint32_t color[4];
             if (!wide) {
                 const RowDesc rd = f.rowd[Y];
-                uint32_t cand[4], texel[4], blend[4];
-                bool fetched[4];
+                uint32_t cand[4], texel[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     ColDesc cd;   // col_slot(X0 + i) = (l & 15) + 16 * i
                     cd.cw = f.col_cw[(l & 15) + 16 * i]; cd.csx = f.col_csx[(l & 15) + 16 * i]; cd.pre_sx = f.col_pre[(l & 15) + 16 * i];
                     const uint32_t p = tile_candidates<NCLASS>(rd, cd.cw);
                     cand[i] = p;
-                    uint32_t tb;
-                    const uint32_t tidx = tile_texel_index<NCLASS>(f, rd, cd, bfind(p | 1u), &tb);
+                    const uint32_t tidx = tile_texel_index<NCLASS>(f, rd, cd, bfind(p | 1u));
                     const bool bg_ok = (rd.pre_row | cd.pre_sx) >= 0;
                     const uint32_t idx = p ? tidx : (uint32_t)rd.pre_row + (uint32_t)cd.pre_sx;
-                    blend[i] = p ? tb : pre_blend;
-                    fetched[i] = p || bg_ok;
-                    texel[i] = fetched[i] ? __ldg(atlas + idx) : 0u;
+                    texel[i] = (p || bg_ok) ? __ldg(atlas + idx) : 0xff000000u;   // nothing there: the clear colour
                 }
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const uint32_t a = (blend[i] && fetched[i]) ? texel[i] >> 24 : 255u;
+                    const uint32_t a = texel[i] >> 24;   // opaque-copy textures carry A = 255 in the atlas
                     color[i] = texel[i];
                     if (a != 255u) {   // transparent: next candidate below; translucent: blend in reference order
                         if (a != 0u) color[i] = shade_base_ordered<G>(f, atlas, X0 + i, Y);

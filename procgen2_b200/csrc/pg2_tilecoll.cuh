@@ -12,8 +12,11 @@ enum CollisionType { COLL_NONE = 0, COLL_FULL = 1, COLL_DOWN_ONLY = 2 };
 struct CollisionResult { float x, y; bool collided; };
 
 // TileAt(x, y) -> tile id with y already in render space (the callee flips: get(x, H-1-y)).
+// `uni` != nullptr: the call is made by ALL lanes of the warp that owns the environment with identical arguments
+// (the agent of a lane-aware game); the window's tiles are then fetched one per lane and OR-reduced.
 template <class TileAt, class TypeOf>
-PG2_DEV CollisionResult tile_collision(Rect rectangle, TileAt tile_at, TypeOf type_of, bool fallthrough = false, float step_y = 0.0f) {
+PG2_DEV CollisionResult tile_collision(Rect rectangle, TileAt tile_at, TypeOf type_of, bool fallthrough = false, float step_y = 0.0f,
+                                       const StepCtx* uni = nullptr) {
     bool collided = false;
     const int lower_x = f2i(floorf(rectangle.x));
     const int lower_y = f2i(floorf(rectangle.y));
@@ -29,9 +32,15 @@ PG2_DEV CollisionResult tile_collision(Rect rectangle, TileAt tile_at, TypeOf ty
         // collision type of every window tile ONCE (independent loads), 2 bits per cell in y-major / x-minor order,
         // then let both passes walk only the non-empty cells in exactly the reference's iteration order.
         uint32_t mask = 0u;
-        for (int iy = 0; iy < nyw; iy++)
-            for (int ix = 0; ix < nxw; ix++)
-                mask |= (uint32_t)type_of(tile_at(lower_x + ix, lower_y + iy)) << (2 * (iy * 4 + ix));
+        if (uni != nullptr && uni->nlanes == 32) {
+            const int l = uni->lane, ix = l & 3, iy = (l >> 2) & 3;
+            if (l < 16 && ix < nxw && iy < nyw) mask = (uint32_t)type_of(tile_at(lower_x + ix, lower_y + iy)) << (2 * l);
+            mask = warp_or(mask);
+        } else {
+            for (int iy = 0; iy < nyw; iy++)
+                for (int ix = 0; ix < nxw; ix++)
+                    mask |= (uint32_t)type_of(tile_at(lower_x + ix, lower_y + iy)) << (2 * (iy * 4 + ix));
+        }
         if (mask == 0u) { CollisionResult r0; r0.x = rectangle.x; r0.y = rectangle.y; r0.collided = false; return r0; }
         for (uint32_t m = mask; m;) {
             const int cell = (__ffs(m) - 1) >> 1;
