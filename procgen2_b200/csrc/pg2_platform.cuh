@@ -10,6 +10,17 @@
 #include <cuda_runtime.h>
 #define PG2_DEV __device__ __forceinline__
 #define PG2_DEV_NOINLINE __device__
+// A real call (never inlined): large bodies that are reached from several sites (the bit-exact libm restatements, the
+// blit axis arithmetic) — one copy keeps the kernels inside the instruction cache.
+#define PG2_DEV_CALL __device__ __noinline__
+#ifndef PG2_COLD_NOINLINE
+#define PG2_COLD_NOINLINE 1
+#endif
+#if PG2_COLD_NOINLINE
+#define PG2_DEV_COLD __device__ __noinline__
+#else
+#define PG2_DEV_COLD __device__
+#endif
 namespace pg2 {
 constexpr int WARP_LANES = 32;
 __device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
@@ -48,6 +59,8 @@ __device__ __forceinline__ uint32_t warp_or(uint32_t v) { return __reduce_or_syn
 #include <algorithm>
 #define PG2_DEV inline
 #define PG2_DEV_NOINLINE inline
+#define PG2_DEV_CALL inline
+#define PG2_DEV_COLD inline
 #define __restrict__
 namespace pg2 {
 constexpr int WARP_LANES = 1;

@@ -116,7 +116,7 @@ struct FrameT {
 
 // Deterministic sin/cos in degrees, mirrored operation by operation from oracle/raster.c
 // (pg2o_sincos_deg): IEEE double add/mul only, fixed order, no FMA.
-PG2_DEV_NOINLINE void sincos_deg(double deg, double* s, double* c) {
+PG2_DEV_CALL void sincos_deg(double deg, double* s, double* c) {
     double r = fmod(deg, 360.0);
     if (r < 0.0) r = __dadd_rn(r, 360.0);
     int q = (int)__ddiv_rn(__dadd_rn(r, 45.0), 90.0);
@@ -469,21 +469,27 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
     __syncthreads();
 }
 
+// Rotated blit: inverse-map the pixel centre into the un-rotated destination rect (oracle/raster.c step 4).
+// A real call: the double-precision chain stays out of the un-rotated blits' inner loop.
+PG2_DEV_CALL bool rotated_texel_coords(int x0, int y0, int w, int h, double rs, double rc, int X, int Y, uint32_t* oi, uint32_t* oj) {
+    double hw = __dmul_rn((double)w, 0.5), hh = __dmul_rn((double)h, 0.5);
+    double cx = __dadd_rn((double)x0, hw), cy = __dadd_rn((double)y0, hh);
+    double px = __dsub_rn(__dadd_rn((double)X, 0.5), cx);
+    double py = __dsub_rn(__dadd_rn((double)Y, 0.5), cy);
+    double u = __dadd_rn(__dmul_rn(px, rc), __dmul_rn(py, rs));
+    double v = __dsub_rn(__dmul_rn(py, rc), __dmul_rn(px, rs));
+    double fu = floor(__dadd_rn(u, hw)), fv = floor(__dadd_rn(v, hh));
+    if (fu < 0.0 || fv < 0.0 || fu >= (double)w || fv >= (double)h) return false;
+    *oi = (uint32_t)(int)fu; *oj = (uint32_t)(int)fv;
+    return true;
+}
+
 // Texel of a blit under pixel (X, Y); false when the pixel is not covered.
 template <bool ROT>
 PG2_DEV bool fast_texel(const FastBlit& fb, const BlitRot* rot, const uint32_t* __restrict__ atlas, int X, int Y, uint32_t* texel) {
     uint32_t i, j;
     if (ROT && (fb.flags & 2u)) {
-        // rotated: inverse-map the pixel centre into the un-rotated destination rect (oracle/raster.c step 4)
-        double hw = __dmul_rn((double)fb.w, 0.5), hh = __dmul_rn((double)fb.h, 0.5);
-        double cx = __dadd_rn((double)fb.x0, hw), cy = __dadd_rn((double)fb.y0, hh);
-        double px = __dsub_rn(__dadd_rn((double)X, 0.5), cx);
-        double py = __dsub_rn(__dadd_rn((double)Y, 0.5), cy);
-        double u = __dadd_rn(__dmul_rn(px, rot->c), __dmul_rn(py, rot->s));
-        double v = __dsub_rn(__dmul_rn(py, rot->c), __dmul_rn(px, rot->s));
-        double fu = floor(__dadd_rn(u, hw)), fv = floor(__dadd_rn(v, hh));
-        if (fu < 0.0 || fv < 0.0 || fu >= (double)fb.w || fv >= (double)fb.h) return false;
-        i = (uint32_t)(int)fu; j = (uint32_t)(int)fv;
+        if (!rotated_texel_coords(fb.x0, fb.y0, fb.w, fb.h, rot->s, rot->c, X, Y, &i, &j)) return false;
     } else {
         i = (uint32_t)(X - fb.x0); j = (uint32_t)(Y - fb.y0);
         if (i >= fb.w || j >= fb.h) return false;
@@ -544,7 +550,7 @@ PG2_DEV uint32_t tile_texel_index(const F& f, const RowDesc& rd, const ColDesc& 
 // top-most layer is translucent, and of every pixel of a `wide` frame (more than two tiles cover a column / row,
 // or a background the tables do not describe), which walks the covering ranges with the axes themselves.
 template <class G, class F>
-PG2_DEV_NOINLINE uint32_t shade_base_ordered(const F& f, const uint32_t* __restrict__ atlas, int X, int Y) {
+PG2_DEV_COLD uint32_t shade_base_ordered(const F& f, const uint32_t* __restrict__ atlas, int X, int Y) {
     uint32_t color = 0u, texel;   // SDL_RenderClear(0,0,0,255)
     for (int k = 0; k < f.npre; k++) {
         const FastBlit fb = f.fpre[k];
@@ -582,7 +588,7 @@ PG2_DEV_NOINLINE uint32_t shade_base_ordered(const F& f, const uint32_t* __restr
 // A pixel whose top-most tile texel turned out transparent: keep walking its candidates top-down (then the
 // background); the first opaque texel decides, a translucent one hands the pixel to shade_base_ordered.
 template <class G, class F>
-PG2_DEV_NOINLINE uint32_t shade_base_continue(const F& f, const uint32_t* __restrict__ atlas, int X, int Y, uint32_t p) {
+PG2_DEV_COLD uint32_t shade_base_continue(const F& f, const uint32_t* __restrict__ atlas, int X, int Y, uint32_t p) {
     const RowDesc rd = f.rowd[Y];
     const ColDesc cd = load_col(f, X);
     while (p) {

@@ -12,3 +12,12 @@ def test_uset_matches_libstdcxx(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith("OK")
+
+
+def test_uset_order_regrouping_matches_libstdcxx(tmp_path):
+    """pg2::USetOrder (pg2_roomgen.cuh): the warp-parallel computation of a fresh unordered_set's iteration order."""
+    exe = str(tmp_path / "test_uset_order")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_uset_order.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("OK")
