@@ -470,8 +470,8 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
 }
 
 // Rotated blit: inverse-map the pixel centre into the un-rotated destination rect (oracle/raster.c step 4).
-// A real call: the double-precision chain stays out of the un-rotated blits' inner loop.
-PG2_DEV_CALL bool rotated_texel_coords(int x0, int y0, int w, int h, double rs, double rc, int X, int Y, uint32_t* oi, uint32_t* oj) {
+// (Measured: a real call here costs bossfight / caveflyer ~10 % of the render.)
+PG2_DEV bool rotated_texel_coords(int x0, int y0, int w, int h, double rs, double rc, int X, int Y, uint32_t* oi, uint32_t* oj) {
     double hw = __dmul_rn((double)w, 0.5), hh = __dmul_rn((double)h, 0.5);
     double cx = __dadd_rn((double)x0, hw), cy = __dadd_rn((double)y0, hh);
     double px = __dsub_rn(__dadd_rn((double)X, 0.5), cx);

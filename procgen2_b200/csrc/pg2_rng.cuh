@@ -25,7 +25,7 @@ struct Mt {
     }
 
     // single-thread twist (thread-per-env kernels)
-    PG2_DEV_NOINLINE void twist_serial() {
+    PG2_DEV_CALL void twist_serial() {
         for (int k = 0; k < MT_N - MT_M; k++) mt[k] = mix(mt[k], mt[k + 1], mt[k + MT_M]);
         for (int k = MT_N - MT_M; k < MT_N - 1; k++) mt[k] = mix(mt[k], mt[k + 1], mt[k + (MT_M - MT_N)]);
         mt[MT_N - 1] = mix(mt[MT_N - 1], mt[0], mt[MT_M - 1]);
@@ -79,7 +79,7 @@ struct WarpMt {
     int idx;
     int lane;
 
-    PG2_DEV_NOINLINE void twist() {
+    PG2_DEV_CALL void twist() {
         __syncwarp();
         // new[k] = mix(mt[k], mt[k+1 mod N], mt[k+M mod N]) in ascending k; chunks of 32 read
         // their inputs before any lane of the chunk writes, later chunks see the updated words
