@@ -51,6 +51,7 @@ struct BossFight {
     static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int TILE_CLASSES = 1;
+    static constexpr bool HAS_TILES = false;     // the frame has a tile layer
     static constexpr int MB = 64, NEX = 8, AB = 32, MAX_BAR = 4;
     enum Tex {
         T_BOSS0 = 0,       // 4 enemy ships
@@ -138,10 +139,17 @@ struct BossFight {
         int hz_id[8];
         for (int k = 0; k < 8; k++) hz_id[k] = k < nhaz ? s.hazard_order[k * N + env] : 0;
 
-        auto hazard_rect = [&](int id) {
+        // barrier rectangles do not move within a step: fetched once, kept in registers (the loops over k are unrolled)
+        float hz_x[8], hz_y[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const bool bar = k < nhaz && hz_id[k] >= 2;
+            hz_x[k] = bar ? __fadd_rn(s.bar_x[(hz_id[k] - 2) * N + env], -0.1f) : 0.0f;
+            hz_y[k] = bar ? __fadd_rn(s.bar_y[(hz_id[k] - 2) * N + env], -0.1f) : 0.0f;
+        }
+        auto hazard_rect_at = [&](int k, int id) {   // k-th hazard of the list (id = hz_id[k])
             if (id == 1) return Rect{ __fadd_rn(bx, -0.6f), __fadd_rn(by, -0.4f), 1.2f, 0.8f };
-            int k = id - 2;
-            return Rect{ __fadd_rn(s.bar_x[k * N + env], -0.1f), __fadd_rn(s.bar_y[k * N + env], -0.1f), 0.2f, 0.2f };
+            return Rect{ hz_x[k], hz_y[k], 0.2f, 0.2f };
         };
 
         const float movement_x = (float)((action == 6 || action == 7 || action == 8) - (action == 0 || action == 1 || action == 2));
@@ -177,8 +185,11 @@ struct BossFight {
                         a_timer = fmaxf(0.0f, __fsub_rn(a_timer, dt));
                     }
                 }
-                for (int k = 0; k < nhaz; k++)
-                    if (check_collision(wc, hazard_rect(hz_id[k]))) { alive = false; break; }
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (k >= nhaz) break;
+                    if (check_collision(wc, hazard_rect_at(k, hz_id[k]))) { alive = false; break; }
+                }
 
                 for (int i = 0; i < a_num; i++) {
                     int bi = ((AB + a_next - 1 - i) % AB) * N + env;
@@ -191,9 +202,11 @@ struct BossFight {
                         Rect bw{ __fsub_rn(x, 0.01f), __fsub_rn(y, 0.01f), 0.02f, 0.02f };
                         if (!check_collision(bw, screen)) { vx = 0.0f; vy = 0.0f; frame = 5.0f; }
                         else {
-                            for (int k = 0; k < nhaz; k++) {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) {
+                                if (k >= nhaz) break;
                                 int h = hz_id[k];
-                                if (check_collision(bw, hazard_rect(h))) {
+                                if (check_collision(bw, hazard_rect_at(k, h))) {
                                     if (h == 1) {
                                         if (phase_index % 2 == 0) {   // shielded: bounce
                                             vx = __fmul_rn(rng.uniform_real(-1.0f, 1.0f), 0.05f);
@@ -330,10 +343,12 @@ struct BossFight {
                             alive = false;
                             stop = true;   // `break` leaves the bullet loop: this bullet is not moved either
                         } else {
-                            for (int k = 0; k < nhaz; k++) {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) {
+                                if (k >= nhaz) break;
                                 int h = hz_id[k];
                                 if (h == 1) continue;
-                                if (check_collision(bw, hazard_rect(h))) { vx = 0.0f; vy = 0.0f; frame = 1.0f; break; }
+                                if (check_collision(bw, hazard_rect_at(k, h))) { vx = 0.0f; vy = 0.0f; frame = 1.0f; break; }
                             }
                         }
                     }

@@ -47,6 +47,7 @@ struct CaveFlyer {
     static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int TILE_CLASSES = 1;
+    static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     enum Obj { O_NONE = 0, O_OBSTACLE, O_TARGET, O_ENEMY };
     enum Tex { T_WALL = 0, T_GOAL, T_TARGET, T_OBSTACLE, T_ENEMY, T_BULLET, T_SHIP, T_PARTICLE, T_EXPL0, T_BG0 = 13, NUM_BG = 13, NUM_TEX = 26 };
 

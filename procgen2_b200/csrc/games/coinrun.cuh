@@ -60,6 +60,7 @@ struct CoinRun {
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int TILE_CLASSES = 1;
+    static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID, LAVA_TOP, LAVA_MID, CRATE };
     enum Ent { E_NONE = 0, E_SAW, E_MOB, E_COIN };
     enum Tex {

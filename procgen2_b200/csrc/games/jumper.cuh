@@ -45,6 +45,7 @@ struct Jumper {
     static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int TILE_CLASSES = 2;
+    static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID, SPIKE };
     enum Tex {
         T_WALL_TOP0 = 0, T_WALL_MID0 = 4, T_SPIKE = 8, T_CARROT, T_STAND, T_JUMP, T_WALK1, T_WALK2, T_PARTICLE,

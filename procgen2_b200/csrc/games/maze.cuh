@@ -36,6 +36,7 @@ struct Maze {
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int TILE_CLASSES = 1;
+    static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr int TILE_STRIDE = 640;
     enum Tex { T_WALL = 0, T_CHEESE = 1, T_MOUSE = 2, T_BG0 = 3, NUM_BG = 9, NUM_TEX = 12 };
 

@@ -622,9 +622,9 @@ PG2_DEV void raster_band_base(F& f, const uint32_t* __restrict__ atlas, int band
                 for (int i = 0; i < 4; i++) {
                     ColDesc cd;   // col_slot(X0 + i) = (l & 15) + 16 * i
                     cd.cw = f.col_cw[(l & 15) + 16 * i]; cd.csx = f.col_csx[(l & 15) + 16 * i]; cd.pre_sx = f.col_pre[(l & 15) + 16 * i];
-                    const uint32_t p = tile_candidates<NCLASS>(rd, cd.cw);
+                    const uint32_t p = G::HAS_TILES ? tile_candidates<NCLASS>(rd, cd.cw) : 0u;
                     cand[i] = p;
-                    const uint32_t tidx = tile_texel_index<NCLASS>(f, rd, cd, bfind(p | 1u));
+                    const uint32_t tidx = G::HAS_TILES ? tile_texel_index<NCLASS>(f, rd, cd, bfind(p | 1u)) : 0u;
                     const bool bg_ok = (rd.pre_row | cd.pre_sx) >= 0;
                     const uint32_t idx = p ? tidx : (uint32_t)rd.pre_row + (uint32_t)cd.pre_sx;
                     texel[i] = (p || bg_ok) ? __ldg(atlas + idx) : 0xff000000u;   // nothing there: the clear colour
