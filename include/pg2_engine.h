@@ -97,6 +97,13 @@ PG2_API int32_t pg2_profile_read(pg2_engine* e, float ms_out[3], int64_t* steps)
 PG2_API int64_t pg2_read_field(pg2_engine* e, const char* name, void* out, int64_t capacity, int32_t* elem_size, int32_t* per_env);
 PG2_API int64_t pg2_write_field(pg2_engine* e, const char* name, const void* in, int64_t bytes);
 
+/* Snapshot / restore of the complete simulation state of the shard (every SoA field incl. the MT19937 streams, the
+ * current observations / rewards / done flags): a checkpoint the reference cannot take.
+ * pg2_snapshot(e, NULL, 0) returns the blob size; otherwise bytes written, <0 on error. A blob restores only into an
+ * engine of the same game and shard size. Stepping after pg2_restore reproduces the steps after pg2_snapshot bit for bit. */
+PG2_API int64_t pg2_snapshot(pg2_engine* e, void* out, int64_t capacity);
+PG2_API int64_t pg2_restore(pg2_engine* e, const void* blob, int64_t bytes);
+
 PG2_API const char* pg2_last_error(void);
 
 #ifdef __cplusplus

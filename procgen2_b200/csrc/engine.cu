@@ -150,6 +150,8 @@ struct EngineBase {
     virtual int step_device(const int32_t* actions_dev) = 0;
     virtual bool find_field(const char* name, void** ptr, int* esz, int* pe) = 0;
     virtual size_t state_bytes_per_env() = 0;
+    virtual size_t state_alloc_bytes() = 0;     // bytes of state_mem
+    virtual uint32_t game_tag() = 0;
 
     int device = 0, N = 0, max_episode_steps = 0, auto_reset = 1;
     uint32_t base_seed = 0;
@@ -406,6 +408,8 @@ struct Engine : EngineBase {
         return st.find(name, ptr, esz, pe) || common.find(name, ptr, esz, pe);
     }
     size_t state_bytes_per_env() override { return (G::State::bytes(1024) + CommonState::bytes(1024)) / 1024; }
+    size_t state_alloc_bytes() override { return G::State::bytes(N); }
+    uint32_t game_tag() override { return (uint32_t)G::NUM_TEX * 2654435761u ^ (uint32_t)G::State::bytes(1024); }   // distinct per game
 };
 
 }  // namespace pg2
@@ -592,6 +596,59 @@ int64_t pg2_write_field(pg2_engine* e, const char* name, const void* in, int64_t
     cudaStreamSynchronize(b->stream);
     if (cudaMemcpy(ptr, in, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { g_error = "pg2_write_field: copy failed"; return -3; }
     return bytes;
+}
+
+// blob = header { magic, game tag, N, parity, state bytes, common bytes } + state_mem + common_mem + obs + reward +
+// terminated + truncated
+struct SnapshotHeader { uint32_t magic, game; int32_t n, parity; uint64_t state_bytes, common_bytes; };
+static const uint32_t SNAPSHOT_MAGIC = 0x50473253u;   // "PG2S"
+
+int64_t pg2_snapshot(pg2_engine* e, void* out, int64_t capacity) {
+    EngineBase* b = e->impl.get();
+    const size_t sb = b->state_alloc_bytes(), cb = CommonState::bytes(b->N), n = (size_t)b->N;
+    const int64_t total = (int64_t)(sizeof(SnapshotHeader) + sb + cb + n * OBS_BYTES + n * sizeof(float) + 2 * n);
+    if (!out) return total;
+    if (capacity < total) { g_error = "pg2_snapshot: buffer too small"; return -2; }
+    if (b->pipelined) { g_error = "pg2_snapshot: flush the pipelined stepping first (pg2_pipeline_flush) and use pg2_step"; }
+    cudaSetDevice(b->device);
+    if (cudaStreamSynchronize(b->stream) != cudaSuccess) { g_error = "pg2_snapshot: sync failed"; return -3; }
+    SnapshotHeader h{ SNAPSHOT_MAGIC, b->game_tag(), b->N, b->parity, (uint64_t)sb, (uint64_t)cb };
+    char* p = (char*)out;
+    memcpy(p, &h, sizeof(h)); p += sizeof(h);
+    bool ok = cudaMemcpy(p, b->state_mem, sb, cudaMemcpyDeviceToHost) == cudaSuccess; p += sb;
+    ok = ok && cudaMemcpy(p, b->common_mem, cb, cudaMemcpyDeviceToHost) == cudaSuccess; p += cb;
+    ok = ok && cudaMemcpy(p, b->obs, n * OBS_BYTES, cudaMemcpyDeviceToHost) == cudaSuccess; p += n * OBS_BYTES;
+    ok = ok && cudaMemcpy(p, b->reward, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess; p += n * sizeof(float);
+    ok = ok && cudaMemcpy(p, b->terminated, n, cudaMemcpyDeviceToHost) == cudaSuccess; p += n;
+    ok = ok && cudaMemcpy(p, b->truncated, n, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (!ok) { g_error = "pg2_snapshot: copy failed"; return -3; }
+    return total;
+}
+
+int64_t pg2_restore(pg2_engine* e, const void* blob, int64_t bytes) {
+    EngineBase* b = e->impl.get();
+    const size_t sb = b->state_alloc_bytes(), cb = CommonState::bytes(b->N), n = (size_t)b->N;
+    const int64_t total = (int64_t)(sizeof(SnapshotHeader) + sb + cb + n * OBS_BYTES + n * sizeof(float) + 2 * n);
+    SnapshotHeader h;
+    if (bytes < (int64_t)sizeof(h)) { g_error = "pg2_restore: truncated blob"; return -2; }
+    memcpy(&h, blob, sizeof(h));
+    if (h.magic != SNAPSHOT_MAGIC || h.game != b->game_tag() || h.n != b->N || h.state_bytes != sb || h.common_bytes != cb || bytes != total) {
+        g_error = "pg2_restore: blob does not belong to this game / shard size"; return -2;
+    }
+    cudaSetDevice(b->device);
+    if (cudaStreamSynchronize(b->stream) != cudaSuccess) { g_error = "pg2_restore: sync failed"; return -3; }
+    const char* p = (const char*)blob + sizeof(h);
+    bool ok = cudaMemcpy(b->state_mem, p, sb, cudaMemcpyHostToDevice) == cudaSuccess; p += sb;
+    ok = ok && cudaMemcpy(b->common_mem, p, cb, cudaMemcpyHostToDevice) == cudaSuccess; p += cb;
+    ok = ok && cudaMemcpy(b->obs, p, n * OBS_BYTES, cudaMemcpyHostToDevice) == cudaSuccess; p += n * OBS_BYTES;
+    ok = ok && cudaMemcpy(b->reward, p, n * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess; p += n * sizeof(float);
+    ok = ok && cudaMemcpy(b->terminated, p, n, cudaMemcpyHostToDevice) == cudaSuccess; p += n;
+    ok = ok && cudaMemcpy(b->truncated, p, n, cudaMemcpyHostToDevice) == cudaSuccess;
+    // the reset-list counters are transient within a step: zero them like a fresh engine, keep the parity of the snapshot
+    ok = ok && cudaMemset(b->reset_count, 0, 4 * sizeof(int)) == cudaSuccess;
+    b->parity = h.parity;
+    if (!ok) { g_error = "pg2_restore: copy failed"; return -3; }
+    return total;
 }
 
 }  // extern "C"

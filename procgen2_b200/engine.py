@@ -61,6 +61,10 @@ def load_library():
     L.pg2_read_field.restype = ctypes.c_int64
     L.pg2_write_field.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64]
     L.pg2_write_field.restype = ctypes.c_int64
+    L.pg2_snapshot.argtypes = [vp, vp, ctypes.c_int64]
+    L.pg2_snapshot.restype = ctypes.c_int64
+    L.pg2_restore.argtypes = [vp, vp, ctypes.c_int64]
+    L.pg2_restore.restype = ctypes.c_int64
     L.pg2_profile.argtypes = [vp, ctypes.c_int32]
     L.pg2_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int64)]
     L.pg2_last_error.restype = ctypes.c_char_p
@@ -199,6 +203,22 @@ class BatchedEnv:
         n = self._L.pg2_write_field(self._h, name.encode(), a.ctypes.data, a.nbytes)
         if n < 0:
             raise RuntimeError(self._L.pg2_last_error().decode())
+
+    def snapshot(self):
+        """Complete simulation state of the shard as bytes (pg2_snapshot): checkpoint / fork point."""
+        n = self._L.pg2_snapshot(self._h, None, 0)
+        buf = np.empty(n, np.uint8)
+        got = self._L.pg2_snapshot(self._h, buf.ctypes.data, n)
+        if got != n:
+            raise RuntimeError("pg2_snapshot: %s" % self._L.pg2_last_error().decode())
+        return buf
+
+    def restore(self, blob):
+        """Restore a snapshot() of an engine of the same game and size; subsequent steps replay bit for bit."""
+        blob = np.ascontiguousarray(blob, np.uint8)
+        got = self._L.pg2_restore(self._h, blob.ctypes.data, blob.size)
+        if got != blob.size:
+            raise RuntimeError("pg2_restore: %s" % self._L.pg2_last_error().decode())
 
     def close(self):
         if getattr(self, "_h", None):

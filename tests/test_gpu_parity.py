@@ -202,3 +202,40 @@ def test_pipelined_stepping_equals_sequential():
     o, r, d = bufs[(T - 1) & 1]
     np.testing.assert_array_equal(o, seq[T - 1][0]); np.testing.assert_array_equal(r, seq[T - 1][1])
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("game", ["coinrun", "bossfight", "jumper"])
+def test_snapshot_restore_replays_bit_exact(game):
+    """pg2_snapshot / pg2_restore: stepping after a restore reproduces the steps that followed
+    the snapshot bit for bit (observations, rewards, done flags, MT19937 streams) — also into a fresh engine, and
+    across episode boundaries (auto-reset, level regeneration, bossfight's per-sub-step RNG)."""
+    from procgen2_b200.engine import BatchedEnv
+    n, T0, T1 = 96, 40, 120
+    rs = np.random.RandomState(5)
+    acts = rs.randint(0, 15, size=(T0 + T1, n)).astype(np.int32)
+    a = BatchedEnv(game, n, seed=77, max_episode_steps=50)
+    a.reset()
+    for t in range(T0):
+        a.step(acts[t])
+    blob = a.snapshot()
+    want = []
+    for t in range(T0, T0 + T1):
+        a.step(acts[t])
+        o, r, d, tr = a.fetch(truncated=True)
+        want.append((o, r, d, tr))
+    mt_want = a.read_field("mt")[0].copy()
+    # (1) same engine rewound, (2) a fresh engine that never saw the first T0 steps
+    b = BatchedEnv(game, n, seed=12345, max_episode_steps=50)
+    b.reset()
+    for env in (a, b):
+        env.restore(blob)
+        np.testing.assert_array_equal(env.fetch()[0], np.frombuffer(blob, np.uint8)[-(n * 12288 + 6 * n):-6 * n].reshape(n, 64, 64, 3))
+        for k, t in enumerate(range(T0, T0 + T1)):
+            env.step(acts[t])
+            o, r, d, tr = env.fetch(truncated=True)
+            np.testing.assert_array_equal(o, want[k][0]); np.testing.assert_array_equal(r, want[k][1])
+            np.testing.assert_array_equal(d, want[k][2]); np.testing.assert_array_equal(tr, want[k][3])
+        np.testing.assert_array_equal(env.read_field("mt")[0], mt_want)
+    with pytest.raises(RuntimeError):
+        BatchedEnv(game, n + 1, seed=0).restore(blob)
+    a.close(); b.close()
