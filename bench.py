@@ -334,7 +334,7 @@ def main():
             if reference_available():
                 pool = ReferencePool(a.game, procs, 8)
                 pool.run(a.ref_inner)
-                n_cpu = max(a.ref_inner, 400)
+                n_cpu = max(a.ref_inner, 4000)   # ~1 s wall on every host core = 10-30 s of CPU work
                 v, wall_cpu = pool.run(n_cpu)
                 pool.close()
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": procs, "kind": "reference",
