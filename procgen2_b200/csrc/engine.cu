@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::
     extern __shared__ __align__(16) char smem[];
     const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* mt = (uint32_t*)smem + warp_in_cta * MT_N;
-    char* arena = smem + RESET_WARPS_PER_CTA * MT_N * 4 + warp_in_cta * RESET_ARENA_BYTES;
+    char* arena = smem + RESET_WARPS_PER_CTA * MT_N * 4 + warp_in_cta * G::RESET_ARENA;
     const int count = reset_list ? *reset_count : N;
     const int total_warps = gridDim.x * RESET_WARPS_PER_CTA;
     for (int w = blockIdx.x * RESET_WARPS_PER_CTA + warp_in_cta; w < count; w += total_warps) {
@@ -331,10 +331,14 @@ struct Engine : EngineBase {
     }
 
     int step_grid() const { int warps = (N + step_epw - 1) / step_epw; return (warps * 32 + 127) / 128; }
-    static int reset_smem() { return RESET_WARPS_PER_CTA * (MT_N * 4 + RESET_ARENA_BYTES); }
+    static int reset_smem() { return RESET_WARPS_PER_CTA * (MT_N * 4 + G::RESET_ARENA); }
+    // as many CTAs as fit the SMs' shared memory at once (227 KB per SM, 1 KB reserved per CTA, <= 16): the games with a
+    // small level-generation scratch run 8x more resets concurrently than the cave generators
     int reset_grid(int count) const {
+        int per_sm = (227 * 1024) / (reset_smem() + 1024);
+        per_sm = per_sm > 16 ? 16 : (per_sm < 1 ? 1 : per_sm);
         int ctas = (count + RESET_WARPS_PER_CTA - 1) / RESET_WARPS_PER_CTA;
-        return ctas < num_sms * 4 ? (ctas < 1 ? 1 : ctas) : num_sms * 4;
+        return ctas < num_sms * per_sm ? (ctas < 1 ? 1 : ctas) : num_sms * per_sm;
     }
     void launch_reset_all() {
         k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, nullptr, nullptr, N);

@@ -50,6 +50,7 @@ struct BossFight {
     static constexpr int MAX_POST = 112;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
+    static constexpr int RESET_ARENA = 2 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
     static constexpr int TILE_CLASSES = 1;
     static constexpr bool HAS_TILES = false;     // the frame has a tile layer
     static constexpr int MB = 64, NEX = 8, AB = 32, MAX_BAR = 4;

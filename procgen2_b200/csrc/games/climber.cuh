@@ -44,6 +44,7 @@ struct Climber {
     static constexpr int MAX_POST = 48;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
+    static constexpr int RESET_ARENA = 4 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
     static constexpr int TILE_CLASSES = 2;   // wall_mid textures are 64x64, one wall_top texture is 64x53
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID };

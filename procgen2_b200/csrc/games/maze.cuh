@@ -35,6 +35,7 @@ struct Maze {
     static constexpr int MAX_POST = 4;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
+    static constexpr int RESET_ARENA = 10 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
     static constexpr int TILE_CLASSES = 1;
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr int TILE_STRIDE = 640;

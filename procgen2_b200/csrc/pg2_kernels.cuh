@@ -44,7 +44,7 @@ PG2_DEV bool step_body(const typename G::State& s, const CommonState& c, int env
     return term || trunc;
 }
 
-// reset() for one env by one warp; `mt` = 624 words of per-warp scratch, `arena` = RESET_ARENA_BYTES
+// reset() for one env by one warp; `mt` = 624 words of per-warp scratch, `arena` = G::RESET_ARENA bytes
 template <class G>
 PG2_DEV void reset_body(const typename G::State& s, const CommonState& c, int env, uint32_t* mt, char* arena, int lane) {
     uint32_t* gmt = c.mt + (size_t)env * MT_N;
@@ -52,7 +52,7 @@ PG2_DEV void reset_body(const typename G::State& s, const CommonState& c, int en
     __syncwarp();
     WarpCtx ctx;
     ctx.rng.mt = mt; ctx.rng.idx = c.mti[env]; ctx.rng.lane = lane;
-    ctx.lane = lane; ctx.arena = arena; ctx.arena_off = 0;
+    ctx.lane = lane; ctx.arena = arena; ctx.arena_off = 0; ctx.arena_cap = G::RESET_ARENA;
     G::regenerate(s, c, env, ctx);
     __syncwarp();
     for (int i = lane; i < MT_N; i += WARP_LANES) gmt[i] = mt[i];

@@ -15,20 +15,24 @@
 namespace pg2 {
 
 constexpr int RESET_WARPS_PER_CTA = 2;
-constexpr int RESET_ARENA_BYTES = 52 * 1024;   // per-warp scratch
+constexpr int RESET_ARENA_BYTES = 52 * 1024;   // largest per-warp scratch of any game (G::RESET_ARENA is what a game gets)
 
 struct WarpCtx {
     WarpMt rng;
     int lane;
     char* arena;       // per-warp shared-memory scratch
     int arena_off;
+    int arena_cap;     // bytes available (G::RESET_ARENA)
 
     template <class T>
     PG2_DEV_NOINLINE T* alloc(int count) {
         int off = (arena_off + 15) & ~15;
         arena_off = off + (int)sizeof(T) * count;
-#ifdef PG2_HOSTSIM
-        if (arena_off > RESET_ARENA_BYTES) { fprintf(stderr, "reset arena overflow: %d > %d\n", arena_off, RESET_ARENA_BYTES); abort(); }
+#ifndef PG2_HOSTSIM
+        if (arena_off > arena_cap) __trap();   // a game outgrew its G::RESET_ARENA: fail loudly, never corrupt
+#else
+        if (arena_off > arena_cap) { fprintf(stderr, "reset arena overflow: %d > %d\n", arena_off, arena_cap); abort(); }
+        if (getenv("PG2_ARENA_TRACE")) { static int hw = 0; if (arena_off > hw) { hw = arena_off; fprintf(stderr, "arena high water %d\n", hw); } }
 #endif
         return (T*)(arena + off);
     }

@@ -29,7 +29,7 @@ int main() {
 
         WarpCtx w;
         w.rng.mt = mt; w.rng.idx = 0; w.rng.lane = 0;
-        w.lane = 0; w.arena = arena.data(); w.arena_off = 0;
+        w.lane = 0; w.arena = arena.data(); w.arena_off = 0; w.arena_cap = RESET_ARENA_BYTES;
         uint16_t* bufa = w.alloc<uint16_t>(ROOM_CELLS + 64);
         uint16_t* bufb = w.alloc<uint16_t>(ROOM_CELLS + 64);
         int* first = w.alloc<int>(ROOM_MAX_BUCKETS);

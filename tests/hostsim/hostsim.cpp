@@ -48,7 +48,7 @@ struct Sim : SimBase {
         common_mem.assign(CommonState::bytes(N), 0);
         st = G::State::bind(state_mem.data(), N);
         c = CommonState::bind(common_mem.data(), N);
-        arena.assign(RESET_ARENA_BYTES, 0);
+        arena.assign(G::RESET_ARENA, 0);
         mt_scratch.assign(MT_N, 0);
         frame.reset(new FrameOf<G>());
         obs.assign((size_t)N * OBS_BYTES, 0); terminated.assign(N, 0); truncated.assign(N, 0); reward.assign(N, 0.0f);
