@@ -12,6 +12,8 @@
  *
  * Batched extension implemented by this project's libraries (reference: one env per library):
  *   make options  "num_envs" (INT, default 1), "device" (INT, default 0),
+ *                 "num_devices" (INT, default 1: devices device .. device + num_devices - 1 each own a
+ *                 contiguous slice of the envs; env i is seeded seed + i whatever the device count),
  *                 "max_episode_steps" (INT, default 0 = never truncate),
  *                 "auto_reset" (INT, default 1 when num_envs > 1, else 0)
  *   actions       key "action", INT, value_buffer_size == num_envs

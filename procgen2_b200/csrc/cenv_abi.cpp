@@ -42,7 +42,11 @@ const int kVersion = 100;        // coinrun.cpp:9
 const int kObsBytes = 64 * 64 * 3;
 const int kNumActions = 15;      // coinrun.cpp:27
 
-pg2_engine* g_engine = nullptr;
+// One engine per device: shard d owns the contiguous env slice [g_first[d], g_first[d] + g_count[d]);
+// seeds stay seed + global env index, so results do not depend on the number of devices.
+std::vector<pg2_engine*> g_engines;
+std::vector<int> g_first, g_count;
+pg2_engine* g_engine = nullptr;   // == g_engines[0] (non-null <=> made)
 int g_num_envs = 1;
 int g_window_w = 512, g_window_h = 512;
 
@@ -56,11 +60,20 @@ std::vector<float> g_reward;
 std::vector<int32_t> g_actions, g_seeds;
 
 int fetch() {
-    if (pg2_fetch(g_engine, g_obs.data(), g_reward.data(), g_term.data(), g_trunc.data())) {
-        fprintf(stderr, "[procgen2_b200] %s\n", pg2_last_error());
-        return 1;
+    for (size_t d = 0; d < g_engines.size(); d++) {
+        const size_t o = (size_t)g_first[d];
+        if (pg2_fetch(g_engines[d], g_obs.data() + o * kObsBytes, g_reward.data() + o, g_term.data() + o, g_trunc.data() + o)) {
+            fprintf(stderr, "[procgen2_b200] %s\n", pg2_last_error());
+            return 1;
+        }
     }
     return 0;
+}
+
+void destroy_all() {
+    for (pg2_engine* e : g_engines) pg2_destroy(e);
+    g_engines.clear(); g_first.clear(); g_count.clear();
+    g_engine = nullptr;
 }
 
 }  // namespace
@@ -70,9 +83,9 @@ extern "C" {
 int32_t cenv_get_env_version() { return kVersion; }
 
 int32_t cenv_make(const char* /*render_mode*/, cenv_option* options, int32_t options_size) {
-    if (g_engine) { pg2_destroy(g_engine); g_engine = nullptr; }
+    destroy_all();
     unsigned int seed = (unsigned int)time(nullptr);     // coinrun.cpp:130
-    int device = 0, max_episode_steps = 0, auto_reset = -1;
+    int device = 0, num_devices = 1, max_episode_steps = 0, auto_reset = -1;
     g_num_envs = 1;
     for (int i = 0; i < options_size; i++) {
         std::string name(options[i].name);
@@ -83,6 +96,7 @@ int32_t cenv_make(const char* /*render_mode*/, cenv_option* options, int32_t opt
         else if (name == "height") g_window_h = v;
         else if (name == "num_envs") g_num_envs = v;
         else if (name == "device") device = v;
+        else if (name == "num_devices") num_devices = v;
         else if (name == "max_episode_steps") max_episode_steps = v;
         else if (name == "auto_reset") auto_reset = v;
     }
@@ -91,21 +105,32 @@ int32_t cenv_make(const char* /*render_mode*/, cenv_option* options, int32_t opt
         return 1;
     }
     if (auto_reset < 0) auto_reset = g_num_envs > 1 ? 1 : 0;
-
-    pg2_config cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.game = PG2_GAME;
-    cfg.num_envs = g_num_envs;
-    cfg.seed = (int32_t)seed;
-    cfg.first_env = 0;
-    cfg.device = device;
-    cfg.max_episode_steps = max_episode_steps;
-    cfg.assets_path = nullptr;
-    cfg.auto_reset = auto_reset;
-    if (pg2_create(&cfg, &g_engine)) {
-        fprintf(stderr, "[procgen2_b200] cenv_make failed: %s\n", pg2_last_error());
+    if (num_devices < 1 || num_devices > g_num_envs) {
+        fprintf(stderr, "[procgen2_b200] num_devices must be in [1, num_envs]\n");
         return 1;
     }
+    for (int d = 0, first = 0; d < num_devices; d++) {
+        const int count = g_num_envs / num_devices + (d < g_num_envs % num_devices ? 1 : 0);
+        pg2_config cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.game = PG2_GAME;
+        cfg.num_envs = count;
+        cfg.seed = (int32_t)seed;
+        cfg.first_env = first;
+        cfg.device = device + d;
+        cfg.max_episode_steps = max_episode_steps;
+        cfg.assets_path = nullptr;
+        cfg.auto_reset = auto_reset;
+        pg2_engine* e = nullptr;
+        if (pg2_create(&cfg, &e)) {
+            fprintf(stderr, "[procgen2_b200] cenv_make failed (device %d): %s\n", device + d, pg2_last_error());
+            destroy_all();
+            return 1;
+        }
+        g_engines.push_back(e); g_first.push_back(first); g_count.push_back(count);
+        first += count;
+    }
+    g_engine = g_engines[0];
 
     g_obs.assign((size_t)g_num_envs * kObsBytes, 0);
     g_reward.assign(g_num_envs, 0.0f);
@@ -165,10 +190,11 @@ int32_t cenv_reset(cenv_option* options, int32_t options_size) {
             reseed = true;
         }
     }
-    if (pg2_reset(g_engine, reseed ? g_seeds.data() : nullptr)) {
-        fprintf(stderr, "[procgen2_b200] cenv_reset failed: %s\n", pg2_last_error());
-        return 1;
-    }
+    for (size_t d = 0; d < g_engines.size(); d++)
+        if (pg2_reset(g_engines[d], reseed ? g_seeds.data() + g_first[d] : nullptr)) {
+            fprintf(stderr, "[procgen2_b200] cenv_reset failed: %s\n", pg2_last_error());
+            return 1;
+        }
     return fetch();
 }
 
@@ -185,10 +211,13 @@ int32_t cenv_step(cenv_key_value* actions, int32_t actions_size) {
             memcpy(g_actions.data(), actions[i].value_buffer.i, sizeof(int32_t) * g_num_envs);
         }
     }
-    if (pg2_step(g_engine, g_actions.data())) {
-        fprintf(stderr, "[procgen2_b200] cenv_step failed: %s\n", pg2_last_error());
-        return 1;
-    }
+    // every device gets its slice of the actions and starts stepping (asynchronous launches); the fetches then
+    // drain the devices one after the other while the others are still computing
+    for (size_t d = 0; d < g_engines.size(); d++)
+        if (pg2_step(g_engines[d], g_actions.data() + g_first[d])) {
+            fprintf(stderr, "[procgen2_b200] cenv_step failed: %s\n", pg2_last_error());
+            return 1;
+        }
     if (fetch()) return 1;
     step_data.reward.f = g_reward[0];
     step_data.terminated = g_term[0] != 0;
@@ -210,7 +239,7 @@ int32_t cenv_render() {
 }
 
 void cenv_close() {
-    if (g_engine) { pg2_destroy(g_engine); g_engine = nullptr; }
+    destroy_all();
     g_obs.clear(); g_frame.clear();
 }
 

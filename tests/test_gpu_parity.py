@@ -239,3 +239,35 @@ def test_snapshot_restore_replays_bit_exact(game):
     with pytest.raises(RuntimeError):
         BatchedEnv(game, n + 1, seed=0).restore(blob)
     a.close(); b.close()
+
+
+def test_cenv_dropin_num_devices_is_invisible():
+    """cenv make-option "num_devices" (SURVEY §8e at the drop-in boundary): the batch sharded over two GPUs inside one
+    library instance returns exactly what one GPU returns (seeds follow the global env index). Needs >= 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from procgen2_b200.build import game_lib_path
+    from procgen2_b200.cenv import CEnv
+    n, T = 50, 60     # 25 + 25, and an uneven 3-way split is exercised by the shard arithmetic below when available
+    rs = np.random.RandomState(4)
+    acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
+    ndev = 3 if torch.cuda.device_count() >= 3 else 2
+    a = CEnv(game_lib_path("coinrun"), options={"seed": 11, "num_envs": n, "max_episode_steps": 25})
+    ra = []
+    obs, _ = a.reset()
+    ra.append(obs["screen"].copy())
+    for t in range(T):
+        obs, _, _, _, info = a.step({"action": acts[t]})
+        ra.append((obs["screen"].copy(), info["reward"].copy(), info["terminated"].copy(), info["truncated"].copy()))
+    a.close()
+    b = CEnv(game_lib_path("coinrun"), options={"seed": 11, "num_envs": n, "max_episode_steps": 25, "num_devices": ndev})
+    obs, _ = b.reset()
+    np.testing.assert_array_equal(obs["screen"], ra[0])
+    for t in range(T):
+        obs, _, _, _, info = b.step({"action": acts[t]})
+        np.testing.assert_array_equal(obs["screen"], ra[t + 1][0])
+        np.testing.assert_array_equal(info["reward"], ra[t + 1][1])
+        np.testing.assert_array_equal(info["terminated"], ra[t + 1][2])
+        np.testing.assert_array_equal(info["truncated"], ra[t + 1][3])
+    b.close()
