@@ -14,3 +14,4 @@ for k in k_render k_step k_reset; do
 done
 tail -2 gpurun_out/${TAG}_bench_default.json | cut -c1-400
 tail -1 gpurun_out/${TAG}_reference.json | cut -c1-300
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; tail -1 gpurun_out/${TAG}_smoke.log
