@@ -630,12 +630,16 @@ PG2_DEV void raster_band_base(F& f, const uint32_t* __restrict__ atlas, int band
                     texel[i] = (p || bg_ok) ? __ldg(atlas + idx) : 0xff000000u;   // nothing there: the clear colour
                 }
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint32_t a = texel[i] >> 24;   // opaque-copy textures carry A = 255 in the atlas
-                    color[i] = texel[i];
-                    if (a != 255u) {   // transparent: next candidate below; translucent: blend in reference order
-                        if (a != 0u) color[i] = shade_base_ordered<G>(f, atlas, X0 + i, Y);
-                        else color[i] = cand[i] ? shade_base_continue<G>(f, atlas, X0 + i, Y, cand[i] & ~(1u << bfind(cand[i]))) : 0u;
+                for (int i = 0; i < 4; i++) color[i] = texel[i];
+                // opaque-copy textures carry A = 255 in the atlas: ONE test covers the common case of four opaque texels
+                if (((texel[0] & texel[1] & texel[2] & texel[3]) >> 24) != 255u) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t a = texel[i] >> 24;
+                        if (a != 255u) {   // transparent: next candidate below; translucent: blend in reference order
+                            if (a != 0u) color[i] = shade_base_ordered<G>(f, atlas, X0 + i, Y);
+                            else color[i] = cand[i] ? shade_base_continue<G>(f, atlas, X0 + i, Y, cand[i] & ~(1u << bfind(cand[i]))) : 0u;
+                        }
                     }
                 }
             } else {
