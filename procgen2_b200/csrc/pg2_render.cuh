@@ -76,7 +76,7 @@ PG2_DEV int col_slot(int X) { return (X >> 2) | (X & 3) << 4; }
 constexpr uint32_t CELL_OFFSET_MASK = 0x0fffffffu, CELL_PRESENT = 0x80000000u;
 // Same for one screen row, plus the tile presence bitmaps of the two candidate tile rows (bit = tile column).
 struct alignas(16) RowDesc {
-    uint32_t rw;       // rlo | vr[0] << 8 | vr[1] << 12   (0b0011 for jr = 0, 0b1100 for jr = 1)
+    uint32_t rw;       // rlo | vr[0] << 8 | vr[1] << 12 | rlo * MAX_WIN << 16   (vr: 0b0011 for jr = 0, 0b1100 for jr = 1)
     int32_t pre_row;   // background: tex_offset + sy * tex_w under this row, -1: not covered
     uint32_t syw[2];   // [cls]: (sy * tex_w) of candidate row 0 | candidate row 1 << 16
     uint32_t rm[2][2]; // [cls][jr]: presence bitmap of class-cls tiles in tile row rlo + jr
@@ -455,7 +455,7 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
         }
         if (is_row) {
             RowDesc rd;
-            rd.rw = word; rd.pre_row = pv; rd.syw[0] = smp[0]; rd.syw[1] = smp[1];
+            rd.rw = word | ((lo <= hi ? (uint32_t)lo : 0u) * MAX_WIN) << 16; rd.pre_row = pv; rd.syw[0] = smp[0]; rd.syw[1] = smp[1];
             const int r0 = lo <= hi ? lo : MAX_WIN;       // row MAX_WIN is always empty
             const int r1 = lo < hi ? lo + 1 : MAX_WIN;
             rd.rm[0][0] = f.rowmask[0][r0]; rd.rm[0][1] = f.rowmask[0][r1];
@@ -535,14 +535,15 @@ PG2_DEV ColDesc load_col(const F& f, int X) {
     return cd;
 }
 
-// Atlas index of tile candidate q under a pixel.
+// Atlas index of tile candidate q under a pixel. q = 2 jr + jc, so the cell (rlo + jr, clo + jc) is at
+// rlo * 32 + clo + 30 jr + q; the 8-bit sx / 16-bit sy*w fields are picked with one byte permute each.
 template <int NCLASS, class F>
 PG2_DEV uint32_t tile_texel_index(const F& f, const RowDesc& rd, const ColDesc& cd, uint32_t q) {
-    const uint32_t jr = q >> 1, jc = q & 1u;
-    const uint32_t w = f.cell[((rd.rw & 31u) + jr) * MAX_WIN + (cd.cw & 31u) + jc];
+    const uint32_t jr = q >> 1;
+    const uint32_t w = f.cell[(rd.rw >> 16) + (cd.cw & 31u) + jr * 30u + q];   // rw >> 16 = rlo * MAX_WIN
     const uint32_t cls = NCLASS > 1 ? (w >> 29) & 1u : 0u;
-    const uint32_t sx = (cd.csx >> ((cls * 2u + jc) * 8u)) & 255u;
-    const uint32_t syw = ((cls ? rd.syw[1] : rd.syw[0]) >> (jr * 16u)) & 0xffffu;
+    const uint32_t sx = byte_perm(cd.csx, 0u, 0x4440u | (cls * 2u + (q & 1u)));
+    const uint32_t syw = byte_perm(cls ? rd.syw[1] : rd.syw[0], 0u, 0x4410u + jr * 0x22u);
     return (w & CELL_OFFSET_MASK) + syw + sx;
 }
 
