@@ -192,11 +192,16 @@ struct CaveFlyer {
             ctx.sync();
             {
                 int dead_index = -1;
+                float life[NPART];   // fetched before the first store: the stores cannot be proven not to alias the loads
+#pragma unroll
+                for (int i = 0; i < NPART; i++) life[i] = s.p_life[i * N + env];
+#pragma unroll
                 for (int i = 0; i < NPART; i++) {
-                    float life = __fsub_rn(s.p_life[i * N + env], dt);
-                    s.p_life[i * N + env] = life;
-                    if (life <= 0.0f) dead_index = i;
+                    life[i] = __fsub_rn(life[i], dt);
+                    if (life[i] <= 0.0f) dead_index = i;
                 }
+#pragma unroll
+                for (int i = 0; i < NPART; i++) s.p_life[i * N + env] = life[i];
                 p_timer = __fadd_rn(p_timer, dt);
                 if (dead_index != -1 && p_timer >= 0.3f && p_enabled) {
                     p_timer = fmodf(p_timer, 0.3f);

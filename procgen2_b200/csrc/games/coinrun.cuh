@@ -218,13 +218,19 @@ struct CoinRun {
             for (int e = ctx.lane; e < nents; e += ctx.nlanes) {
                 int type = s.ent_type[e * N + env];
                 if (type == E_MOB) {
+                    // all ten lifetimes are fetched before the first store (the compiler cannot prove the stores do not
+                    // alias the next load, which would serialise ten L2 round trips)
                     int dead_index = -1;
+                    float life[NPART];
+#pragma unroll
+                    for (int i = 0; i < NPART; i++) life[i] = s.part_life[(e * NPART + i) * N + env];
+#pragma unroll
                     for (int i = 0; i < NPART; i++) {
-                        int pi = (e * NPART + i) * N + env;
-                        float life = __fsub_rn(s.part_life[pi], dt);
-                        s.part_life[pi] = life;
-                        if (life <= 0.0f) dead_index = i;
+                        life[i] = __fsub_rn(life[i], dt);
+                        if (life[i] <= 0.0f) dead_index = i;
                     }
+#pragma unroll
+                    for (int i = 0; i < NPART; i++) s.part_life[(e * NPART + i) * N + env] = life[i];
                     float timer = __fadd_rn(s.part_timer[e * N + env], dt);
                     if (dead_index != -1 && timer >= 0.5f) {
                         timer = fmodf(timer, 0.5f);
