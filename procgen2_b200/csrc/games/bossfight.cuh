@@ -192,13 +192,26 @@ struct BossFight {
                     if (check_collision(wc, hazard_rect_at(k, hz_id[k]))) { alive = false; break; }
                 }
 
+                // same software pipelining as the boss's bullets below: bullet i + 1 is fetched before bullet i is stored
+                float af = -1.0f, anx = 0.0f, any_ = 0.0f, anvx = 0.0f, anvy = 0.0f, anbt = 0.0f;
+                bool anb = false;
+                if (a_num > 0) {
+                    const int b0 = ((AB + a_next - 1) % AB) * N + env;
+                    af = s.ab_frame[b0]; anx = s.ab_x[b0]; any_ = s.ab_y[b0]; anvx = s.ab_vx[b0]; anvy = s.ab_vy[b0];
+                    anb = s.ab_bouncing[b0] != 0; anbt = s.ab_bounce_timer[b0];
+                }
                 for (int i = 0; i < a_num; i++) {
                     int bi = ((AB + a_next - 1 - i) % AB) * N + env;
-                    float frame = s.ab_frame[bi];
+                    float frame = af;
+                    float x = anx, y = any_, vx = anvx, vy = anvy;
+                    bool bouncing = anb;
+                    float btimer = anbt;
+                    if (i + 1 < a_num) {
+                        const int bn = ((AB + a_next - 2 - i) % AB) * N + env;
+                        af = s.ab_frame[bn]; anx = s.ab_x[bn]; any_ = s.ab_y[bn]; anvx = s.ab_vx[bn]; anvy = s.ab_vy[bn];
+                        anb = s.ab_bouncing[bn] != 0; anbt = s.ab_bounce_timer[bn];
+                    }
                     if (frame == -1.0f) continue;
-                    float x = s.ab_x[bi], y = s.ab_y[bi], vx = s.ab_vx[bi], vy = s.ab_vy[bi];
-                    bool bouncing = s.ab_bouncing[bi] != 0;
-                    float btimer = s.ab_bounce_timer[bi];
                     if (frame == 0.0f) {
                         Rect bw{ __fsub_rn(x, 0.01f), __fsub_rn(y, 0.01f), 0.02f, 0.02f };
                         if (!check_collision(bw, screen)) { vx = 0.0f; vy = 0.0f; frame = 5.0f; }
@@ -330,11 +343,22 @@ struct BossFight {
                 bx = __fadd_rn(bx, __fmul_rn(bvx, dt));
                 by = __fadd_rn(by, __fmul_rn(bvy, dt));
 
+                // The ring is walked newest to oldest; bullet i + 1 is fetched BEFORE bullet i is stored (a store cannot be
+                // proven not to alias the next load, which would put one L2 round trip between consecutive bullets).
+                float nf = -1.0f, nx = 0.0f, ny = 0.0f, nvx = 0.0f, nvy = 0.0f;
+                if (mp.num_bullets > 0) {
+                    const int b0 = ((MB + mp.next_bullet - 1) % MB) * N + env;
+                    nf = s.mb_frame[b0]; nx = s.mb_x[b0]; ny = s.mb_y[b0]; nvx = s.mb_vx[b0]; nvy = s.mb_vy[b0];
+                }
                 for (int i = 0; i < mp.num_bullets; i++) {
                     int bi = ((MB + mp.next_bullet - 1 - i) % MB) * N + env;
-                    float frame = s.mb_frame[bi];
+                    float frame = nf;
+                    float x = nx, y = ny, vx = nvx, vy = nvy;
+                    if (i + 1 < mp.num_bullets) {   // distinct ring slot: not touched by this iteration's stores
+                        const int bn = ((MB + mp.next_bullet - 2 - i) % MB) * N + env;
+                        nf = s.mb_frame[bn]; nx = s.mb_x[bn]; ny = s.mb_y[bn]; nvx = s.mb_vx[bn]; nvy = s.mb_vy[bn];
+                    }
                     if (frame == -1.0f) continue;
-                    float x = s.mb_x[bi], y = s.mb_y[bi], vx = s.mb_vx[bi], vy = s.mb_vy[bi];
                     bool stop = false;
                     if (frame == 0.0f) {
                         Rect bw{ __fsub_rn(x, 0.01f), __fsub_rn(y, 0.01f), 0.02f, 0.02f };

@@ -214,16 +214,20 @@ struct CoinRun {
                 else if (movement_x < 0.0f) face_forward = false;
             }
 
-            // ---- System_Particles::update + System_Sprite_Render::update (animation), one entity per lane
+            // ---- System_Particles::update + System_Sprite_Render::update (animation), one entity per lane.
+            // Every load of the entity is issued before the first store (stores cannot be proven not to alias later loads).
             for (int e = ctx.lane; e < nents; e += ctx.nlanes) {
-                int type = s.ent_type[e * N + env];
-                if (type == E_MOB) {
-                    // all ten lifetimes are fetched before the first store (the compiler cannot prove the stores do not
-                    // alias the next load, which would serialise ten L2 round trips)
-                    int dead_index = -1;
-                    float life[NPART];
+                const int type = s.ent_type[e * N + env];
+                const bool mob = type == E_MOB, animated = type == E_MOB || type == E_SAW;
+                float life[NPART];
 #pragma unroll
-                    for (int i = 0; i < NPART; i++) life[i] = s.part_life[(e * NPART + i) * N + env];
+                for (int i = 0; i < NPART; i++) life[i] = mob ? s.part_life[(e * NPART + i) * N + env] : 1.0f;
+                float timer = mob ? s.part_timer[e * N + env] : 0.0f;
+                const float ent_x = mob ? s.ent_x[e * N + env] : 0.0f, ent_y = mob ? s.ent_y[e * N + env] : 0.0f;
+                float anim_t = animated ? s.ent_anim_t[e * N + env] : 0.0f;
+                const int frame = animated ? s.ent_frame[e * N + env] : 0;
+                if (mob) {
+                    int dead_index = -1;
 #pragma unroll
                     for (int i = 0; i < NPART; i++) {
                         life[i] = __fsub_rn(life[i], dt);
@@ -231,23 +235,23 @@ struct CoinRun {
                     }
 #pragma unroll
                     for (int i = 0; i < NPART; i++) s.part_life[(e * NPART + i) * N + env] = life[i];
-                    float timer = __fadd_rn(s.part_timer[e * N + env], dt);
+                    timer = __fadd_rn(timer, dt);
                     if (dead_index != -1 && timer >= 0.5f) {
                         timer = fmodf(timer, 0.5f);
                         int pi = (e * NPART + dead_index) * N + env;
                         s.part_life[pi] = 5.0f;
-                        s.part_x[pi] = __fadd_rn(s.ent_x[e * N + env], 0.0f);
-                        s.part_y[pi] = __fadd_rn(s.ent_y[e * N + env], 0.34f);
+                        s.part_x[pi] = __fadd_rn(ent_x, 0.0f);
+                        s.part_y[pi] = __fadd_rn(ent_y, 0.34f);
                     }
                     s.part_timer[e * N + env] = timer;
                 }
-                if (type == E_MOB || type == E_SAW) {
+                if (animated) {
                     const float rate = type == E_SAW ? 1.0f : 0.2f;
-                    float t = __fadd_rn(s.ent_anim_t[e * N + env], dt);
+                    float t = __fadd_rn(anim_t, dt);
                     int adv = f2i(__fmul_rn(t, rate));
                     t = __fsub_rn(t, __fdiv_rn((float)adv, rate));
                     s.ent_anim_t[e * N + env] = t;
-                    s.ent_frame[e * N + env] = (uint8_t)((s.ent_frame[e * N + env] + adv) % 2);
+                    s.ent_frame[e * N + env] = (uint8_t)((frame + adv) % 2);
                 }
             }
             if (!alive || achieved_goal) break;
