@@ -136,23 +136,25 @@ struct Climber {
                 int type = s.ent_type[e * N + env];
                 if (type == E_MOB) {
                     float x = s.ent_x[e * N + env], y = s.ent_y[e * N + env], vx = s.ent_vx[e * N + env];
+                    // fetched here, before the first store of the entity (stores cannot be proven not to alias later loads)
+                    const int spawn_x = s.ent_spawn_x[e * N + env], frame0 = s.ent_frame[e * N + env];
+                    const float anim_t0 = s.ent_anim_t[e * N + env];
                     x = __fadd_rn(x, __fmul_rn(vx, dt));
                     Rect wall_sensor{ __fsub_rn(x, 0.5f), __fsub_rn(y, 0.6f), 1.0f, 0.5f };
                     CollisionResult wc = tile_collision(wall_sensor, tile_at, wall);
                     x = __fadd_rn(wc.x, 0.5f);
                     Rect rect{ __fadd_rn(-0.4f, x), __fadd_rn(-0.4f, y), 0.8f, 0.8f };
                     if (check_collision(agent_rect, rect)) hit = true;
-                    int spawn_x = s.ent_spawn_x[e * N + env];
                     bool end_patrol = x > (float)(spawn_x + 4) || x < (float)(spawn_x - 4);
                     if (wc.collided || end_patrol) vx = __fmul_rn(vx, -1.0f);
                     s.ent_x[e * N + env] = x; s.ent_vx[e * N + env] = vx;
                     s.ent_flip[e * N + env] = vx < 0.0f;
                     // System_Sprite_Render::update (animation) of the same entity
-                    float t = __fadd_rn(s.ent_anim_t[e * N + env], dt);
+                    float t = __fadd_rn(anim_t0, dt);
                     int adv = f2i(__fmul_rn(t, 0.2f));
                     t = __fsub_rn(t, __fdiv_rn((float)adv, 0.2f));
                     s.ent_anim_t[e * N + env] = t;
-                    s.ent_frame[e * N + env] = (uint8_t)((s.ent_frame[e * N + env] + adv) % 2);
+                    s.ent_frame[e * N + env] = (uint8_t)((frame0 + adv) % 2);
                 } else if (type == E_POINT) {
                     Rect rect{ __fadd_rn(-0.5f, s.ent_x[e * N + env]), __fadd_rn(-0.5f, s.ent_y[e * N + env]), 1.0f, 1.0f };
                     if (check_collision(agent_rect, rect)) { delta++; s.ent_type[e * N + env] = E_NONE; }
