@@ -115,7 +115,8 @@ template <class G>
 __global__ void __launch_bounds__(RENDER_THREADS, PG2_RENDER_MIN_CTAS) k_render(typename G::State s, CommonState c, const TexInfo* __restrict__ tex,
                                                            const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs,
                                                            int* __restrict__ ticket, int mode, const int* __restrict__ list,
-                                                           const int* __restrict__ list_count, const uint8_t* __restrict__ pending, int N) {
+                                                           const int* __restrict__ list_count, const uint8_t* __restrict__ pending, int N,
+                                                           uint8_t* __restrict__ view_cache) {
     __shared__ FrameOf<G> f;
     __shared__ int s_env;
     const int count = mode == 2 ? *list_count : N;
@@ -129,14 +130,18 @@ __global__ void __launch_bounds__(RENDER_THREADS, PG2_RENDER_MIN_CTAS) k_render(
     if (threadIdx.x == 0) next = take_ticket();
     for (;;) {
         __syncthreads();   // every warp is done with the previous frame (bands are stored per warp, without a CTA barrier)
-        if (threadIdx.x == 0) s_env = next < count ? (mode == 2 ? list[next] : next) : -1;
-        frame_begin(f);
+        bool reuse = false;
+        if (threadIdx.x == 0) {
+            s_env = next < count ? (mode == 2 ? list[next] : next) : -1;
+            reuse = G::STATIC_VIEW && view_cache != nullptr && s_env >= 0 && c.view_valid[s_env] != 0;
+        }
+        frame_begin(f, reuse);
         __syncthreads();
         const int env = s_env;
         if (env < 0) break;
         // the next frame's ticket is taken now: the atomic's round trip overlaps this frame's work
         if (threadIdx.x == 0) next = take_ticket();
-        render_body<G>(s, c, env, f, tex, atlas, obs, false);
+        render_body<G>(s, c, env, f, tex, atlas, obs, view_cache, false);
     }
     if ((threadIdx.x & 31) == 0) frame_store_wait();   // every warp issued bulk stores of its own
 }
@@ -192,6 +197,7 @@ struct EngineBase {
     cudaEvent_t ev_step[2] = { nullptr, nullptr }, ev_copy[2] = { nullptr, nullptr }, ev_h2d[2] = { nullptr, nullptr };
     bool copy_pending[2] = { false, false };
     uint8_t* sort_table = nullptr;
+    uint8_t* view_cache = nullptr;   // G::STATIC_VIEW: VIEW_BLOCK_BYTES per env (k_render keeps the view of an episode)
     // optional per-kernel timing
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;   // 4 per step
@@ -238,7 +244,7 @@ struct EngineBase {
         if (stream) cudaStreamSynchronize(stream);
         if (pipelined) { cudaStreamSynchronize(copy_stream); obs = obs_b[0]; reward = reward_b[0]; terminated = term_b[0]; truncated = trunc_b[0]; }
         cudaFree(state_mem); cudaFree(common_mem); cudaFree(obs); cudaFree(reward); cudaFree(terminated);
-        cudaFree(truncated); cudaFree(actions); cudaFree(seeds_dev); cudaFree(reset_list); cudaFree(reset_count);
+        cudaFree(truncated); cudaFree(actions); cudaFree(seeds_dev); cudaFree(reset_list); cudaFree(reset_count); cudaFree(view_cache);
         cudaFree(texinfo); cudaFree(atlas); cudaFree(sort_table); cudaFree(pending);
         if (reset_stream) { cudaStreamSynchronize(reset_stream); cudaStreamDestroy(reset_stream); cudaEventDestroy(ev_stepped); cudaEventDestroy(ev_reset_done); }
         if (actions_pinned) cudaFreeHost(actions_pinned);
@@ -288,6 +294,7 @@ struct Engine : EngineBase {
         PG2_CUDA(cudaMalloc(&actions, sizeof(int32_t) * N));
         PG2_CUDA(cudaMalloc(&seeds_dev, sizeof(int32_t) * N));
         PG2_CUDA(cudaMalloc(&reset_list, sizeof(int) * N));
+        if (G::STATIC_VIEW) PG2_CUDA(cudaMalloc(&view_cache, (size_t)N * VIEW_BLOCK_BYTES));
         PG2_CUDA(cudaMalloc(&reset_count, 4 * sizeof(int)));
         PG2_CUDA(cudaMemsetAsync(reset_count, 0, 4 * sizeof(int), stream));
         PG2_CUDA(cudaMalloc(&pending, N));
@@ -348,7 +355,7 @@ struct Engine : EngineBase {
         int per_sm = 8;
         if (const char* o = getenv("PG2_RENDER_CTAS_PER_SM")) per_sm = atoi(o) > 0 ? atoi(o) : per_sm;
         int grid = N < num_sms * per_sm ? N : num_sms * per_sm;
-        k_render<G><<<grid, RENDER_THREADS, 0, on>>>(st, common, texinfo, atlas, obs, ticket, mode, reset_list, reset_count + parity, pending, N);
+        k_render<G><<<grid, RENDER_THREADS, 0, on>>>(st, common, texinfo, atlas, obs, ticket, mode, reset_list, reset_count + parity, pending, N, view_cache);
         launches++;
     }
 
@@ -599,6 +606,7 @@ int64_t pg2_write_field(pg2_engine* e, const char* name, const void* in, int64_t
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     if (cudaMemcpy(ptr, in, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { g_error = "pg2_write_field: copy failed"; return -3; }
+    cudaMemset(b->common.view_valid, 0, (size_t)b->N);   // a tile map or camera may have changed: drop the cached views
     return bytes;
 }
 
@@ -650,6 +658,7 @@ int64_t pg2_restore(pg2_engine* e, const void* blob, int64_t bytes) {
     ok = ok && cudaMemcpy(b->truncated, p, n, cudaMemcpyHostToDevice) == cudaSuccess;
     // the reset-list counters are transient within a step: zero them like a fresh engine, keep the parity of the snapshot
     ok = ok && cudaMemset(b->reset_count, 0, 4 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMemset(b->common.view_valid, 0, (size_t)b->N) == cudaSuccess;   // the view caches are not part of the blob
     b->parity = h.parity;
     if (!ok) { g_error = "pg2_restore: copy failed"; return -3; }
     return total;

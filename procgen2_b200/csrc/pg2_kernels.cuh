@@ -13,7 +13,7 @@ PG2_DEV_NOINLINE void seed_body(const CommonState& c, int env, uint32_t seed, bo
     c.mti[env] = MT_N;
     if (init_persistent) {
         c.cam_x[env] = 0.0f; c.cam_y[env] = 0.0f;   // Renderer::camera_position{0} (renderer.h:18)
-        c.sprites_valid[env] = 0; c.ep_steps[env] = 0; c.fault[env] = 0;
+        c.sprites_valid[env] = 0; c.ep_steps[env] = 0; c.fault[env] = 0; c.view_valid[env] = 0;
     }
 }
 
@@ -56,24 +56,33 @@ PG2_DEV void reset_body(const typename G::State& s, const CommonState& c, int en
     G::regenerate(s, c, env, ctx);
     __syncwarp();
     for (int i = lane; i < MT_N; i += WARP_LANES) gmt[i] = mt[i];
-    if (lane == 0) { c.mti[env] = ctx.rng.idx; c.ep_steps[env] = 0; }
+    if (lane == 0) { c.mti[env] = ctx.rng.idx; c.ep_steps[env] = 0; c.view_valid[env] = 0; }   // new level: the cached view is stale
     __syncwarp();
 }
 
 template <class G>
 using FrameOf = FrameT<G::MAX_POST, G::ROTATES, G::TILE_CLASSES>;
 
-// render_game(true) + RGBA->RGB pack for one env by one CTA (f.tiletex filled by frame_init_tiletex before)
+// render_game(true) + RGBA->RGB pack for one env by one CTA (f.tileword filled by frame_init_tiletex before).
+// view_cache (G::STATIC_VIEW games, else nullptr): VIEW_BLOCK_BYTES per env; c.view_valid[env] says whether it is current.
 template <class G>
 PG2_DEV void render_body(const typename G::State& s, const CommonState& c, int env, FrameOf<G>& f, const TexInfo* __restrict__ tex,
-                         const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs, bool begin_and_sync = true) {
+                         const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs, uint8_t* __restrict__ view_cache = nullptr,
+                         bool begin_and_sync = true) {
+    uint8_t* cache = (G::STATIC_VIEW && view_cache) ? view_cache + (size_t)env * VIEW_BLOCK_BYTES : nullptr;
     if (begin_and_sync) {
-        frame_begin(f);
+        frame_begin(f, cache != nullptr && c.view_valid[env] != 0);
         __syncthreads();
     }
+    const bool reuse = f.reuse != 0;
+    if (reuse) load_view(f, cache);
     G::build_frame(s, c, env, f, tex);
     __syncthreads();   // the only barrier between the frame builder's smem writes and their readers
     frame_finalize<G>(f);
+    if (cache && !reuse && !f.wide) {   // first frame of the episode: keep the view for the following ones
+        store_view(f, cache);
+        if (threadIdx.x == 0) c.view_valid[env] = 1;   // read by later launches only
+    }
     frame_rasterise<G>(f, atlas, obs + (size_t)env * OBS_BYTES);
 }
 

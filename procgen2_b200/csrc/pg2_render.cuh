@@ -89,27 +89,35 @@ struct FrameT {
     static constexpr int MAX_POST = MAXP, NROT = ROT ? MAXP : 1;
     static constexpr bool ROTATES = ROT;
     alignas(16) uint8_t band_rgb[RENDER_THREADS / 32][BAND_BYTES];   // per warp: the band it is drawing, packed RGB rows
-    uint32_t col_cw[OBS_W], col_csx[OBS_W];     // ColDesc fields, indexed by col_slot(X)
+    // ---- the view: everything the rasteriser needs of background + tile layer. For games whose camera and tile map
+    // do not change within an episode (G::STATIC_VIEW) this block is kept per env in HBM and re-loaded instead of rebuilt.
+    alignas(16) uint32_t col_cw[OBS_W];         // ColDesc fields, indexed by col_slot(X)
+    uint32_t col_csx[OBS_W];
     int32_t col_pre[OBS_W];
     RowDesc rowd[OBS_H];
-    FastBlit fpost[MAXP];
+    uint32_t cell[(MAX_WIN + 1) * MAX_WIN];     // window cells (+1 row: branch-free reads)
     FastBlit fpre[MAX_PRE];
+    int npre;
+    int wide;                                   // the frame needs the general ordered path for every pixel (never observed)
+    int pre_blend;                              // background texture carries alpha
+    int view_pad;
+    alignas(16) int view_end;                   // marker: [col_cw, view_end) is the view block
+    // ---- per frame
+    int reuse;                                  // the view block was loaded from the cache: skip its construction
+    FastBlit fpost[MAXP];
     BlitRot post_rot[NROT];
     Blit pre[MAX_PRE];
-    int npre, npost;
+    int npost;
     // tile layer: window origin (tile coordinates, y in render space), extents, descriptors per texture shape class
     int tx0, ty0, ncol, nrow, nclass;
     Axis col[NCLS][MAX_WIN];
     Axis row[NCLS][MAX_WIN];
-    uint32_t cell[(MAX_WIN + 1) * MAX_WIN];     // window cells (+1 row: branch-free reads)
     uint32_t rowmask[2][MAX_WIN + 1];           // [cls][tile row]: bit cx set = a class-cls tile at window column cx
     int cov_lo[2 * OBS_W], cov_hi[2 * OBS_W];   // [0,64): per screen column, [64,128): per screen row: covering tile range
-    uint8_t bandmask[MAXP];                     // post blit k touches band b <=> bit b
+    uint16_t bandmask[MAXP];                    // post blit k touches band b <=> bit b
     uint8_t live[256];                          // live_list(): ids of the live sprites in set order
     int wcount[2][RENDER_THREADS / 32];         // emit_post_blits: visible blits per warp (double-buffered by round)
     int next_band;                              // dynamic hand-out of the row bands to warps
-    int wide;                                   // the frame needs the general ordered path for every pixel (never observed)
-    int pre_blend;                              // background texture carries alpha
     int class_w[2];                             // texture width of the tile shape classes
     uint32_t tileword[MAX_TILE_TEX];            // per CTA (filled once): window cell word of every tile texture id
 };
@@ -335,12 +343,34 @@ PG2_DEV void tile_window(const Camera& cam, int* lower_x, int* lower_y, int* upp
     *upper_y = f2i(ceilf(__fadd_rn(ay, aw)));
 }
 
-// Start of a frame (every thread; followed by a __syncthreads() before the game's frame builder runs).
+// Bytes of the view block of a frame ([col_cw, view_end)): identical for every game (checked in frame_init_tiletex).
+constexpr size_t VIEW_BLOCK_BYTES = 3 * OBS_W * 4 + OBS_H * sizeof(RowDesc) + (MAX_WIN + 1) * MAX_WIN * 4 + MAX_PRE * sizeof(FastBlit) + 16;
+
+// Start of a frame (every thread; followed by a __syncthreads() before the game's frame builder runs). `reuse`: the view
+// block comes from the env's cache (loaded by load_view right after that barrier).
 template <class F>
-PG2_DEV void frame_begin(F& f) {
+PG2_DEV void frame_begin(F& f, bool reuse = false) {   // `reuse` is only looked at by thread 0 (which knows the env)
     const int tid = threadIdx.x;
-    if (tid == 0) { f.npre = 0; f.npost = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1; f.wide = 0; f.next_band = 0; f.pre_blend = 0; }
+    if (tid == 0) {
+        f.npost = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1; f.next_band = 0; f.reuse = reuse ? 1 : 0;
+        if (!reuse) { f.npre = 0; f.wide = 0; f.pre_blend = 0; }
+    }
     for (int k = tid; k < 2 * OBS_W; k += blockDim.x) { f.cov_lo[k] = 255; f.cov_hi[k] = -1; }
+}
+
+// View block <-> its per-env cache in HBM (16-byte words, coalesced).
+struct alignas(16) Word16 { uint32_t a, b, c, d; };
+template <class F>
+PG2_DEV void load_view(F& f, const uint8_t* __restrict__ cache) {
+    Word16* dst = (Word16*)&f.col_cw;
+    const Word16* src = (const Word16*)cache;
+    for (int i = threadIdx.x; i < (int)(VIEW_BLOCK_BYTES / 16); i += blockDim.x) dst[i] = src[i];
+}
+template <class F>
+PG2_DEV void store_view(const F& f, uint8_t* __restrict__ cache) {
+    const Word16* src = (const Word16*)&f.col_cw;
+    Word16* dst = (Word16*)cache;
+    for (int i = threadIdx.x; i < (int)(VIEW_BLOCK_BYTES / 16); i += blockDim.x) dst[i] = src[i];
 }
 
 // Background + tile layer of a frame (the "pre" blit of render_game and System_Tilemap::render, tilemap.cpp:294-320),
@@ -358,6 +388,7 @@ PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int n
                               ClassTex class_tex, TileAt tile_at, int bg_tex, float bg_x, float bg_y, float bg_scale) {
     const int tid = threadIdx.x, lane = tid % WARP_LANES, warp = tid / WARP_LANES;
     const int nwarps = ((int)blockDim.x + WARP_LANES - 1) / WARP_LANES;
+    if (f.reuse) return;   // the view block (descriptors, cells, background) was loaded from the env's cache
     const int per = ncol + nrow, njobs = 2 + nclass * per;
     if (tid == 0) { f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = nclass; f.npre = 1; }
     for (int job = (int)blockDim.x - 1 - tid; job < njobs; job += blockDim.x) {
@@ -405,6 +436,7 @@ PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int n
 // After the game's frame builder (and a __syncthreads()): ColDesc / RowDesc of every screen column / row.
 template <class G, class F>
 PG2_DEV_NOINLINE void frame_finalize(F& f) {
+    if (f.reuse) { __syncthreads(); return; }
     const int tid = threadIdx.x;
     const int npre = f.npre, nclass = f.nclass;
     // the fast path handles ONE un-rotated background with alpha_mod 255
@@ -736,6 +768,7 @@ PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas, 
 // Per-CTA table of the game's tile textures (ids < MAX_TILE_TEX) as window cell words, filled once before the first frame.
 template <class G, class F>
 PG2_DEV void frame_init_tiletex(F& f, const TexInfo* __restrict__ tex) {
+    static_assert(offsetof(F, view_end) - offsetof(F, col_cw) == VIEW_BLOCK_BYTES && offsetof(F, col_cw) % 16 == 0, "view block layout");
     for (int t = threadIdx.x; t < MAX_TILE_TEX; t += blockDim.x) {
         uint32_t w = 0u;
         if (t < G::NUM_TEX) {

@@ -58,7 +58,8 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
     F(float, cam_y, 1)                                                                         \
     F(uint8_t, sprites_valid, 1)  /* sprite draw list rebuilt since the last reset (Q9) */     \
     F(int32_t, ep_steps, 1)       /* steps in the current episode (max_episode_steps ext.) */  \
-    F(int32_t, fault, 1)          /* latent-UB sites of the reference hit (Q20) */
+    F(int32_t, fault, 1)          /* latent-UB sites of the reference hit (Q20) */                \
+    F(uint8_t, view_valid, 1)     /* the env's cached view block (k_render, G::STATIC_VIEW) is current */
 
 PG2_DEFINE_STATE(CommonState, PG2_COMMON_FIELDS)
 

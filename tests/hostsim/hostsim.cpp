@@ -37,6 +37,7 @@ struct Sim : SimBase {
     typename G::State st;
     CommonState c;
     std::vector<char> state_mem, common_mem, arena;
+    std::vector<uint8_t> view_cache;
     std::vector<uint32_t> mt_scratch;
     std::vector<TexInfo> tex;
     std::vector<uint32_t> atlas;
@@ -49,6 +50,7 @@ struct Sim : SimBase {
         st = G::State::bind(state_mem.data(), N);
         c = CommonState::bind(common_mem.data(), N);
         arena.assign(G::RESET_ARENA, 0);
+        view_cache.assign((size_t)N * VIEW_BLOCK_BYTES, 0);
         mt_scratch.assign(MT_N, 0);
         frame.reset(new FrameOf<G>());
         obs.assign((size_t)N * OBS_BYTES, 0); terminated.assign(N, 0); truncated.assign(N, 0); reward.assign(N, 0.0f);
@@ -60,7 +62,7 @@ struct Sim : SimBase {
         for (int e = 0; e < N; e++) reset_body<G>(st, c, e, mt_scratch.data(), arena.data(), 0);
         return true;
     }
-    void render(int e) { render_body<G>(st, c, e, *frame, tex.data(), atlas.data(), obs.data()); }
+    void render(int e) { render_body<G>(st, c, e, *frame, tex.data(), atlas.data(), obs.data(), G::STATIC_VIEW ? view_cache.data() : nullptr); }
     void reset_all(const int32_t* seeds) override {
         for (int e = 0; e < N; e++) {
             if (seeds) seed_body(c, e, (uint32_t)seeds[e], false);
