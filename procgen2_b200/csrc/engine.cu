@@ -197,7 +197,7 @@ struct EngineBase {
     cudaEvent_t ev_step[2] = { nullptr, nullptr }, ev_copy[2] = { nullptr, nullptr }, ev_h2d[2] = { nullptr, nullptr };
     bool copy_pending[2] = { false, false };
     uint8_t* sort_table = nullptr;
-    uint8_t* view_cache = nullptr;   // G::STATIC_VIEW: VIEW_BLOCK_BYTES per env (k_render keeps the view of an episode)
+    uint8_t* view_cache = nullptr;   // G::STATIC_VIEW: VIEW_CACHE_BYTES per env (k_render keeps the view of an episode)
     // optional per-kernel timing
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;   // 4 per step
@@ -294,7 +294,7 @@ struct Engine : EngineBase {
         PG2_CUDA(cudaMalloc(&actions, sizeof(int32_t) * N));
         PG2_CUDA(cudaMalloc(&seeds_dev, sizeof(int32_t) * N));
         PG2_CUDA(cudaMalloc(&reset_list, sizeof(int) * N));
-        if (G::STATIC_VIEW) PG2_CUDA(cudaMalloc(&view_cache, (size_t)N * VIEW_BLOCK_BYTES));
+        if (G::STATIC_VIEW) PG2_CUDA(cudaMalloc(&view_cache, (size_t)N * VIEW_CACHE_BYTES));
         PG2_CUDA(cudaMalloc(&reset_count, 4 * sizeof(int)));
         PG2_CUDA(cudaMemsetAsync(reset_count, 0, 4 * sizeof(int), stream));
         PG2_CUDA(cudaMalloc(&pending, N));

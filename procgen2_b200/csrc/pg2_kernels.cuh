@@ -64,26 +64,24 @@ template <class G>
 using FrameOf = FrameT<G::MAX_POST, G::ROTATES, G::TILE_CLASSES>;
 
 // render_game(true) + RGBA->RGB pack for one env by one CTA (f.tileword filled by frame_init_tiletex before).
-// view_cache (G::STATIC_VIEW games, else nullptr): VIEW_BLOCK_BYTES per env; c.view_valid[env] says whether it is current.
+// view_cache (G::STATIC_VIEW games, else nullptr): VIEW_CACHE_BYTES per env = the env's base image;
+// c.view_valid[env] says whether it is current.
 template <class G>
 PG2_DEV void render_body(const typename G::State& s, const CommonState& c, int env, FrameOf<G>& f, const TexInfo* __restrict__ tex,
                          const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs, uint8_t* __restrict__ view_cache = nullptr,
                          bool begin_and_sync = true) {
-    uint8_t* cache = (G::STATIC_VIEW && view_cache) ? view_cache + (size_t)env * VIEW_BLOCK_BYTES : nullptr;
+    uint8_t* cache = (G::STATIC_VIEW && view_cache) ? view_cache + (size_t)env * VIEW_CACHE_BYTES : nullptr;
     if (begin_and_sync) {
         frame_begin(f, cache != nullptr && c.view_valid[env] != 0);
         __syncthreads();
     }
-    const bool reuse = f.reuse != 0;
-    if (reuse) load_view(f, cache);
     G::build_frame(s, c, env, f, tex);
     __syncthreads();   // the only barrier between the frame builder's smem writes and their readers
     frame_finalize<G>(f);
-    if (cache && !reuse && !f.wide) {   // first frame of the episode: keep the view for the following ones
-        store_view(f, cache);
-        if (threadIdx.x == 0) c.view_valid[env] = 1;   // read by later launches only
-    }
-    frame_rasterise<G>(f, atlas, obs + (size_t)env * OBS_BYTES);
+    // a frame that needs the general ordered path everywhere (never observed) is neither cached nor marked
+    uint8_t* img = (cache && (f.reuse || !f.wide)) ? cache : nullptr;
+    frame_rasterise<G>(f, atlas, obs + (size_t)env * OBS_BYTES, img);
+    if (img && !f.reuse && threadIdx.x == 0) c.view_valid[env] = 1;   // read by later launches only
 }
 
 }  // namespace pg2

@@ -89,8 +89,7 @@ struct FrameT {
     static constexpr int MAX_POST = MAXP, NROT = ROT ? MAXP : 1;
     static constexpr bool ROTATES = ROT;
     alignas(16) uint8_t band_rgb[RENDER_THREADS / 32][BAND_BYTES];   // per warp: the band it is drawing, packed RGB rows
-    // ---- the view: everything the rasteriser needs of background + tile layer. For games whose camera and tile map
-    // do not change within an episode (G::STATIC_VIEW) this block is kept per env in HBM and re-loaded instead of rebuilt.
+    // ---- the view: everything the rasteriser needs of background + tile layer
     alignas(16) uint32_t col_cw[OBS_W];         // ColDesc fields, indexed by col_slot(X)
     uint32_t col_csx[OBS_W];
     int32_t col_pre[OBS_W];
@@ -100,10 +99,8 @@ struct FrameT {
     int npre;
     int wide;                                   // the frame needs the general ordered path for every pixel (never observed)
     int pre_blend;                              // background texture carries alpha
-    int view_pad;
-    alignas(16) int view_end;                   // marker: [col_cw, view_end) is the view block
     // ---- per frame
-    int reuse;                                  // the view block was loaded from the cache: skip its construction
+    int reuse;                                  // the base image comes from the env's cache: the view is not built
     FastBlit fpost[MAXP];
     BlitRot post_rot[NROT];
     Blit pre[MAX_PRE];
@@ -343,11 +340,13 @@ PG2_DEV void tile_window(const Camera& cam, int* lower_x, int* lower_y, int* upp
     *upper_y = f2i(ceilf(__fadd_rn(ay, aw)));
 }
 
-// Bytes of the view block of a frame ([col_cw, view_end)): identical for every game (checked in frame_init_tiletex).
-constexpr size_t VIEW_BLOCK_BYTES = 3 * OBS_W * 4 + OBS_H * sizeof(RowDesc) + (MAX_WIN + 1) * MAX_WIN * 4 + MAX_PRE * sizeof(FastBlit) + 16;
+// Games whose camera and tile map are fixed within an episode (G::STATIC_VIEW: maze, chaser) keep the BASE IMAGE of an env
+// (clear + background + tile layer, 12 288 B of packed RGB) in HBM: the first frame of an episode draws and stores it, the
+// following frames load it band by band instead of describing and rasterising the tile layer again.
+constexpr size_t VIEW_CACHE_BYTES = OBS_BYTES;
 
-// Start of a frame (every thread; followed by a __syncthreads() before the game's frame builder runs). `reuse`: the view
-// block comes from the env's cache (loaded by load_view right after that barrier).
+// Start of a frame (every thread; followed by a __syncthreads() before the game's frame builder runs). `reuse`: the base
+// image comes from the env's cache (G::STATIC_VIEW), so the view is not built.
 template <class F>
 PG2_DEV void frame_begin(F& f, bool reuse = false) {   // `reuse` is only looked at by thread 0 (which knows the env)
     const int tid = threadIdx.x;
@@ -358,19 +357,13 @@ PG2_DEV void frame_begin(F& f, bool reuse = false) {   // `reuse` is only looked
     for (int k = tid; k < 2 * OBS_W; k += blockDim.x) { f.cov_lo[k] = 255; f.cov_hi[k] = -1; }
 }
 
-// View block <-> its per-env cache in HBM (16-byte words, coalesced).
+// One band of the base image: band buffer <-> cache (16-byte words, 3 per lane, coalesced).
 struct alignas(16) Word16 { uint32_t a, b, c, d; };
-template <class F>
-PG2_DEV void load_view(F& f, const uint8_t* __restrict__ cache) {
-    Word16* dst = (Word16*)&f.col_cw;
-    const Word16* src = (const Word16*)cache;
-    for (int i = threadIdx.x; i < (int)(VIEW_BLOCK_BYTES / 16); i += blockDim.x) dst[i] = src[i];
+PG2_DEV void band_from_cache(uint8_t* buf, const uint8_t* __restrict__ cache_band, int lane) {
+    for (int i = lane; i < BAND_BYTES / 16; i += WARP_LANES) ((Word16*)buf)[i] = ((const Word16*)cache_band)[i];
 }
-template <class F>
-PG2_DEV void store_view(const F& f, uint8_t* __restrict__ cache) {
-    const Word16* src = (const Word16*)&f.col_cw;
-    Word16* dst = (Word16*)cache;
-    for (int i = threadIdx.x; i < (int)(VIEW_BLOCK_BYTES / 16); i += blockDim.x) dst[i] = src[i];
+PG2_DEV void band_to_cache(const uint8_t* buf, uint8_t* __restrict__ cache_band, int lane) {
+    for (int i = lane; i < BAND_BYTES / 16; i += WARP_LANES) ((Word16*)cache_band)[i] = ((const Word16*)buf)[i];
 }
 
 // Background + tile layer of a frame (the "pre" blit of render_game and System_Tilemap::render, tilemap.cpp:294-320),
@@ -388,7 +381,7 @@ PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int n
                               ClassTex class_tex, TileAt tile_at, int bg_tex, float bg_x, float bg_y, float bg_scale) {
     const int tid = threadIdx.x, lane = tid % WARP_LANES, warp = tid / WARP_LANES;
     const int nwarps = ((int)blockDim.x + WARP_LANES - 1) / WARP_LANES;
-    if (f.reuse) return;   // the view block (descriptors, cells, background) was loaded from the env's cache
+    if (f.reuse) return;   // the base image comes from the env's cache: no descriptors, cells or background needed
     const int per = ncol + nrow, njobs = 2 + nclass * per;
     if (tid == 0) { f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = nclass; f.npre = 1; }
     for (int job = (int)blockDim.x - 1 - tid; job < njobs; job += blockDim.x) {
@@ -737,8 +730,9 @@ PG2_DEV void band_store(uint8_t* __restrict__ dst, const uint8_t* buf, int lane)
 
 // Draw the frame: warps take bands from a ticket counter (a warp that drew cheap bands simply takes more of them),
 // per band: base pass, post blits in submission order, bulk store.
+// cache_img != nullptr (G::STATIC_VIEW): the env's base image; f.reuse says whether to load it or to (draw and) store it.
 template <class G, class F>
-PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas, uint8_t* __restrict__ dst) {
+PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas, uint8_t* __restrict__ dst, uint8_t* __restrict__ cache_img = nullptr) {
     const int lane = threadIdx.x % WARP_LANES;
     uint8_t* buf = f.band_rgb[threadIdx.x / WARP_LANES % (RENDER_THREADS / 32)];
     const int npost = f.npost;
@@ -747,7 +741,13 @@ PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas, 
         if (lane == 0) { band = smem_atomic_inc(&f.next_band); frame_store_wait(); }   // the previous band has left the buffer
         band = warp_bcast(band);
         if (band >= NUM_BANDS) break;
-        raster_band_base<G>(f, atlas, band, lane, buf);
+        if (cache_img != nullptr && f.reuse) {
+            __syncwarp();
+            band_from_cache(buf, cache_img + band * BAND_BYTES, lane);
+        } else {
+            raster_band_base<G>(f, atlas, band, lane, buf);
+            if (cache_img != nullptr) { __syncwarp(); band_to_cache(buf, cache_img + band * BAND_BYTES, lane); }
+        }
         __syncwarp();
         for (int base = 0; base < npost; base += 32) {
             uint32_t m = 0u;
@@ -768,7 +768,6 @@ PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas, 
 // Per-CTA table of the game's tile textures (ids < MAX_TILE_TEX) as window cell words, filled once before the first frame.
 template <class G, class F>
 PG2_DEV void frame_init_tiletex(F& f, const TexInfo* __restrict__ tex) {
-    static_assert(offsetof(F, view_end) - offsetof(F, col_cw) == VIEW_BLOCK_BYTES && offsetof(F, col_cw) % 16 == 0, "view block layout");
     for (int t = threadIdx.x; t < MAX_TILE_TEX; t += blockDim.x) {
         uint32_t w = 0u;
         if (t < G::NUM_TEX) {

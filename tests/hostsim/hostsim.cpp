@@ -50,7 +50,7 @@ struct Sim : SimBase {
         st = G::State::bind(state_mem.data(), N);
         c = CommonState::bind(common_mem.data(), N);
         arena.assign(G::RESET_ARENA, 0);
-        view_cache.assign((size_t)N * VIEW_BLOCK_BYTES, 0);
+        view_cache.assign((size_t)N * VIEW_CACHE_BYTES, 0);
         mt_scratch.assign(MT_N, 0);
         frame.reset(new FrameOf<G>());
         obs.assign((size_t)N * OBS_BYTES, 0); terminated.assign(N, 0); truncated.assign(N, 0); reward.assign(N, 0.0f);
