@@ -53,7 +53,7 @@ struct BossFight {
     static constexpr int RESET_ARENA = 2 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
     static constexpr int TILE_CLASSES = 1;
     static constexpr bool HAS_TILES = false;     // the frame has a tile layer
-    static constexpr bool STATIC_VIEW = false;   // camera and tile map are fixed within an episode: the view block is cached per env
+    static constexpr bool STATIC_VIEW = true;    // fixed camera, no tile layer: the background image is cached per env
     static constexpr int MB = 64, NEX = 8, AB = 32, MAX_BAR = 4;
     enum Tex {
         T_BOSS0 = 0,       // 4 enemy ships

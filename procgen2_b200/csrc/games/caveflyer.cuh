@@ -49,7 +49,7 @@ struct CaveFlyer {
     static constexpr int RESET_ARENA = 52 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
     static constexpr int TILE_CLASSES = 1;
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
-    static constexpr bool STATIC_VIEW = false;   // camera and tile map are fixed within an episode: the view block is cached per env
+    static constexpr bool STATIC_VIEW = false;   // the camera follows the agent: the base image changes every frame (a camera-keyed cache measured slower)
     enum Obj { O_NONE = 0, O_OBSTACLE, O_TARGET, O_ENEMY };
     enum Tex { T_WALL = 0, T_GOAL, T_TARGET, T_OBSTACLE, T_ENEMY, T_BULLET, T_SHIP, T_PARTICLE, T_EXPL0, T_BG0 = 13, NUM_BG = 13, NUM_TEX = 26 };
 

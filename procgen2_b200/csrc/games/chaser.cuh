@@ -49,7 +49,7 @@ struct Chaser {
     static constexpr int RESET_ARENA = 10 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
     static constexpr int TILE_CLASSES = 1;
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
-    static constexpr bool STATIC_VIEW = true;   // camera and tile map are fixed within an episode: the view block is cached per env
+    static constexpr bool STATIC_VIEW = true;    // fixed camera and tile map within an episode: the base image (background + tiles) is cached per env
     static constexpr int TILE_STRIDE = 128, FREE_STRIDE = 64;
     enum Kind { K_NONE = 0, K_ORB, K_MOB, K_POINT };
     enum Tex { T_WALL = 0, T_CRYSTAL, T_EGG, T_POINT, T_FLY0, T_FLY1, T_FLY2, T_WALK, T_AGENT, T_BG0, NUM_BG = 9, NUM_TEX = 18 };
