@@ -46,7 +46,10 @@ __device__ const uint8_t* g_sort_perm;
 #endif
 PG2_DEV int sort_perm(int n, int k) { return (n <= 16 || n > SORT_MAXN) ? k : g_sort_perm[n * SORT_MAXN + k]; }
 
-struct BlitRot { double s, c; };   // sin/cos of the blit angle (deterministic, see sincos_deg)
+struct BlitRot {
+    double s, c;       // sin/cos of the blit angle (deterministic, see sincos_deg)
+    int ex, ey;        // half extents (pixels, rounded up + 2) of the rotated rect's axis-aligned bounding box
+};
 
 // Per-pixel form of a blit (what the frame keeps): coverage test = two unsigned compares, sampling = one
 // multiply-add + shift per axis (a horizontal flip is folded into hx / incx, which wrap modulo 2^32 to the
@@ -237,12 +240,21 @@ PG2_DEV FastBlit make_fast(const Blit& b) {
     return fb;
 }
 
-// Bands (8 rows each) a blit can touch; a rotated rect is bounded by centre +- half diagonal.
-PG2_DEV uint32_t blit_bands(const FastBlit& fb) {
+// Half extents of the axis-aligned bounding box of a rotated destination rect: a pixel centre passes the inverse-mapping
+// test of rotated_texel_coords only if |x - cx| <= hw |c| + hh |s| and |y - cy| <= hw |s| + hh |c|; + 2 px of slack for
+// the integer centre and rounding (a bound only has to be conservative, it never changes which pixels are drawn).
+PG2_DEV void rotated_extents(const FastBlit& fb, BlitRot* rot) {
+    const double hw = 0.5 * (double)fb.w, hh = 0.5 * (double)fb.h, ac = fabs(rot->c), as = fabs(rot->s);
+    rot->ex = (int)ceil(hw * ac + hh * as) + 2;
+    rot->ey = (int)ceil(hw * as + hh * ac) + 2;
+}
+
+// Bands (8 rows each) a blit can touch.
+PG2_DEV uint32_t blit_bands(const FastBlit& fb, const BlitRot& rot) {
     int y0 = fb.y0, y1 = fb.y0 + fb.h - 1;
     if (fb.flags & 2u) {
-        int rad = ((int)fb.w + (int)fb.h) / 2 + 2, cy = fb.y0 + fb.h / 2;
-        y0 = cy - rad; y1 = cy + rad;
+        const int cy = fb.y0 + fb.h / 2;
+        y0 = cy - rot.ey; y1 = cy + rot.ey;
     }
     if (y1 < 0 || y0 >= OBS_H) return 0u;
     int b0 = max(y0, 0) / BAND_ROWS, b1 = min(y1, OBS_H - 1) / BAND_ROWS;
@@ -282,7 +294,7 @@ PG2_DEV void emit_post_blits(F& f, const TexInfo* tex, int ncand, MakeFn make) {
     for (int base = 0; base < ncand; base += blockDim.x, round ^= 1) {
         int k = base + tid;
         BlitReq req; BlitRot rot;
-        req.mode = 0; rot.s = 0.0; rot.c = 1.0;
+        req.mode = 0; rot.s = 0.0; rot.c = 1.0; rot.ex = 0; rot.ey = 0;
         if (k < ncand) make(k, req, rot);
         Blit b;
         b.ax.visible = 0;
@@ -300,8 +312,9 @@ PG2_DEV void emit_post_blits(F& f, const TexInfo* tex, int ncand, MakeFn make) {
         if (vis) {
             int idx = n + before + __popc(m & ((1u << lane) - 1u));
             if (idx < F::MAX_POST) {
+                if (F::ROTATES && (fb.flags & 2u)) rotated_extents(fb, &rot);
                 f.fpost[idx] = fb;
-                f.bandmask[idx] = (uint8_t)blit_bands(fb);
+                f.bandmask[idx] = (uint8_t)blit_bands(fb, rot);
                 if (F::ROTATES) f.post_rot[idx] = rot;
             }
         }
@@ -580,7 +593,7 @@ PG2_DEV_COLD uint32_t shade_base_ordered(const F& f, const uint32_t* __restrict_
     uint32_t color = 0u, texel;   // SDL_RenderClear(0,0,0,255)
     for (int k = 0; k < f.npre; k++) {
         const FastBlit fb = f.fpre[k];
-        BlitRot rot{ 0.0, 1.0 };
+        BlitRot rot{ 0.0, 1.0, 0, 0 };
         if (!(fb.flags & 4u) && fast_texel<false>(fb, &rot, atlas, X, Y, &texel)) color = blend_packed(color, texel, fb.flags & 1u, fb.alpha_mod);
     }
     if (!f.wide) {
@@ -685,10 +698,9 @@ PG2_DEV void draw_blit_band(F& f, const uint32_t* __restrict__ atlas, int k, int
     const FastBlit fb = f.fpost[k];
     const BlitRot* rot = &f.post_rot[F::ROTATES ? k : 0];
     int x0 = fb.x0, y0 = fb.y0, x1 = fb.x0 + fb.w - 1, y1 = fb.y0 + fb.h - 1;
-    if (F::ROTATES && (fb.flags & 2u)) {   // conservative bounds of a rotated rect: centre +- half diagonal
-        int rad = ((int)fb.w + (int)fb.h) / 2 + 2;
-        int cx = fb.x0 + fb.w / 2, cy = fb.y0 + fb.h / 2;
-        x0 = cx - rad; x1 = cx + rad; y0 = cy - rad; y1 = cy + rad;
+    if (F::ROTATES && (fb.flags & 2u)) {   // bounding box of the rotated rect (rotated_extents)
+        const int cx = fb.x0 + fb.w / 2, cy = fb.y0 + fb.h / 2;
+        x0 = cx - rot->ex; x1 = cx + rot->ex; y0 = cy - rot->ey; y1 = cy + rot->ey;
     }
     x0 = max(x0, 0); x1 = min(x1, OBS_W - 1); y0 = max(y0, Y0); y1 = min(y1, Y0 + BAND_ROWS - 1);
     const uint32_t blend = fb.flags & 1u, alpha_mod = fb.alpha_mod;
