@@ -143,6 +143,9 @@ struct RoomGen {
     int* res;             // lane 0 -> all lanes: [0] best_room size, [1] path length, [2] BFS tail, [3] queue index of dst
     int* claim;           // per cell: smallest (lane * 4 + neighbour) that wants it in the running BFS chunk
     int* scratch;         // ROOM_MAX_BUCKETS ints (USetOrder)
+    uint64_t* rows_a;     // bit rows (bit y of rows[x] = cell (x, y)): grid / member / scratch of update() and expand()
+    uint64_t* rows_b;
+    uint64_t* rows_c;
 
     PG2_DEV_NOINLINE void init(WarpCtx& w, int width, int height) {
         W = width; H = height;
@@ -157,22 +160,57 @@ struct RoomGen {
         res = w.alloc<int>(4);
         claim = w.alloc<int>(ROOM_MAX_BUCKETS);     // ROOM_CELLS claims during a BFS, bucket table afterwards
         scratch = w.alloc<int>(ROOM_MAX_BUCKETS);
+        rows_a = w.alloc<uint64_t>(ROOM_DIM); rows_b = w.alloc<uint64_t>(ROOM_DIM); rows_c = w.alloc<uint64_t>(ROOM_DIM);
     }
 
     PG2_DEV int get(int x, int y) const { return (x < 0 || y < 0 || x >= W || y >= H) ? 1 : grid[y + H * x]; }
 
-    // Room_Generator::update
-    PG2_DEV_NOINLINE void update(WarpCtx& w) {
-        __syncwarp();
-        for (int i = w.lane; i < W * H; i += WARP_LANES) {
-            int x = i / H, y = i % H, n = 0;
-            for (int a = -1; a <= 1; a++)
-                for (int b = -1; b <= 1; b++) n += get(x + a, y + b) == 1;
-            tmp[i] = n >= 5 ? 1 : 0;
+    // ---- bit rows: rows[x] bit y = bytes[y + H * x] (0 / 1 bytes; H a multiple of 4, <= 64: four cells per 32-bit word)
+    PG2_DEV void bytes_to_rows(WarpCtx& w, const uint8_t* bytes, uint64_t* rows) {
+        for (int x = w.lane; x < W; x += WARP_LANES) {
+            const uint32_t* p = (const uint32_t*)(bytes + H * x);
+            uint64_t m = 0;
+            for (int k = 0; k < H / 4; k++)   // bytes b0..b3 of a word -> bits 21..24 of word * 0x204081
+                m |= (uint64_t)(((p[k] & 0x01010101u) * 0x00204081u >> 21) & 15u) << (4 * k);
+            rows[x] = m;
         }
         __syncwarp();
-        for (int i = w.lane; i < W * H; i += WARP_LANES) grid[i] = tmp[i];
+    }
+    PG2_DEV void rows_to_bytes(WarpCtx& w, const uint64_t* rows, uint8_t* bytes) {
+        for (int x = w.lane; x < W; x += WARP_LANES) {
+            uint32_t* p = (uint32_t*)(bytes + H * x);
+            const uint64_t m = rows[x];
+            for (int k = 0; k < H / 4; k++) p[k] = ((uint32_t)(m >> (4 * k)) & 15u) * 0x00204081u & 0x01010101u;
+        }
         __syncwarp();
+    }
+
+    // Room_Generator::update: a cell becomes wall iff >= 5 of the 9 cells of its Moore neighbourhood (itself included,
+    // out of bounds = wall) are walls. One lane per grid column x on 64-bit rows: the nine neighbour rows are added
+    // bit-sliced (carry-save adders), count >= 5 <=> eights | (fours & (twos | ones)).
+    PG2_DEV_NOINLINE void update(WarpCtx& w) {
+        __syncwarp();
+        bytes_to_rows(w, grid, rows_a);
+        const uint64_t ALL = H >= 64 ? ~0ull : (1ull << H) - 1ull;
+        for (int x = w.lane; x < W; x += WARP_LANES) {
+            const uint64_t r[3] = { x > 0 ? rows_a[x - 1] : ALL, rows_a[x], x < W - 1 ? rows_a[x + 1] : ALL };
+            uint64_t ones[3], twos[3];
+            for (int k = 0; k < 3; k++) {
+                const uint64_t up = ((r[k] << 1) | 1ull) & ALL;             // neighbour y - 1 (y = 0: out of bounds = wall)
+                const uint64_t dn = (r[k] >> 1) | (1ull << (H - 1));        // neighbour y + 1 (y = H-1: out of bounds)
+                ones[k] = r[k] ^ up ^ dn;
+                twos[k] = (r[k] & up) | (dn & (r[k] ^ up));
+            }
+            const uint64_t s1 = ones[0] ^ ones[1] ^ ones[2];                                   // weight 1
+            const uint64_t c1 = (ones[0] & ones[1]) | (ones[2] & (ones[0] ^ ones[1]));         // weight 2
+            const uint64_t t = twos[0] ^ twos[1] ^ twos[2];                                    // weight 2
+            const uint64_t c2 = (twos[0] & twos[1]) | (twos[2] & (twos[0] ^ twos[1]));         // weight 4
+            const uint64_t s2 = t ^ c1, c3 = t & c1;                                           // weight 2, weight 4
+            const uint64_t s4 = c2 ^ c3, s8 = c2 & c3;                                         // weight 4, weight 8
+            rows_b[x] = (s8 | (s4 & (s2 | s1))) & ALL;
+        }
+        __syncwarp();
+        rows_to_bytes(w, rows_b, grid);
     }
 
     // The queue discipline of build_room / find_path (room_generator.cpp:38-78 / 80-141) by the whole warp:
@@ -309,33 +347,29 @@ struct RoomGen {
         return res[1];
     }
 
-    // wide_path = goal_path dilated `rounds` times (Room_Generator::expand_room); member[] is the result
+    // wide_path = goal_path dilated `rounds` times (Room_Generator::expand_room); member[] is the result. A space cell
+    // joins when one of its 8 neighbours is a member on a space cell: on bit rows that is three rows OR-ed with their
+    // one-bit shifts, per round and lane (= grid column).
     PG2_DEV_NOINLINE void expand(WarpCtx& w, const uint16_t* cells_in, int n, int rounds, uint8_t* member) {
         __syncwarp();
         for (int i = w.lane; i < W * H; i += WARP_LANES) member[i] = 0;
         __syncwarp();
         for (int i = w.lane; i < n; i += WARP_LANES) member[cells_in[i]] = 1;
         __syncwarp();
+        bytes_to_rows(w, grid, rows_a);       // walls
+        bytes_to_rows(w, member, rows_b);     // members
+        const uint64_t ALL = H >= 64 ? ~0ull : (1ull << H) - 1ull;
         for (int r = 0; r < rounds; r++) {
-            for (int i = w.lane; i < W * H; i += WARP_LANES) {
-                int v = member[i];
-                if (!v && grid[i] == 0) {
-                    int x = i / H, y = i % H;
-                    for (int a = -1; a <= 1 && !v; a++)
-                        for (int b = -1; b <= 1; b++) {
-                            int nx = x + a, ny = y + b;
-                            if ((a || b) && nx >= 0 && ny >= 0 && nx < W && ny < H) {
-                                int j = ny + H * nx;
-                                if (member[j] && grid[j] == 0) { v = 1; break; }
-                            }
-                        }
-                }
-                tmp[i] = (uint8_t)v;
+            for (int x = w.lane; x < W; x += WARP_LANES) rows_c[x] = rows_b[x] & ~rows_a[x];   // members on space cells
+            __syncwarp();
+            for (int x = w.lane; x < W; x += WARP_LANES) {
+                const uint64_t qa = x > 0 ? rows_c[x - 1] : 0ull, qb = rows_c[x], qc = x < W - 1 ? rows_c[x + 1] : 0ull;
+                const uint64_t near = qa | (qa << 1) | (qa >> 1) | (qb << 1) | (qb >> 1) | qc | (qc << 1) | (qc >> 1);
+                rows_b[x] |= near & ~rows_a[x] & ALL;
             }
             __syncwarp();
-            for (int i = w.lane; i < W * H; i += WARP_LANES) member[i] = tmp[i];
-            __syncwarp();
         }
+        rows_to_bytes(w, rows_b, member);
     }
 };
 
