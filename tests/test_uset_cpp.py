@@ -21,3 +21,13 @@ def test_uset_order_regrouping_matches_libstdcxx(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.startswith("OK")
+
+
+def test_roomgen_bit_rows_match_per_cell_restatement(tmp_path):
+    """Cellular automaton and path dilation on 64-bit bit rows (pg2_roomgen.cuh) == per-cell restatements of
+    room_generator.cpp on random grids."""
+    exe = str(tmp_path / "test_roomgen_bits")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_roomgen_bits.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("OK")
