@@ -105,6 +105,45 @@ __global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::
     }
 }
 
+// Level prefetch (G::PREFETCH_LEVELS): the NEXT level of every env is generated one episode ahead into a shadow copy of the
+// state; when an env finishes, k_swap copies the shadow's reset-written fields over the live ones (one warp per finished
+// env) and hands the env to the asynchronous generator (k_reset on the shadow state, second stream), which prepares the
+// level after that. Field table: one entry per copied SoA field.
+struct SwapField { char* live; const char* shadow; int esz, per_env, env_major; };
+constexpr int MAX_SWAP_FIELDS = 64;
+struct SwapTable { SwapField f[MAX_SWAP_FIELDS]; int n; };
+
+__global__ void __launch_bounds__(128) k_swap(SwapTable t, CommonState live_c, CommonState shadow_c, const int* __restrict__ list,
+                                              const int* __restrict__ count, int* __restrict__ prep_list, int* __restrict__ prep_count, int N) {
+    const int n = *count, lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *prep_count = n;
+    // one warp per (finished env, field): the copies are independent, so the swap costs a couple of memory round trips
+    for (int item = warp; item < n * t.n; item += nwarps) {
+        const int k = item / t.n, i = item - k * t.n;
+        const int env = list[k];
+        const SwapField f = t.f[i];
+        if (f.env_major) {   // per_env contiguous elements: copy as bytes / words
+            const size_t off = (size_t)env * f.per_env * f.esz;
+            const int bytes = f.per_env * f.esz;
+            if (((off | (size_t)bytes) & 3) == 0) for (int b = lane; b < bytes / 4; b += 32) ((uint32_t*)(f.live + off))[b] = ((const uint32_t*)(f.shadow + off))[b];
+            else for (int b = lane; b < bytes; b += 32) f.live[off + b] = f.shadow[off + b];
+        } else {             // element j at [j * N + env]
+            for (int j = lane; j < f.per_env; j += 32) {
+                const size_t off = ((size_t)j * N + env) * f.esz;
+                if (f.esz == 4) *(uint32_t*)(f.live + off) = *(const uint32_t*)(f.shadow + off);
+                else if (f.esz == 1) f.live[off] = f.shadow[off];
+                else for (int b = 0; b < f.esz; b++) f.live[off + b] = f.shadow[off + b];
+            }
+        }
+        if (i == 0 && lane == 0) {   // once per env: the list entry for the generator + what reset_body does besides the level
+            prep_list[k] = env;
+            live_c.ep_steps[env] = 0; live_c.view_valid[env] = 0;
+            live_c.fault[env] |= shadow_c.fault[env];
+        }
+    }
+}
+
 #ifndef PG2_RENDER_MIN_CTAS
 #define PG2_RENDER_MIN_CTAS 8   // CTAs per SM the register allocation of k_render aims at
 #endif
@@ -157,6 +196,7 @@ struct EngineBase {
     virtual size_t state_bytes_per_env() = 0;
     virtual size_t state_alloc_bytes() = 0;     // bytes of state_mem
     virtual uint32_t game_tag() = 0;
+    virtual int init_shadow() = 0;              // level prefetch: regenerate every env's next level (after state was written)
 
     int device = 0, N = 0, max_episode_steps = 0, auto_reset = 1;
     uint32_t base_seed = 0;
@@ -197,6 +237,16 @@ struct EngineBase {
     cudaEvent_t ev_step[2] = { nullptr, nullptr }, ev_copy[2] = { nullptr, nullptr }, ev_h2d[2] = { nullptr, nullptr };
     bool copy_pending[2] = { false, false };
     uint8_t* sort_table = nullptr;
+    // level prefetch
+    bool prefetch = false;
+    void* shadow_state_mem = nullptr;
+    void* shadow_common_mem = nullptr;
+    CommonState shadow_common;
+    int* prep_list = nullptr;        // [2][N]: private copy of a step's reset list for the asynchronous generator
+    int* prep_count = nullptr;       // [2]
+    cudaStream_t prep_stream = nullptr;
+    cudaEvent_t ev_swapped = nullptr, ev_prepared = nullptr;
+    SwapTable swap_table;
     uint8_t* view_cache = nullptr;   // G::STATIC_VIEW: VIEW_CACHE_BYTES per env (k_render keeps the view of an episode)
     // optional per-kernel timing
     bool profiling = false;
@@ -245,6 +295,10 @@ struct EngineBase {
         if (pipelined) { cudaStreamSynchronize(copy_stream); obs = obs_b[0]; reward = reward_b[0]; terminated = term_b[0]; truncated = trunc_b[0]; }
         cudaFree(state_mem); cudaFree(common_mem); cudaFree(obs); cudaFree(reward); cudaFree(terminated);
         cudaFree(truncated); cudaFree(actions); cudaFree(seeds_dev); cudaFree(reset_list); cudaFree(reset_count); cudaFree(view_cache);
+        if (prep_stream) { cudaStreamSynchronize(prep_stream); cudaStreamDestroy(prep_stream); }
+        if (ev_swapped) cudaEventDestroy(ev_swapped);
+        if (ev_prepared) cudaEventDestroy(ev_prepared);
+        cudaFree(shadow_state_mem); cudaFree(shadow_common_mem); cudaFree(prep_list); cudaFree(prep_count);
         cudaFree(texinfo); cudaFree(atlas); cudaFree(sort_table); cudaFree(pending);
         if (reset_stream) { cudaStreamSynchronize(reset_stream); cudaStreamDestroy(reset_stream); cudaEventDestroy(ev_stepped); cudaEventDestroy(ev_reset_done); }
         if (actions_pinned) cudaFreeHost(actions_pinned);
@@ -262,6 +316,7 @@ struct EngineBase {
 template <class G>
 struct Engine : EngineBase {
     typename G::State st;
+    typename G::State shadow_st;
 
     int init(const pg2_config* cfg) {
         device = cfg->device; N = cfg->num_envs; max_episode_steps = cfg->max_episode_steps; auto_reset = cfg->auto_reset;
@@ -299,8 +354,27 @@ struct Engine : EngineBase {
         PG2_CUDA(cudaMemsetAsync(reset_count, 0, 4 * sizeof(int), stream));
         PG2_CUDA(cudaMalloc(&pending, N));
         PG2_CUDA(cudaMemsetAsync(pending, 0, N, stream));
-        overlap_reset = G::SLOW_RESET && auto_reset;
-        if (const char* o = getenv("PG2_OVERLAP_RESET")) overlap_reset = atoi(o) != 0 && auto_reset;
+        prefetch = G::PREFETCH_LEVELS && auto_reset;
+        if (const char* o = getenv("PG2_PREFETCH")) prefetch = atoi(o) != 0 && G::PREFETCH_LEVELS && auto_reset;
+        if (prefetch) {
+            PG2_CUDA(cudaMalloc(&shadow_state_mem, G::State::bytes(N)));
+            PG2_CUDA(cudaMalloc(&shadow_common_mem, CommonState::bytes(N)));
+            shadow_st = G::State::bind(shadow_state_mem, N);
+            shadow_common = CommonState::bind(shadow_common_mem, N);
+            PG2_CUDA(cudaMalloc(&prep_list, sizeof(int) * 2 * (size_t)N));
+            PG2_CUDA(cudaMalloc(&prep_count, 2 * sizeof(int)));
+            PG2_CUDA(cudaMemsetAsync(prep_count, 0, 2 * sizeof(int), stream));
+            {   // the generator's few long-running CTAs must get onto the SMs before the render fills them: highest priority
+                int lo = 0, hi = 0;
+                PG2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                PG2_CUDA(cudaStreamCreateWithPriority(&prep_stream, cudaStreamNonBlocking, hi));
+            }
+            PG2_CUDA(cudaEventCreateWithFlags(&ev_swapped, cudaEventDisableTiming));
+            PG2_CUDA(cudaEventCreateWithFlags(&ev_prepared, cudaEventDisableTiming));
+            if (build_swap_table()) return 1;
+        }
+        overlap_reset = G::SLOW_RESET && auto_reset && !prefetch;
+        if (const char* o = getenv("PG2_OVERLAP_RESET")) overlap_reset = atoi(o) != 0 && auto_reset && !prefetch;
         if (overlap_reset) {
             PG2_CUDA(cudaStreamCreateWithFlags(&reset_stream, cudaStreamNonBlocking));
             PG2_CUDA(cudaEventCreateWithFlags(&ev_stepped, cudaEventDisableTiming));
@@ -332,8 +406,51 @@ struct Engine : EngineBase {
         k_seed<<<(N + 127) / 128, 128, 0, stream>>>(common, N, base_seed, nullptr, 1);
         launches++;
         launch_reset_all();
+        if (init_shadow()) return 1;
         PG2_CUDA(cudaGetLastError());
         PG2_CUDA(cudaStreamSynchronize(stream));
+        return 0;
+    }
+
+    // Fields k_swap copies from the shadow state: every field of the game state and mt / mti / sprites_valid (+ the camera
+    // where reset() sets it), except the ones the game lists as persisting across reset() (G::reset_keeps()).
+    int build_swap_table() {
+        swap_table.n = 0;
+        const std::string keeps = G::reset_keeps();
+        bool overflow = false;
+        auto add = [&](const char* name, void* live_ptr, void* shadow_ptr, int esz, int per_env) {
+            if (keeps.find(std::string(" ") + name + " ") != std::string::npos) return;
+            if (swap_table.n >= MAX_SWAP_FIELDS) { overflow = true; return; }
+            const bool env_major = !strcmp(name, "tiles") || !strcmp(name, "mt");
+            swap_table.f[swap_table.n++] = SwapField{ (char*)live_ptr, (const char*)shadow_ptr, esz, per_env, env_major ? 1 : 0 };
+        };
+        std::vector<void*> shadow_ptrs;
+        shadow_st.for_each_field([&](const char*, void* p, int, int) { shadow_ptrs.push_back(p); });
+        size_t i = 0;
+        st.for_each_field([&](const char* name, void* p, int esz, int pe) { add(name, p, shadow_ptrs[i++], esz, pe); });
+        std::vector<void*> shadow_cptrs;
+        shadow_common.for_each_field([&](const char*, void* p, int, int) { shadow_cptrs.push_back(p); });
+        i = 0;
+        common.for_each_field([&](const char* name, void* p, int esz, int pe) {
+            void* sp = shadow_cptrs[i++];
+            if (!strcmp(name, "mt") || !strcmp(name, "mti") || !strcmp(name, "sprites_valid") || !strcmp(name, "cam_x") || !strcmp(name, "cam_y"))
+                add(name, p, sp, esz, pe);
+        });
+        if (overflow) return fail("level prefetch: too many state fields for the swap table");
+        return 0;
+    }
+
+    // Shadow := live, then reset() on the shadow: every env's next level, generated ahead of time. Synchronous (cold path:
+    // cenv_make, cenv_reset, pg2_restore, pg2_write_field).
+    int init_shadow() override {
+        if (!prefetch) return 0;
+        PG2_CUDA(cudaStreamSynchronize(prep_stream));
+        PG2_CUDA(cudaMemcpyAsync(shadow_state_mem, state_mem, G::State::bytes(N), cudaMemcpyDeviceToDevice, stream));
+        PG2_CUDA(cudaMemcpyAsync(shadow_common_mem, common_mem, CommonState::bytes(N), cudaMemcpyDeviceToDevice, stream));
+        k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(shadow_st, shadow_common, nullptr, nullptr, N);
+        launches++;
+        PG2_CUDA(cudaEventRecord(ev_prepared, stream));
+        PG2_CUDA(cudaGetLastError());
         return 0;
     }
 
@@ -368,6 +485,7 @@ struct Engine : EngineBase {
             launches++;
         }
         launch_reset_all();
+        if (init_shadow()) return 1;
         PG2_CUDA(cudaMemsetAsync(reset_count + 2, 0, 2 * sizeof(int), stream));
         launch_render(0, reset_count + 2, stream);
         PG2_CUDA(cudaMemsetAsync(reward, 0, sizeof(float) * N, stream));
@@ -389,7 +507,24 @@ struct Engine : EngineBase {
                                                      reset_count, parity, N, max_episode_steps, auto_reset, step_epw);
         launches++;
         if (prof) prof_mark();
-        if (overlap_reset) {
+        if (prefetch) {
+            // finished envs take the level that was generated ahead of time (k_swap: a field-wise copy), every env is
+            // rendered, and the level after that is generated on the second stream while the following steps run; the
+            // next swap waits for it (one generator launch in flight)
+            PG2_CUDA(cudaStreamWaitEvent(stream, ev_prepared, 0));
+            int* pl = prep_list + (size_t)parity * N;
+            k_swap<<<num_sms * 8, 128, 0, stream>>>(swap_table, common, shadow_common, reset_list, reset_count + parity, pl, prep_count + parity, N);
+            launches++;
+            PG2_CUDA(cudaEventRecord(ev_swapped, stream));
+            if (prof) prof_mark();
+            // generator first (high-priority stream), then the render: both become runnable when k_swap ends
+            PG2_CUDA(cudaStreamWaitEvent(prep_stream, ev_swapped, 0));
+            k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), prep_stream>>>(shadow_st, shadow_common, pl, prep_count + parity, N);
+            launches++;
+            PG2_CUDA(cudaEventRecord(ev_prepared, prep_stream));
+            launch_render(0, reset_count + 2, stream);
+            if (prof) prof_mark();
+        } else if (overlap_reset) {
             // k_reset stays on the main stream (first in line after k_step, so its few long-running CTAs get their
             // shared memory before the render fills the SMs); the render of all OTHER envs runs on the second stream
             PG2_CUDA(cudaEventRecord(ev_stepped, stream));
@@ -607,6 +742,7 @@ int64_t pg2_write_field(pg2_engine* e, const char* name, const void* in, int64_t
     cudaStreamSynchronize(b->stream);
     if (cudaMemcpy(ptr, in, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { g_error = "pg2_write_field: copy failed"; return -3; }
     cudaMemset(b->common.view_valid, 0, (size_t)b->N);   // a tile map or camera may have changed: drop the cached views
+    if (b->init_shadow()) return -3;                      // ... and the levels generated ahead of time (RNG state may have changed)
     return bytes;
 }
 
@@ -661,6 +797,7 @@ int64_t pg2_restore(pg2_engine* e, const void* blob, int64_t bytes) {
     ok = ok && cudaMemset(b->common.view_valid, 0, (size_t)b->N) == cudaSuccess;   // the view caches are not part of the blob
     b->parity = h.parity;
     if (!ok) { g_error = "pg2_restore: copy failed"; return -3; }
+    if (b->init_shadow()) return -3;   // the levels generated ahead of time are not part of the blob: regenerate them
     return total;
 }
 

@@ -51,6 +51,8 @@ struct BossFight {
     static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int RESET_ARENA = 2 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
+    static constexpr bool PREFETCH_LEVELS = false;   // step() draws from the RNG: the next level is not known ahead of time
+    static const char* reset_keeps() { return ""; }
     static constexpr int TILE_CLASSES = 1;
     static constexpr bool HAS_TILES = false;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = true;    // fixed camera, no tile layer: the background image is cached per env

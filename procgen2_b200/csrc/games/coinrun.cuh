@@ -60,6 +60,8 @@ struct CoinRun {
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int RESET_ARENA = 8 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
+    static constexpr bool PREFETCH_LEVELS = false;   // possible (the RNG is only drawn inside reset()) but the generator is short: measured -3 % / +-1 %
+    static const char* reset_keeps() { return " cam_x cam_y "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 1;
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = false;   // the camera follows the agent: the base image changes every frame (a camera-keyed cache measured slower)

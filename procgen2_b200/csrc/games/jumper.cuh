@@ -45,6 +45,8 @@ struct Jumper {
     static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int RESET_ARENA = 52 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
+    static constexpr bool PREFETCH_LEVELS = true;    // the RNG is only drawn inside reset(): the next level is generated one episode ahead
+    static const char* reset_keeps() { return " cam_x cam_y to_goal_x to_goal_y "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 2;
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = false;   // the camera follows the agent: the base image changes every frame (a camera-keyed cache measured slower)

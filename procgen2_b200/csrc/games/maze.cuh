@@ -36,6 +36,8 @@ struct Maze {
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int RESET_ARENA = 10 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
+    static constexpr bool PREFETCH_LEVELS = true;    // the RNG is only drawn inside reset(): the next level is generated one episode ahead
+    static const char* reset_keeps() { return "  "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 1;
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = true;    // fixed camera and tile map within an episode: the base image (background + tiles) is cached per env

@@ -26,6 +26,8 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
         return true;                                                              \
     }
 
+#define PG2_FIELD_VISIT(type, name, per_env) fn(#name, (void*)this->name, (int)sizeof(type), (int)(per_env));
+
 #define PG2_DEFINE_STATE(NAME, FIELDS)                                   \
     struct NAME {                                                        \
         int N;                                                           \
@@ -47,6 +49,9 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
         bool find(const char* q, void** ptr, int* esz, int* pe) const {  \
             FIELDS(PG2_FIELD_FIND)                                       \
             return false;                                                \
+        }                                                                \
+        template <class Fn> void for_each_field(Fn fn) const {           \
+            FIELDS(PG2_FIELD_VISIT)                                      \
         }                                                                \
     };
 
