@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(128) k_step(typename G::State s, CommonState c
 template <class G>
 __global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::State s, CommonState c,
                                                                     const int* __restrict__ reset_list,
-                                                                    const int* __restrict__ reset_count, int N) {
+                                                                    const int* __restrict__ reset_count, int N,
+                                                                    int* __restrict__ gen_done = nullptr) {
     extern __shared__ __align__(16) char smem[];
     const int warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* mt = (uint32_t*)smem + warp_in_cta * MT_N;
@@ -102,6 +103,11 @@ __global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::
     for (int w = blockIdx.x * RESET_WARPS_PER_CTA + warp_in_cta; w < count; w += total_warps) {
         int env = reset_list ? reset_list[w] : w;
         reset_body<G>(s, c, env, mt, arena, lane);
+        if (gen_done != nullptr) {   // level prefetch: publish "the next level of env exists" (k_swap_wait polls it)
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(&gen_done[env], 1);
+        }
     }
 }
 
@@ -113,8 +119,25 @@ struct SwapField { char* live; const char* shadow; int esz, per_env, env_major; 
 constexpr int MAX_SWAP_FIELDS = 64;
 struct SwapTable { SwapField f[MAX_SWAP_FIELDS]; int n; };
 
+// One thread per finished env: wait until the generator has delivered the level this env is about to take (gen_done counts
+// delivered levels beyond the first, used counts levels taken: ready <=> gen_done >= used). Almost always true on arrival —
+// the generator had a whole episode; the poll is bounded so that a logic error can never hang the GPU (fault bit 4 instead).
+__global__ void k_swap_wait(const int* __restrict__ list, const int* __restrict__ count, const int* gen_done, const int* __restrict__ used,
+                            CommonState live_c) {
+    const int n = *count;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int env = list[k], need = used[env];
+        const volatile int* g = gen_done + env;
+        int spins = 0;
+        while (*g < need && spins < (1 << 22)) { __nanosleep(200); spins++; }
+        if (*g < need) live_c.fault[env] |= 4;
+        __threadfence();
+    }
+}
+
 __global__ void __launch_bounds__(128) k_swap(SwapTable t, CommonState live_c, CommonState shadow_c, const int* __restrict__ list,
-                                              const int* __restrict__ count, int* __restrict__ prep_list, int* __restrict__ prep_count, int N) {
+                                              const int* __restrict__ count, int* __restrict__ prep_list, int* __restrict__ prep_count, int N,
+                                              int* __restrict__ used) {
     const int n = *count, lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) *prep_count = n;
@@ -138,6 +161,7 @@ __global__ void __launch_bounds__(128) k_swap(SwapTable t, CommonState live_c, C
         }
         if (i == 0 && lane == 0) {   // once per env: the list entry for the generator + what reset_body does besides the level
             prep_list[k] = env;
+            used[env] += 1;                                   // read by the next step's k_swap_wait only
             live_c.ep_steps[env] = 0; live_c.view_valid[env] = 0;
             live_c.fault[env] |= shadow_c.fault[env];
         }
@@ -242,10 +266,14 @@ struct EngineBase {
     void* shadow_state_mem = nullptr;
     void* shadow_common_mem = nullptr;
     CommonState shadow_common;
-    int* prep_list = nullptr;        // [2][N]: private copy of a step's reset list for the asynchronous generator
-    int* prep_count = nullptr;       // [2]
-    cudaStream_t prep_stream = nullptr;
-    cudaEvent_t ev_swapped = nullptr, ev_prepared = nullptr;
+    static constexpr int PREP_SLOTS = 4;   // generator launches that may be in flight (each with a private reset list)
+    int* prep_list = nullptr;        // [PREP_SLOTS][N]: private copy of a step's reset list for the asynchronous generator
+    int* prep_count = nullptr;       // [PREP_SLOTS]
+    int* gen_done = nullptr;         // [N] levels delivered by the generator (beyond the first)
+    int* gen_used = nullptr;         // [N] levels taken by k_swap
+    int prep_slot = 0;
+    cudaStream_t prep_streams[4] = { nullptr, nullptr, nullptr, nullptr };   // one per slot: the launches overlap
+    cudaEvent_t ev_swapped = nullptr, ev_prepared[PREP_SLOTS] = { nullptr, nullptr, nullptr, nullptr };
     SwapTable swap_table;
     uint8_t* view_cache = nullptr;   // G::STATIC_VIEW: VIEW_CACHE_BYTES per env (k_render keeps the view of an episode)
     // optional per-kernel timing
@@ -295,10 +323,10 @@ struct EngineBase {
         if (pipelined) { cudaStreamSynchronize(copy_stream); obs = obs_b[0]; reward = reward_b[0]; terminated = term_b[0]; truncated = trunc_b[0]; }
         cudaFree(state_mem); cudaFree(common_mem); cudaFree(obs); cudaFree(reward); cudaFree(terminated);
         cudaFree(truncated); cudaFree(actions); cudaFree(seeds_dev); cudaFree(reset_list); cudaFree(reset_count); cudaFree(view_cache);
-        if (prep_stream) { cudaStreamSynchronize(prep_stream); cudaStreamDestroy(prep_stream); }
+        for (int j = 0; j < PREP_SLOTS; j++) if (prep_streams[j]) { cudaStreamSynchronize(prep_streams[j]); cudaStreamDestroy(prep_streams[j]); }
         if (ev_swapped) cudaEventDestroy(ev_swapped);
-        if (ev_prepared) cudaEventDestroy(ev_prepared);
-        cudaFree(shadow_state_mem); cudaFree(shadow_common_mem); cudaFree(prep_list); cudaFree(prep_count);
+        for (int j = 0; j < PREP_SLOTS; j++) if (ev_prepared[j]) cudaEventDestroy(ev_prepared[j]);
+        cudaFree(shadow_state_mem); cudaFree(shadow_common_mem); cudaFree(prep_list); cudaFree(prep_count); cudaFree(gen_done); cudaFree(gen_used);
         cudaFree(texinfo); cudaFree(atlas); cudaFree(sort_table); cudaFree(pending);
         if (reset_stream) { cudaStreamSynchronize(reset_stream); cudaStreamDestroy(reset_stream); cudaEventDestroy(ev_stepped); cudaEventDestroy(ev_reset_done); }
         if (actions_pinned) cudaFreeHost(actions_pinned);
@@ -361,16 +389,18 @@ struct Engine : EngineBase {
             PG2_CUDA(cudaMalloc(&shadow_common_mem, CommonState::bytes(N)));
             shadow_st = G::State::bind(shadow_state_mem, N);
             shadow_common = CommonState::bind(shadow_common_mem, N);
-            PG2_CUDA(cudaMalloc(&prep_list, sizeof(int) * 2 * (size_t)N));
-            PG2_CUDA(cudaMalloc(&prep_count, 2 * sizeof(int)));
-            PG2_CUDA(cudaMemsetAsync(prep_count, 0, 2 * sizeof(int), stream));
+            PG2_CUDA(cudaMalloc(&prep_list, sizeof(int) * PREP_SLOTS * (size_t)N));
+            PG2_CUDA(cudaMalloc(&prep_count, PREP_SLOTS * sizeof(int)));
+            PG2_CUDA(cudaMemsetAsync(prep_count, 0, PREP_SLOTS * sizeof(int), stream));
+            PG2_CUDA(cudaMalloc(&gen_done, sizeof(int) * (size_t)N));
+            PG2_CUDA(cudaMalloc(&gen_used, sizeof(int) * (size_t)N));
             {   // the generator's few long-running CTAs must get onto the SMs before the render fills them: highest priority
                 int lo = 0, hi = 0;
                 PG2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-                PG2_CUDA(cudaStreamCreateWithPriority(&prep_stream, cudaStreamNonBlocking, hi));
+                for (int j = 0; j < PREP_SLOTS; j++) PG2_CUDA(cudaStreamCreateWithPriority(&prep_streams[j], cudaStreamNonBlocking, hi));
             }
             PG2_CUDA(cudaEventCreateWithFlags(&ev_swapped, cudaEventDisableTiming));
-            PG2_CUDA(cudaEventCreateWithFlags(&ev_prepared, cudaEventDisableTiming));
+            for (int j = 0; j < PREP_SLOTS; j++) PG2_CUDA(cudaEventCreateWithFlags(&ev_prepared[j], cudaEventDisableTiming));
             if (build_swap_table()) return 1;
         }
         overlap_reset = G::SLOW_RESET && auto_reset && !prefetch;
@@ -444,12 +474,14 @@ struct Engine : EngineBase {
     // cenv_make, cenv_reset, pg2_restore, pg2_write_field).
     int init_shadow() override {
         if (!prefetch) return 0;
-        PG2_CUDA(cudaStreamSynchronize(prep_stream));
+        for (int j = 0; j < PREP_SLOTS; j++) PG2_CUDA(cudaStreamSynchronize(prep_streams[j]));
         PG2_CUDA(cudaMemcpyAsync(shadow_state_mem, state_mem, G::State::bytes(N), cudaMemcpyDeviceToDevice, stream));
         PG2_CUDA(cudaMemcpyAsync(shadow_common_mem, common_mem, CommonState::bytes(N), cudaMemcpyDeviceToDevice, stream));
         k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(shadow_st, shadow_common, nullptr, nullptr, N);
         launches++;
-        PG2_CUDA(cudaEventRecord(ev_prepared, stream));
+        PG2_CUDA(cudaMemsetAsync(gen_done, 0, sizeof(int) * (size_t)N, stream));   // ready <=> gen_done >= used
+        PG2_CUDA(cudaMemsetAsync(gen_used, 0, sizeof(int) * (size_t)N, stream));
+        for (int j = 0; j < PREP_SLOTS; j++) PG2_CUDA(cudaEventRecord(ev_prepared[j], stream));
         PG2_CUDA(cudaGetLastError());
         return 0;
     }
@@ -509,19 +541,24 @@ struct Engine : EngineBase {
         if (prof) prof_mark();
         if (prefetch) {
             // finished envs take the level that was generated ahead of time (k_swap: a field-wise copy), every env is
-            // rendered, and the level after that is generated on the second stream while the following steps run; the
-            // next swap waits for it (one generator launch in flight)
-            PG2_CUDA(cudaStreamWaitEvent(stream, ev_prepared, 0));
-            int* pl = prep_list + (size_t)parity * N;
-            k_swap<<<num_sms * 8, 128, 0, stream>>>(swap_table, common, shadow_common, reset_list, reset_count + parity, pl, prep_count + parity, N);
-            launches++;
+            // rendered, and the level after that is generated on the second stream while the following steps run: up to
+            // PREP_SLOTS generator launches are in flight, each with a private copy of its step's reset list; an env that
+            // finishes again before its next level exists (episodes shorter than a generation) is waited for individually
+            const int slot = prep_slot;
+            prep_slot = (prep_slot + 1) % PREP_SLOTS;
+            PG2_CUDA(cudaStreamWaitEvent(stream, ev_prepared[slot], 0));   // the launch that last used this slot's list is done
+            int* pl = prep_list + (size_t)slot * N;
+            int* pc = prep_count + slot;
+            k_swap_wait<<<num_sms, 128, 0, stream>>>(reset_list, reset_count + parity, gen_done, gen_used, common);
+            k_swap<<<num_sms * 8, 128, 0, stream>>>(swap_table, common, shadow_common, reset_list, reset_count + parity, pl, pc, N, gen_used);
+            launches += 2;
             PG2_CUDA(cudaEventRecord(ev_swapped, stream));
             if (prof) prof_mark();
             // generator first (high-priority stream), then the render: both become runnable when k_swap ends
-            PG2_CUDA(cudaStreamWaitEvent(prep_stream, ev_swapped, 0));
-            k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), prep_stream>>>(shadow_st, shadow_common, pl, prep_count + parity, N);
+            PG2_CUDA(cudaStreamWaitEvent(prep_streams[slot], ev_swapped, 0));
+            k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), prep_streams[slot]>>>(shadow_st, shadow_common, pl, pc, N, gen_done);
             launches++;
-            PG2_CUDA(cudaEventRecord(ev_prepared, prep_stream));
+            PG2_CUDA(cudaEventRecord(ev_prepared[slot], prep_streams[slot]));
             launch_render(0, reset_count + 2, stream);
             if (prof) prof_mark();
         } else if (overlap_reset) {
