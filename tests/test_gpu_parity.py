@@ -271,3 +271,30 @@ def test_cenv_dropin_num_devices_is_invisible():
         np.testing.assert_array_equal(info["terminated"], ra[t + 1][2])
         np.testing.assert_array_equal(info["truncated"], ra[t + 1][3])
     b.close()
+
+
+@pytest.mark.parametrize("game,max_ep", [("maze", 1), ("jumper", 2), ("caveflyer", 3), ("maze", 7)])
+def test_level_prefetch_equals_inline_reset(game, max_ep, monkeypatch):
+    """Level prefetch (next level generated one episode ahead into the shadow state, swapped in by k_swap) against the
+    inline reset path (PG2_PREFETCH=0) on very short episodes: every env finishes every 1-3 steps, so envs finish again
+    before their next level exists (k_swap_wait) and all four generator slots are in flight."""
+    from procgen2_b200.engine import BatchedEnv
+    n, T = 96, 40
+    rs = np.random.RandomState(17)
+    acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
+    monkeypatch.setenv("PG2_PREFETCH", "0")
+    a = BatchedEnv(game, n, seed=5, max_episode_steps=max_ep)
+    monkeypatch.setenv("PG2_PREFETCH", "1")
+    b = BatchedEnv(game, n, seed=5, max_episode_steps=max_ep)
+    a.reset(); b.reset()
+    np.testing.assert_array_equal(a.fetch()[0], b.fetch()[0])
+    for t in range(T):
+        a.step(acts[t]); b.step(acts[t])
+        oa, ra, da, ta = a.fetch(truncated=True)
+        ob, rb, db, tb = b.fetch(truncated=True)
+        np.testing.assert_array_equal(oa, ob); np.testing.assert_array_equal(ra, rb)
+        np.testing.assert_array_equal(da, db); np.testing.assert_array_equal(ta, tb)
+    b.sync()
+    for name in ("mt", "mti", "tiles", "fault"):
+        np.testing.assert_array_equal(a.read_field(name)[0], b.read_field(name)[0])
+    a.close(); b.close()
