@@ -82,6 +82,7 @@ PG2_API uint8_t* pg2_truncated_device(pg2_engine* e);
 PG2_API int32_t pg2_sync(pg2_engine* e);
 PG2_API void* pg2_stream(pg2_engine* e);            /* cudaStream_t the engine launches on */
 PG2_API int32_t pg2_num_envs(pg2_engine* e);
+PG2_API int32_t pg2_step_epw(pg2_engine* e);        /* environments per warp in the step kernel (1 = a whole warp per env) */
 PG2_API int64_t pg2_kernel_launches(pg2_engine* e); /* kernels launched so far (bench.py gpu_launches) */
 PG2_API int64_t pg2_state_bytes_per_env(pg2_engine* e);
 
@@ -103,6 +104,13 @@ PG2_API int64_t pg2_write_field(pg2_engine* e, const char* name, const void* in,
  * engine of the same game and shard size. Stepping after pg2_restore reproduces the steps after pg2_snapshot bit for bit. */
 PG2_API int64_t pg2_snapshot(pg2_engine* e, void* out, int64_t capacity);
 PG2_API int64_t pg2_restore(pg2_engine* e, const void* blob, int64_t bytes);
+
+/* Host-only helper (no CUDA call, works without a GPU): texture `name` (an "assets/..." path of the reference) exactly as
+ * the engine uploads it into its device atlas — w*h RGBA8 texels (little-endian R,G,B,A; opaque RGB textures carry A = 255),
+ * blend = 1 for alpha textures. Replaces Asset_Texture::load (games/coinrun/common_assets.cpp:3-17) for inspection:
+ * the build-container test compares it with the PNG decoded by PIL. Returns the texel count (out may be NULL), <0 on error. */
+PG2_API int64_t pg2_load_texture_host(const char* assets_path, const char* name, int32_t* w, int32_t* h, int32_t* blend,
+                                      uint32_t* out, int64_t capacity);
 
 PG2_API const char* pg2_last_error(void);
 

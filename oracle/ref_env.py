@@ -88,6 +88,14 @@ class RefEnv:
         self._kv_ref = ctypes.byref(self._kv)
         os.unlink(self.path)  # mapping stays valid
 
+    def close(self):
+        """Unload this environment's private library copy (many-seed sweeps would otherwise keep thousands mapped)."""
+        lib, self.lib = self.lib, None
+        if lib is not None:
+            import _ctypes
+            self.step_data = self.reset_data = None
+            _ctypes.dlclose(lib._handle)
+
     def _obs(self, kv):
         n = kv.value_buffer_size
         return np.ctypeslib.as_array(kv.value_buffer.b, shape=(n,)).reshape(64, 64, 3).copy()

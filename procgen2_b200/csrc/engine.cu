@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,23 @@ static int fail(const std::string& msg) { g_error = msg; return 1; }
             return 1;                                                                           \
         }                                                                                       \
     } while (0)
+
+// Every C ABI entry point runs on the engine's device and leaves the caller's current device untouched (a torch / CUDA
+// host framework keeps allocating and launching where it was).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) ok = cudaSetDevice(device) == cudaSuccess; else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define PG2_ON_DEVICE(dev)                                                   \
+    DeviceGuard guard__(dev);                                                \
+    if (!guard__.ok) return fail("cudaSetDevice failed for the engine's device")
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -129,7 +147,7 @@ __global__ void k_swap_wait(const int* __restrict__ list, const int* __restrict_
         const int env = list[k], need = used[env];
         const volatile int* g = gen_done + env;
         int spins = 0;
-        while (*g < need && spins < (1 << 22)) { __nanosleep(200); spins++; }
+        while (*g < need && spins < (1 << 18)) { __nanosleep(200); spins++; }
         if (*g < need) live_c.fault[env] |= 4;
         __threadfence();
     }
@@ -212,6 +230,26 @@ __global__ void __launch_bounds__(RENDER_THREADS, PG2_RENDER_MIN_CTAS) k_render(
 // ------------------------------------------------------------------------------------------------
 // host engine
 
+// The std::sort permutation table (pg2_render.cuh: g_sort_perm) is a constant of the process: uploaded once per device by
+// the first engine created there, shared by every engine and every lib<Game>.so of the process, never rewritten and never
+// freed (16.5 KB) — so no engine can pull it from under another one's kernels.
+static int ensure_sort_table(int device) {
+    static std::mutex mu;
+    static bool done[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 0 || device >= 64) return fail("device ordinal out of range");
+    if (done[device]) return 0;
+    std::vector<uint8_t> table = build_sort_perm(SORT_MAXN);
+    uint8_t* dev_table = nullptr;
+    PG2_CUDA(cudaMalloc(&dev_table, table.size()));
+    PG2_CUDA(cudaMemcpy(dev_table, table.data(), table.size(), cudaMemcpyHostToDevice));
+    const uint8_t* p = dev_table;
+    PG2_CUDA(cudaMemcpyToSymbol(g_sort_perm, &p, sizeof(p)));
+    PG2_CUDA(cudaDeviceSynchronize());
+    done[device] = true;
+    return 0;
+}
+
 struct EngineBase {
     virtual ~EngineBase() {}
     virtual int reset(const int32_t* seeds) = 0;
@@ -260,7 +298,6 @@ struct EngineBase {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_step[2] = { nullptr, nullptr }, ev_copy[2] = { nullptr, nullptr }, ev_h2d[2] = { nullptr, nullptr };
     bool copy_pending[2] = { false, false };
-    uint8_t* sort_table = nullptr;
     // level prefetch
     bool prefetch = false;
     void* shadow_state_mem = nullptr;
@@ -318,7 +355,7 @@ struct EngineBase {
     }
 
     int free_all() {
-        cudaSetDevice(device);
+        DeviceGuard guard(device);
         if (stream) cudaStreamSynchronize(stream);
         if (pipelined) { cudaStreamSynchronize(copy_stream); obs = obs_b[0]; reward = reward_b[0]; terminated = term_b[0]; truncated = trunc_b[0]; }
         cudaFree(state_mem); cudaFree(common_mem); cudaFree(obs); cudaFree(reward); cudaFree(terminated);
@@ -327,7 +364,7 @@ struct EngineBase {
         if (ev_swapped) cudaEventDestroy(ev_swapped);
         for (int j = 0; j < PREP_SLOTS; j++) if (ev_prepared[j]) cudaEventDestroy(ev_prepared[j]);
         cudaFree(shadow_state_mem); cudaFree(shadow_common_mem); cudaFree(prep_list); cudaFree(prep_count); cudaFree(gen_done); cudaFree(gen_used);
-        cudaFree(texinfo); cudaFree(atlas); cudaFree(sort_table); cudaFree(pending);
+        cudaFree(texinfo); cudaFree(atlas); cudaFree(pending);
         if (reset_stream) { cudaStreamSynchronize(reset_stream); cudaStreamDestroy(reset_stream); cudaEventDestroy(ev_stepped); cudaEventDestroy(ev_reset_done); }
         if (actions_pinned) cudaFreeHost(actions_pinned);
         if (pipelined) {
@@ -422,14 +459,7 @@ struct Engine : EngineBase {
         PG2_CUDA(cudaMalloc(&atlas, sizeof(uint32_t) * texels.size()));
         PG2_CUDA(cudaMemcpyAsync(texinfo, infos.data(), sizeof(TexInfo) * ntex, cudaMemcpyHostToDevice, stream));
         PG2_CUDA(cudaMemcpyAsync(atlas, texels.data(), sizeof(uint32_t) * texels.size(), cudaMemcpyHostToDevice, stream));
-        {
-            std::vector<uint8_t> table = build_sort_perm(SORT_MAXN);
-            PG2_CUDA(cudaMalloc(&sort_table, table.size()));
-            PG2_CUDA(cudaMemcpyAsync(sort_table, table.data(), table.size(), cudaMemcpyHostToDevice, stream));
-            PG2_CUDA(cudaStreamSynchronize(stream));
-            const uint8_t* p = sort_table;
-            PG2_CUDA(cudaMemcpyToSymbol(g_sort_perm, &p, sizeof(p)));
-        }
+        if (ensure_sort_table(device)) return 1;
         PG2_CUDA(cudaStreamSynchronize(stream));
         PG2_CUDA(cudaFuncSetAttribute(k_reset<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, reset_smem()));
         // cenv_make: seed, then reset() once (level #1 is generated and never rendered, Q29)
@@ -509,8 +539,9 @@ struct Engine : EngineBase {
     }
 
     int reset(const int32_t* seeds) override {
-        PG2_CUDA(cudaSetDevice(device));
         if (seeds) {
+            // the pinned staging buffer is shared with pg2_step's action copy, which may still be in flight
+            PG2_CUDA(cudaStreamSynchronize(stream));
             memcpy(actions_pinned, seeds, sizeof(int32_t) * N);
             PG2_CUDA(cudaMemcpyAsync(seeds_dev, actions_pinned, sizeof(int32_t) * N, cudaMemcpyHostToDevice, stream));
             k_seed<<<(N + 127) / 128, 128, 0, stream>>>(common, N, 0u, seeds_dev, 0);
@@ -619,6 +650,7 @@ int32_t pg2_create(const pg2_config* cfg, pg2_engine** out) {
     for (auto& ch : g) ch = (char)tolower(ch);
     std::unique_ptr<EngineBase> impl;
     int rc = 1;
+    PG2_ON_DEVICE(cfg->device);
 #define PG2_TRY_GAME(NAME, TYPE) \
     if (!impl && g == NAME) { auto* e = new Engine<TYPE>(); impl.reset(e); rc = e->init(cfg); }
     PG2_FOR_EACH_GAME(PG2_TRY_GAME)
@@ -635,11 +667,14 @@ void pg2_destroy(pg2_engine* e) {
     delete e;
 }
 
-int32_t pg2_reset(pg2_engine* e, const int32_t* seeds) { return e->impl->reset(seeds); }
+int32_t pg2_reset(pg2_engine* e, const int32_t* seeds) {
+    PG2_ON_DEVICE(e->impl->device);
+    return e->impl->reset(seeds);
+}
 
 int32_t pg2_step(pg2_engine* e, const int32_t* actions_host) {
     EngineBase* b = e->impl.get();
-    PG2_CUDA(cudaSetDevice(b->device));
+    PG2_ON_DEVICE(b->device);
     // the pinned staging buffer is reused every step: wait for the previous copy to have left it
     PG2_CUDA(cudaStreamSynchronize(b->stream));
     memcpy(b->actions_pinned, actions_host, sizeof(int32_t) * b->N);
@@ -648,13 +683,13 @@ int32_t pg2_step(pg2_engine* e, const int32_t* actions_host) {
 }
 
 int32_t pg2_step_device(pg2_engine* e, const int32_t* actions_device) {
-    PG2_CUDA(cudaSetDevice(e->impl->device));
+    PG2_ON_DEVICE(e->impl->device);
     return e->impl->step_device(actions_device);
 }
 
 int32_t pg2_fetch(pg2_engine* e, uint8_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated) {
     EngineBase* b = e->impl.get();
-    PG2_CUDA(cudaSetDevice(b->device));
+    PG2_ON_DEVICE(b->device);
     if (obs) PG2_CUDA(cudaMemcpyAsync(obs, b->obs, (size_t)b->N * OBS_BYTES, cudaMemcpyDeviceToHost, b->stream));
     if (reward) PG2_CUDA(cudaMemcpyAsync(reward, b->reward, sizeof(float) * b->N, cudaMemcpyDeviceToHost, b->stream));
     if (terminated) PG2_CUDA(cudaMemcpyAsync(terminated, b->terminated, b->N, cudaMemcpyDeviceToHost, b->stream));
@@ -689,7 +724,7 @@ static int enable_pipeline(EngineBase* b) {
 
 int32_t pg2_step_pipelined(pg2_engine* e, const int32_t* actions_host, uint8_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated) {
     EngineBase* b = e->impl.get();
-    PG2_CUDA(cudaSetDevice(b->device));
+    PG2_ON_DEVICE(b->device);
     if (!b->pipelined && enable_pipeline(b)) return 1;
     const int prev = b->cur, slot = b->cur ^ 1, N = b->N;
     // this slot's HBM outputs were last read by the copy issued two calls ago, its staging buffer by that call's H2D
@@ -716,7 +751,7 @@ int32_t pg2_step_pipelined(pg2_engine* e, const int32_t* actions_host, uint8_t* 
 // Wait for the results of the last pg2_step_pipelined call.
 int32_t pg2_pipeline_flush(pg2_engine* e) {
     EngineBase* b = e->impl.get();
-    PG2_CUDA(cudaSetDevice(b->device));
+    PG2_ON_DEVICE(b->device);
     if (b->pipelined) PG2_CUDA(cudaStreamSynchronize(b->copy_stream));
     return 0;
 }
@@ -727,18 +762,19 @@ uint8_t* pg2_terminated_device(pg2_engine* e) { return e->impl->terminated; }
 uint8_t* pg2_truncated_device(pg2_engine* e) { return e->impl->truncated; }
 
 int32_t pg2_sync(pg2_engine* e) {
-    PG2_CUDA(cudaSetDevice(e->impl->device));
+    PG2_ON_DEVICE(e->impl->device);
     PG2_CUDA(cudaStreamSynchronize(e->impl->stream));
     return 0;
 }
 void* pg2_stream(pg2_engine* e) { return (void*)e->impl->stream; }
 int32_t pg2_num_envs(pg2_engine* e) { return e->impl->N; }
+int32_t pg2_step_epw(pg2_engine* e) { return e->impl->step_epw; }
 int64_t pg2_kernel_launches(pg2_engine* e) { return e->impl->launches; }
 int64_t pg2_state_bytes_per_env(pg2_engine* e) { return (int64_t)e->impl->state_bytes_per_env(); }
 
 int32_t pg2_profile(pg2_engine* e, int32_t enable) {
     EngineBase* b = e->impl.get();
-    cudaSetDevice(b->device);
+    DeviceGuard guard__(b->device);
     b->prof_collect();
     b->profiling = enable != 0;
     b->prof_steps = 0;
@@ -747,7 +783,7 @@ int32_t pg2_profile(pg2_engine* e, int32_t enable) {
 }
 int32_t pg2_profile_read(pg2_engine* e, float ms_out[3], int64_t* steps) {
     EngineBase* b = e->impl.get();
-    cudaSetDevice(b->device);
+    DeviceGuard guard__(b->device);
     b->prof_collect();
     for (int k = 0; k < 3; k++) ms_out[k] = (float)b->prof_ms[k];
     if (steps) *steps = b->prof_steps;
@@ -763,7 +799,7 @@ int64_t pg2_read_field(pg2_engine* e, const char* name, void* out, int64_t capac
     int64_t bytes = (int64_t)esz * pe * b->N;
     if (!out) return bytes;
     if (capacity < bytes) { g_error = "pg2_read_field: buffer too small"; return -2; }
-    cudaSetDevice(b->device);
+    DeviceGuard guard__(b->device);
     cudaStreamSynchronize(b->stream);
     if (cudaMemcpy(out, ptr, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { g_error = "pg2_read_field: copy failed"; return -3; }
     return bytes;
@@ -775,7 +811,7 @@ int64_t pg2_write_field(pg2_engine* e, const char* name, const void* in, int64_t
     if (!b->find_field(name, &ptr, &esz, &pe)) { g_error = std::string("unknown field ") + name; return -1; }
     int64_t bytes = (int64_t)esz * pe * b->N;
     if (bytes_in != bytes) { g_error = "pg2_write_field: size mismatch"; return -2; }
-    cudaSetDevice(b->device);
+    DeviceGuard guard__(b->device);
     cudaStreamSynchronize(b->stream);
     if (cudaMemcpy(ptr, in, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { g_error = "pg2_write_field: copy failed"; return -3; }
     cudaMemset(b->common.view_valid, 0, (size_t)b->N);   // a tile map or camera may have changed: drop the cached views
@@ -794,8 +830,8 @@ int64_t pg2_snapshot(pg2_engine* e, void* out, int64_t capacity) {
     const int64_t total = (int64_t)(sizeof(SnapshotHeader) + sb + cb + n * OBS_BYTES + n * sizeof(float) + 2 * n);
     if (!out) return total;
     if (capacity < total) { g_error = "pg2_snapshot: buffer too small"; return -2; }
-    if (b->pipelined) { g_error = "pg2_snapshot: flush the pipelined stepping first (pg2_pipeline_flush) and use pg2_step"; }
-    cudaSetDevice(b->device);
+    if (b->pipelined) { g_error = "pg2_snapshot: flush the pipelined stepping first (pg2_pipeline_flush) and use pg2_step"; return -2; }
+    DeviceGuard guard__(b->device);
     if (cudaStreamSynchronize(b->stream) != cudaSuccess) { g_error = "pg2_snapshot: sync failed"; return -3; }
     SnapshotHeader h{ SNAPSHOT_MAGIC, b->game_tag(), b->N, b->parity, (uint64_t)sb, (uint64_t)cb };
     char* p = (char*)out;
@@ -820,7 +856,7 @@ int64_t pg2_restore(pg2_engine* e, const void* blob, int64_t bytes) {
     if (h.magic != SNAPSHOT_MAGIC || h.game != b->game_tag() || h.n != b->N || h.state_bytes != sb || h.common_bytes != cb || bytes != total) {
         g_error = "pg2_restore: blob does not belong to this game / shard size"; return -2;
     }
-    cudaSetDevice(b->device);
+    DeviceGuard guard__(b->device);
     if (cudaStreamSynchronize(b->stream) != cudaSuccess) { g_error = "pg2_restore: sync failed"; return -3; }
     const char* p = (const char*)blob + sizeof(h);
     bool ok = cudaMemcpy(b->state_mem, p, sb, cudaMemcpyHostToDevice) == cudaSuccess; p += sb;
@@ -836,6 +872,25 @@ int64_t pg2_restore(pg2_engine* e, const void* blob, int64_t bytes) {
     if (!ok) { g_error = "pg2_restore: copy failed"; return -3; }
     if (b->init_shadow()) return -3;   // the levels generated ahead of time are not part of the blob: regenerate them
     return total;
+}
+
+// Host-only (no CUDA call): texture `name` as the engine uploads it into the device atlas — RGBA8 texels, RGB textures with
+// A = 255 — decoded from the packed blob by the product's own loader (assets.cpp). The build-container test compares it
+// with the reference's PNG (tests/test_assets_blob.py). Returns the texel count, <0 on error; out may be NULL to query.
+int64_t pg2_load_texture_host(const char* assets_path, const char* name, int32_t* w, int32_t* h, int32_t* blend, uint32_t* out, int64_t capacity) {
+    std::vector<TexInfo> infos;
+    std::vector<uint32_t> texels;
+    std::string err;
+    const char* names[1] = { name };
+    if (!name || !load_textures(assets_path, names, 1, &infos, &texels, &err)) { g_error = err.empty() ? "pg2_load_texture_host: null name" : err; return -1; }
+    if (w) *w = infos[0].w;
+    if (h) *h = infos[0].h;
+    if (blend) *blend = (int32_t)infos[0].blend;
+    if (out) {
+        if (capacity < (int64_t)texels.size()) { g_error = "pg2_load_texture_host: buffer too small"; return -2; }
+        memcpy(out, texels.data(), texels.size() * sizeof(uint32_t));
+    }
+    return (int64_t)texels.size();
 }
 
 }  // extern "C"

@@ -53,6 +53,7 @@ def load_library():
         getattr(L, name).restype = vp
     L.pg2_sync.argtypes = [vp]
     L.pg2_num_envs.argtypes = [vp]
+    L.pg2_step_epw.argtypes = [vp]
     L.pg2_kernel_launches.argtypes = [vp]
     L.pg2_kernel_launches.restype = ctypes.c_int64
     L.pg2_state_bytes_per_env.argtypes = [vp]
@@ -177,6 +178,11 @@ class BatchedEnv:
     @property
     def stream_ptr(self):
         return self._L.pg2_stream(self._h)
+
+    @property
+    def step_epw(self):
+        """Environments per warp in the step kernel (1: a whole warp per environment)."""
+        return int(self._L.pg2_step_epw(self._h))
 
     @property
     def kernel_launches(self):

@@ -1,0 +1,226 @@
+"""GPU parity tests of the paths the first-round suite never drove against the oracle (pytest -m gpu on a B200, all
+against the LIVE reference oracle/_ref, bit-exact):
+
+  (a) the packed-warp k_step mapping (PG2_STEP_EPW = 2 / 4 / 32 environments per warp), which the engine selects by
+      itself from 16 384 envs on for the thread-per-env games — incl. the real BASELINE configs[2] shape, bossfight at
+      16 384 envs, checked on sampled envs;
+  (b) max_episode_steps truncation (BASELINE configs[4]: short episodes), dozens of episodes per env: the oracle is
+      driven as "step; every k steps: reset()" — hammers the persisted ECS bucket counts (Q25), the camera surviving
+      reset (Q10) and level generation on a continuing MT19937 stream;
+  (c) maze's 500-step timeout (maze.cpp:308-310), how BASELINE configs[0] episodes end;
+  (d) GPU level generation over >= 512 seeds x 4 consecutive resets: full tile map + all 624 MT19937 words + position.
+"""
+import numpy as np
+import pytest
+
+from tests.conftest import IMPLEMENTED
+
+pytestmark = pytest.mark.gpu
+
+THREAD_PER_ENV_GAMES = ["maze", "bossfight", "caveflyer", "jumper"]   # G::LANE_AWARE == false: step_epw > 1 exists
+
+
+def _need_oracle(oracle_available):
+    if not oracle_available:
+        pytest.skip("oracle/_ref did not travel")
+    from oracle import ref_env
+    return ref_env
+
+
+def _mixed_actions(rs, T, n):
+    return np.where(rs.rand(T, n) < 0.5, rs.randint(0, 15, size=(T, n)), rs.choice([6, 7, 8, 8, 5], size=(T, n))).astype(np.int32)
+
+
+def _assert_no_fault(env):
+    f = env.read_field("fault")[0].view(np.int32)
+    assert not f.any(), "latent-UB / overflow flags set for envs %s" % np.nonzero(f)[0][:8]
+
+
+def _check_state(env, refs, idx=None, tag=""):
+    """Full MT19937 state + position + tile map of the engine's envs `idx` against the reference processes."""
+    n = env.num_envs
+    mt = env.read_field("mt")[0].view(np.uint32).reshape(n, 624)
+    mti = env.read_field("mti")[0].view(np.int32)
+    try:
+        tb, _, pe = env.read_field("tiles")
+        tiles = tb.reshape(n, pe)
+    except KeyError:
+        tiles = None
+    for k, r in enumerate(refs):
+        i = k if idx is None else int(idx[k])
+        st, pos = r.rng_state()
+        assert pos == mti[i], "%s MT19937 position, env %d" % (tag, i)
+        np.testing.assert_array_equal(st, mt[i], err_msg="%s MT19937 words, env %d" % (tag, i))
+        rt = r.tiles()
+        if tiles is not None and rt.size:
+            w, h = rt.shape
+            np.testing.assert_array_equal((tiles[i, :w * h] & 15).reshape(w, h), rt, err_msg="%s tile map, env %d" % (tag, i))
+
+
+# ---- (a) packed-warp step mapping ---------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("epw", [2, 4, 32])
+@pytest.mark.parametrize("game", THREAD_PER_ENV_GAMES)
+def test_step_epw_live_oracle(game, epw, oracle_available, monkeypatch):
+    ref_env = _need_oracle(oracle_available)
+    from procgen2_b200.engine import BatchedEnv
+    from tests.parity_util import check_against_oracle
+    from tests.test_gpu_parity import EngineAdapter
+    n, T, seed = 96, 400, 1300 + epw
+    acts = _mixed_actions(np.random.RandomState(40 + epw), T, n)
+    monkeypatch.setenv("PG2_STEP_EPW", str(epw))
+    a = EngineAdapter(game, n, seed)
+    monkeypatch.delenv("PG2_STEP_EPW")
+    assert a.env.step_epw == epw
+    refs = [ref_env.RefEnv(game, seed + i) for i in range(n)]
+    episodes = check_against_oracle(a, refs, acts, tag="%s epw=%d" % (game, epw))
+    _check_state(a.env, refs, tag=game)
+    _assert_no_fault(a.env)
+    assert episodes > 0 or game in ("maze", "jumper")
+    for r in refs:
+        r.close()
+    a.env.close()
+
+
+def test_bossfight_16384_sampled_oracle(oracle_available):
+    """BASELINE configs[2] as the engine runs it (16 384 envs => 2 environments per warp chosen by the engine itself):
+    64 sampled envs, 50 steps, against reference processes with the same seeds."""
+    ref_env = _need_oracle(oracle_available)
+    from procgen2_b200.engine import BatchedEnv
+    n, T, seed = 16384, 50, 7
+    rs = np.random.RandomState(8)
+    acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
+    env = BatchedEnv("bossfight", n, seed=seed)
+    assert env.step_epw == 2
+    idx = np.sort(rs.choice(n, 64, replace=False))
+    idx[:4] = [0, 1, n - 2, n - 1]
+    idx = np.unique(idx)
+    refs = [ref_env.RefEnv("bossfight", seed + int(i)) for i in idx]
+    env.reset()
+    np.testing.assert_array_equal(env.fetch()[0][idx], np.stack([r.reset() for r in refs]))
+    for t in range(T):
+        env.step(acts[t])
+        o, r, d, _ = env.fetch()
+        ro, rr, rd = [], [], []
+        for k, e in enumerate(refs):
+            oo, w, dd = e.step(acts[t, idx[k]])
+            if dd:
+                oo = e.reset()
+            ro.append(oo); rr.append(w); rd.append(dd)
+        np.testing.assert_array_equal(r[idx], np.array(rr, np.float32), err_msg="reward, step %d" % t)
+        np.testing.assert_array_equal(d[idx], np.array(rd), err_msg="terminated, step %d" % t)
+        np.testing.assert_array_equal(o[idx], np.stack(ro), err_msg="pixels, step %d" % t)
+    _check_state(env, refs, idx, tag="bossfight@16384")
+    _assert_no_fault(env)
+    for r in refs:
+        r.close()
+    env.close()
+
+
+# ---- (b) truncation = BASELINE configs[4] ------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("max_ep", [1, 3, 8, 32])
+@pytest.mark.parametrize("game", IMPLEMENTED)
+def test_truncation_live_oracle(game, max_ep, oracle_available):
+    ref_env = _need_oracle(oracle_available)
+    from procgen2_b200.engine import BatchedEnv
+    n, seed = 32, 2100 + max_ep
+    T = max(24, 21 * max_ep)     # >= 21 episodes per env
+    acts = _mixed_actions(np.random.RandomState(60 + max_ep), T, n)
+    env = BatchedEnv(game, n, seed=seed, max_episode_steps=max_ep)
+    refs = [ref_env.RefEnv(game, seed + i) for i in range(n)]
+    env.reset()
+    np.testing.assert_array_equal(env.fetch()[0], np.stack([r.reset() for r in refs]), err_msg="reset frame")
+    age = np.zeros(n, np.int64)
+    episodes = 0
+    for t in range(T):
+        env.step(acts[t])
+        o, rw, d, tr = env.fetch(truncated=True)
+        ro, rr, rd, rt = [], [], [], []
+        for i, e in enumerate(refs):
+            oo, w, dd = e.step(acts[t, i])
+            age[i] += 1
+            trunc = (not dd) and age[i] >= max_ep
+            if dd or trunc:
+                oo = e.reset()
+                age[i] = 0
+                episodes += 1
+            ro.append(oo); rr.append(w); rd.append(dd); rt.append(trunc)
+        np.testing.assert_array_equal(rw, np.array(rr, np.float32), err_msg="reward, step %d" % t)
+        np.testing.assert_array_equal(d, np.array(rd), err_msg="terminated, step %d" % t)
+        np.testing.assert_array_equal(tr, np.array(rt), err_msg="truncated, step %d" % t)
+        np.testing.assert_array_equal(o, np.stack(ro), err_msg="pixels, step %d" % t)
+        if t % 16 == 15 or t == T - 1:
+            _check_state(env, refs, tag="%s step %d" % (game, t))
+    assert episodes >= 20 * n
+    _assert_no_fault(env)
+    for r in refs:
+        r.close()
+    env.close()
+
+
+# ---- (c) maze timeout -----------------------------------------------------------------------------------------------------
+
+def test_maze_timeout_live_oracle(oracle_available):
+    ref_env = _need_oracle(oracle_available)
+    from tests.parity_util import check_against_oracle
+    from tests.test_gpu_parity import EngineAdapter
+    n, T, seed = 48, 520, 3100
+    rs = np.random.RandomState(70)
+    acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
+    acts[:, : n // 2] = 4          # half of the envs never move: their episodes can only end by the 500-step timeout
+    a = EngineAdapter("maze", n, seed)
+    refs = [ref_env.RefEnv("maze", seed + i) for i in range(n)]
+    episodes = check_against_oracle(a, refs, acts, tag="maze timeout")
+    assert episodes >= n // 2
+    _check_state(a.env, refs, tag="maze timeout")
+    _assert_no_fault(a.env)
+    for r in refs:
+        r.close()
+    a.env.close()
+
+
+# ---- (d) level generation, many seeds ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("game", IMPLEMENTED)
+def test_gpu_level_generation_many_seeds(game, oracle_available):
+    """The warp-parallel generators (ordered BFS with atomicMin claims, unordered_set regrouping, bit-row automaton) exist
+    only in the GPU build: 512 seeds x (make + 4 resets), tile map + complete RNG state + the reset frame every time."""
+    ref_env = _need_oracle(oracle_available)
+    from procgen2_b200.engine import BatchedEnv
+    n, seed, chunk = 512, 52000, 128
+    env = BatchedEnv(game, n, seed=seed)
+    frames = []
+    fields = []
+    for rnd in range(5):
+        mt = env.read_field("mt")[0].view(np.uint32).reshape(n, 624).copy()
+        mti = env.read_field("mti")[0].view(np.int32).copy()
+        try:
+            tb, _, pe = env.read_field("tiles")
+            tiles = tb.reshape(n, pe).copy()
+        except KeyError:
+            tiles = None
+        fields.append((mt, mti, tiles))
+        if rnd < 4:
+            env.reset()
+            frames.append(env.fetch()[0])
+    _assert_no_fault(env)
+    env.close()
+    for c0 in range(0, n, chunk):
+        refs = [ref_env.RefEnv(game, seed + i) for i in range(c0, min(n, c0 + chunk))]
+        for rnd in range(5):
+            mt, mti, tiles = fields[rnd]
+            for k, r in enumerate(refs):
+                i = c0 + k
+                st, pos = r.rng_state()
+                assert pos == mti[i], (game, rnd, i)
+                np.testing.assert_array_equal(st, mt[i], err_msg="%s MT19937 words, level %d, seed %d" % (game, rnd, seed + i))
+                rt = r.tiles()
+                if tiles is not None and rt.size:
+                    w, h = rt.shape
+                    np.testing.assert_array_equal((tiles[i, :w * h] & 15).reshape(w, h), rt, err_msg="%s tile map, level %d, seed %d" % (game, rnd, seed + i))
+            if rnd < 4:
+                np.testing.assert_array_equal(frames[rnd][c0:c0 + len(refs)], np.stack([r.reset() for r in refs]),
+                                              err_msg="%s reset frame %d" % (game, rnd))
+        for r in refs:
+            r.close()

@@ -80,3 +80,54 @@ def test_max_episode_steps_truncates():
     b, _, _ = sim.field("ep_steps")
     assert (b.view(np.int32) == 0).all()       # truncated at step 5 -> regenerated
     assert not term.any()                      # truncation is not termination
+
+
+@pytest.mark.parametrize("game", IMPLEMENTED)
+@pytest.mark.parametrize("max_ep", [1, 5])
+def test_truncation_live_oracle(game, max_ep, oracle_available):
+    """max_episode_steps (BASELINE configs[4]) against the reference driven as "step; every k steps: reset()":
+    pixels, rewards, terminated, truncated, and the RNG state + tile map at the end. (GPU twin with more envs,
+    longer horizons and k up to 32: tests/test_gpu_parity_r2.py.)"""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_env
+    n, seed, T = 3, 600 + max_ep, 8 * max_ep + 3
+    rs = np.random.RandomState(9)
+    acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
+    sim = SimAdapter(game, n, seed, max_episode_steps=max_ep)
+    refs = [ref_env.RefEnv(game, seed + i) for i in range(n)]
+    np.testing.assert_array_equal(sim.reset(), np.stack([r.reset() for r in refs]))
+    age = np.zeros(n, np.int64)
+    for t in range(T):
+        o, rw, d = sim.step(acts[t])
+        tr = np.ctypeslib.as_array(__import__("tests.simlib", fromlist=["lib"]).lib().hs_truncated(sim.sim.h), shape=(n,)).astype(bool)
+        for i, e in enumerate(refs):
+            oo, w, dd = e.step(acts[t, i])
+            age[i] += 1
+            trunc = (not dd) and age[i] >= max_ep
+            if dd or trunc:
+                oo = e.reset()
+                age[i] = 0
+            assert w == rw[i] and dd == d[i] and trunc == tr[i], (t, i)
+            np.testing.assert_array_equal(o[i], oo, err_msg="pixels, step %d env %d" % (t, i))
+    f = sim.fields()
+    for i, r in enumerate(refs):
+        st, pos = r.rng_state()
+        assert pos == f["mti"][i]
+        np.testing.assert_array_equal(st, f["mt"][i])
+        r.close()
+
+
+def test_maze_timeout_live_oracle(oracle_available):
+    """maze.cpp:308-310: an env that never reaches the goal terminates at step 500."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_env
+    n, seed, T = 2, 41, 503
+    acts = np.full((T, n), 4, np.int32)
+    acts[:, 1] = np.random.RandomState(1).randint(0, 15, size=T)
+    refs = [ref_env.RefEnv("maze", seed + i) for i in range(n)]
+    episodes = check_against_oracle(SimAdapter("maze", n, seed), refs, acts, tag="maze timeout")
+    assert episodes >= 1
+    for r in refs:
+        r.close()
