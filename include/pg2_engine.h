@@ -82,6 +82,7 @@ PG2_API uint8_t* pg2_truncated_device(pg2_engine* e);
 PG2_API int32_t pg2_sync(pg2_engine* e);
 PG2_API void* pg2_stream(pg2_engine* e);            /* cudaStream_t the engine launches on */
 PG2_API int32_t pg2_num_envs(pg2_engine* e);
+PG2_API int32_t pg2_debug_phases(pg2_engine* e, uint64_t out[8]);   /* -DPG2_PHASE_TIMERS builds: render phase cycle counters; else -1 */
 PG2_API int32_t pg2_step_epw(pg2_engine* e);        /* environments per warp in the step kernel (1 = a whole warp per env) */
 PG2_API int64_t pg2_kernel_launches(pg2_engine* e); /* kernels launched so far (bench.py gpu_launches) */
 PG2_API int64_t pg2_state_bytes_per_env(pg2_engine* e);

@@ -43,6 +43,7 @@ bool load_textures(const char* blob_path, const char* const* names, int count, s
     for (uint32_t i = 0; i < n; i++) index[std::string(entries[i].name, strnlen(entries[i].name, sizeof(entries[i].name)))] = (int)i;
     infos->resize(count);
     texels->clear();
+    texels->push_back(0xff000000u);   // atlas[0] = opaque black = the clear colour (what the rasteriser reads where nothing is drawn)
     std::vector<uint8_t> z, raw;
     for (int t = 0; t < count; t++) {
         auto it = index.find(names[t]);

@@ -210,6 +210,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, PG2_RENDER_MIN_CTAS) k_render(
     int next = 0;
     if (threadIdx.x == 0) next = take_ticket();
     for (;;) {
+#ifdef PG2_PHASE_TIMERS
+        long long phase_t__ = clock64();
+#endif
         __syncthreads();   // every warp is done with the previous frame (bands are stored per warp, without a CTA barrier)
         bool reuse = false;
         if (threadIdx.x == 0) {
@@ -220,6 +223,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, PG2_RENDER_MIN_CTAS) k_render(
         __syncthreads();
         const int env = s_env;
         if (env < 0) break;
+        PG2_PHASE_MARK(1);
+#ifdef PG2_PHASE_TIMERS
+        if (threadIdx.x == 0) atomicAdd(&g_phase[0], 1ull);
+#endif
         // the next frame's ticket is taken now: the atomic's round trip overlaps this frame's work
         if (threadIdx.x == 0) next = take_ticket();
         render_body<G>(s, c, env, f, tex, atlas, obs, view_cache, false);
@@ -266,6 +273,7 @@ struct EngineBase {
     int64_t launches = 0;
     int num_sms = 148;
     int step_epw = 1;          // environments per warp in k_step
+    int render_ctas_per_sm = 8;   // resident CTAs of k_render per SM (occupancy query)
     // device buffers
     void* state_mem = nullptr;
     void* common_mem = nullptr;
@@ -462,6 +470,10 @@ struct Engine : EngineBase {
         if (ensure_sort_table(device)) return 1;
         PG2_CUDA(cudaStreamSynchronize(stream));
         PG2_CUDA(cudaFuncSetAttribute(k_reset<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, reset_smem()));
+        // persistent render grid = exactly the CTAs that are resident at once (registers / shared memory decide)
+        PG2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&render_ctas_per_sm, k_render<G>, RENDER_THREADS, 0));
+        if (render_ctas_per_sm < 1) render_ctas_per_sm = 1;
+        if (const char* o = getenv("PG2_RENDER_CTAS_PER_SM")) render_ctas_per_sm = atoi(o) > 0 ? atoi(o) : render_ctas_per_sm;
         // cenv_make: seed, then reset() once (level #1 is generated and never rendered, Q29)
         k_seed<<<(N + 127) / 128, 128, 0, stream>>>(common, N, base_seed, nullptr, 1);
         launches++;
@@ -531,8 +543,7 @@ struct Engine : EngineBase {
         launches++;
     }
     void launch_render(int mode, int* ticket, cudaStream_t on) {
-        int per_sm = 8;
-        if (const char* o = getenv("PG2_RENDER_CTAS_PER_SM")) per_sm = atoi(o) > 0 ? atoi(o) : per_sm;
+        const int per_sm = render_ctas_per_sm;
         int grid = N < num_sms * per_sm ? N : num_sms * per_sm;
         k_render<G><<<grid, RENDER_THREADS, 0, on>>>(st, common, texinfo, atlas, obs, ticket, mode, reset_list, reset_count + parity, pending, N, view_cache);
         launches++;
@@ -768,6 +779,20 @@ int32_t pg2_sync(pg2_engine* e) {
 }
 void* pg2_stream(pg2_engine* e) { return (void*)e->impl->stream; }
 int32_t pg2_num_envs(pg2_engine* e) { return e->impl->N; }
+// Debug builds only (-DPG2_PHASE_TIMERS): reads and clears the render phase counters (pg2_kernels.cuh); -1 otherwise.
+int32_t pg2_debug_phases(pg2_engine* e, uint64_t out[8]) {
+#ifdef PG2_PHASE_TIMERS
+    PG2_ON_DEVICE(e->impl->device);
+    unsigned long long z[8] = {};
+    PG2_CUDA(cudaDeviceSynchronize());
+    PG2_CUDA(cudaMemcpyFromSymbol(out, g_phase, sizeof(z)));
+    PG2_CUDA(cudaMemcpyToSymbol(g_phase, z, sizeof(z)));
+    return 0;
+#else
+    (void)e; (void)out;
+    return -1;
+#endif
+}
 int32_t pg2_step_epw(pg2_engine* e) { return e->impl->step_epw; }
 int64_t pg2_kernel_launches(pg2_engine* e) { return e->impl->launches; }
 int64_t pg2_state_bytes_per_env(pg2_engine* e) { return (int64_t)e->impl->state_bytes_per_env(); }
@@ -886,11 +911,12 @@ int64_t pg2_load_texture_host(const char* assets_path, const char* name, int32_t
     if (w) *w = infos[0].w;
     if (h) *h = infos[0].h;
     if (blend) *blend = (int32_t)infos[0].blend;
+    const size_t n = (size_t)infos[0].w * infos[0].h;   // the texture follows the atlas' black texel (atlas[0])
     if (out) {
-        if (capacity < (int64_t)texels.size()) { g_error = "pg2_load_texture_host: buffer too small"; return -2; }
-        memcpy(out, texels.data(), texels.size() * sizeof(uint32_t));
+        if (capacity < (int64_t)n) { g_error = "pg2_load_texture_host: buffer too small"; return -2; }
+        memcpy(out, texels.data() + infos[0].offset, n * sizeof(uint32_t));
     }
-    return (int64_t)texels.size();
+    return (int64_t)n;
 }
 
 }  // extern "C"

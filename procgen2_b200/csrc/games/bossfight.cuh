@@ -54,6 +54,7 @@ struct BossFight {
     static constexpr bool PREFETCH_LEVELS = false;   // step() draws from the RNG: the next level is not known ahead of time
     static const char* reset_keeps() { return ""; }
     static constexpr int TILE_CLASSES = 1;
+    static constexpr int WIN_ROWS = 1;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
     static constexpr bool HAS_TILES = false;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = true;    // fixed camera, no tile layer: the background image is cached per env
     static constexpr int MB = 64, NEX = 8, AB = 32, MAX_BAR = 4;

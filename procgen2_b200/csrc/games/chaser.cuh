@@ -50,6 +50,7 @@ struct Chaser {
     static constexpr bool PREFETCH_LEVELS = false;   // step() draws from the RNG: the next level is not known ahead of time
     static const char* reset_keeps() { return ""; }
     static constexpr int TILE_CLASSES = 1;
+    static constexpr int WIN_ROWS = 14;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = true;    // fixed camera and tile map within an episode: the base image (background + tiles) is cached per env
     static constexpr int TILE_STRIDE = 128, FREE_STRIDE = 64;

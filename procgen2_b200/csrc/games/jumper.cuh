@@ -48,6 +48,7 @@ struct Jumper {
     static constexpr bool PREFETCH_LEVELS = true;    // the RNG is only drawn inside reset(): the next level is generated one episode ahead
     static const char* reset_keeps() { return " cam_x cam_y to_goal_x to_goal_y "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 2;
+    static constexpr int WIN_ROWS = 16;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = false;   // the camera follows the agent: the base image changes every frame (a camera-keyed cache measured slower)
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID, SPIKE };

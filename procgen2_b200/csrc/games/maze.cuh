@@ -39,6 +39,7 @@ struct Maze {
     static constexpr bool PREFETCH_LEVELS = true;    // the RNG is only drawn inside reset(): the next level is generated one episode ahead
     static const char* reset_keeps() { return "  "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 1;
+    static constexpr int WIN_ROWS = 28;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = true;    // fixed camera and tile map within an episode: the base image (background + tiles) is cached per env
     static constexpr int TILE_STRIDE = 640;

@@ -60,8 +60,17 @@ PG2_DEV void reset_body(const typename G::State& s, const CommonState& c, int en
     __syncwarp();
 }
 
+// Debug build (-DPG2_PHASE_TIMERS): wall cycles of the render phases of a frame, as seen by thread 0 of the CTA, summed over
+// all frames: [0] frames, [1] ticket + frame_begin, [2] build_frame, [3] finalize, [4] rasterise (thread 0's warp).
+#ifdef PG2_PHASE_TIMERS
+__device__ unsigned long long g_phase[8];
+#define PG2_PHASE_MARK(k) do { if (threadIdx.x == 0) { long long now__ = clock64(); atomicAdd(&g_phase[k], (unsigned long long)(now__ - phase_t__)); phase_t__ = now__; } } while (0)
+#else
+#define PG2_PHASE_MARK(k) do { } while (0)
+#endif
+
 template <class G>
-using FrameOf = FrameT<G::MAX_POST, G::ROTATES, G::TILE_CLASSES>;
+using FrameOf = FrameT<G::MAX_POST, G::ROTATES, G::TILE_CLASSES, G::WIN_ROWS>;
 
 // render_game(true) + RGBA->RGB pack for one env by one CTA (f.tileword filled by frame_init_tiletex before).
 // view_cache (G::STATIC_VIEW games, else nullptr): VIEW_CACHE_BYTES per env = the env's base image;
@@ -75,13 +84,20 @@ PG2_DEV void render_body(const typename G::State& s, const CommonState& c, int e
         frame_begin(f, cache != nullptr && c.view_valid[env] != 0);
         __syncthreads();
     }
+#ifdef PG2_PHASE_TIMERS
+    long long phase_t__ = clock64();
+#endif
     G::build_frame(s, c, env, f, tex);
     __syncthreads();   // the only barrier between the frame builder's smem writes and their readers
+    PG2_PHASE_MARK(2);
     frame_finalize<G>(f);
+    PG2_PHASE_MARK(3);
     // a frame that needs the general ordered path everywhere (never observed) is neither cached nor marked
     uint8_t* img = (cache && (f.reuse || !f.wide)) ? cache : nullptr;
     frame_rasterise<G>(f, atlas, obs + (size_t)env * OBS_BYTES, img);
+    PG2_PHASE_MARK(4);
     if (img && !f.reuse && threadIdx.x == 0) c.view_valid[env] = 1;   // read by later launches only
+    if (f.overflow && threadIdx.x == 0) c.fault[env] |= 8;            // tile window taller than G::WIN_ROWS: the frame is wrong
 }
 
 }  // namespace pg2

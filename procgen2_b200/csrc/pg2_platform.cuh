@@ -92,6 +92,7 @@ inline int warp_bcast(int v) { return v; }
 inline float warp_bcast(float v) { return v; }
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
+inline uint32_t atomicExch(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
 inline int smem_atomic_inc(int* p) { return (*p)++; }
 inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }

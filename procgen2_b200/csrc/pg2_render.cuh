@@ -6,15 +6,18 @@
 //   clear(0,0,0) -> "pre" blit (background) -> tile layer (y-major, x-minor; tilemap.cpp:303-320)
 //   -> "post" blits (particles, sprites, agent, HUD) in submission order.
 //
-// The frame is drawn in shared memory by row bands (8 bands x 8 rows, handed out to the CTA's warps):
-//   base pass   every thread owns a run of 4 pixels of one row. Background + tile layer are a GATHER: per pixel
-//               the top-most tile candidate is found from per-row tile presence bitmaps (no walk over empty
-//               cells), ONE texel is fetched (four independent fetches in flight per thread), an opaque texel
-//               decides the pixel; a transparent / translucent one sends that pixel to the ordered slow path.
-//               Four finished pixels are packed into three 32-bit words with byte permutes and stored.
+// The frame is drawn in shared memory by row bands (8 bands x 8 rows, handed out to the CTA's warps), as RGBA words:
+//   base pass   every thread owns a run of 4 pixels of one row. Background + tile layer are a GATHER through a table
+//               resolved once per frame: rowcell[tile row][screen column] = atlas address of the top-most tile of that
+//               tile row under that column (texture + source column already folded in), so that a pixel costs one
+//               16-byte table read per 4 pixels, one add (the source row) and ONE texel fetch; an opaque texel decides
+//               the pixel, a transparent / translucent one (or an ambiguous table entry) takes the ordered slow path.
 //   post pass   the same warp then draws the post blits that touch its band, blit by blit in submission order
-//               (lanes = an 8x4 patch of the blit's destination rectangle), straight onto the packed RGB rows.
-//   store       the band leaves the SM as one 1 536-byte TMA bulk store (cp.async.bulk.global.shared::cta).
+//               (lanes = an 8x4 patch of the blit's destination rectangle), onto the RGBA words (two channels per
+//               multiply in the integer SRC-over).
+//   store       the band is packed RGBA -> RGB in place (byte permutes) and leaves the SM as one 1 536-byte TMA bulk
+//               store (cp.async.bulk.global.shared::cta); cached base images (G::STATIC_VIEW) come in the same way,
+//               as one 2 048-byte TMA bulk load per band (cp.async.bulk.shared::cta.global + mbarrier).
 //
 // The tile layer exploits that render_texture() is separable: a tile's destination columns only
 // depend on its x index and its rows only on its y index, so a frame needs <= 32 column and <= 32
@@ -32,7 +35,7 @@ constexpr int MAX_PRE = 2;
 #endif
 constexpr int RENDER_THREADS = PG2_RENDER_THREADS;
 constexpr uint8_t NO_TILE = 0xff;
-constexpr int BAND_ROWS = 8, NUM_BANDS = OBS_H / BAND_ROWS, BAND_BYTES = BAND_ROWS * OBS_W * 3;
+constexpr int BAND_ROWS = 8, NUM_BANDS = OBS_H / BAND_ROWS, BAND_BYTES = BAND_ROWS * OBS_W * 3, BAND_PX = BAND_ROWS * OBS_W;
 
 // std::sort permutation table. System_Sprite_Render::update sorts (z, entity) pairs
 // by z with std::sort (common_systems.cpp:36-38); every sprite of a game has the same z, so the
@@ -82,38 +85,61 @@ struct alignas(16) RowDesc {
     uint32_t rw;       // rlo | vr[0] << 8 | vr[1] << 12 | rlo * MAX_WIN << 16   (vr: 0b0011 for jr = 0, 0b1100 for jr = 1)
     int32_t pre_row;   // background: tex_offset + sy * tex_w under this row, -1: not covered
     uint32_t syw[2];   // [cls]: (sy * tex_w) of candidate row 0 | candidate row 1 << 16
-    uint32_t rm[2][2]; // [cls][jr]: presence bitmap of class-cls tiles in tile row rlo + jr
 };
+// Candidate slot of a screen column / row, written by the make_axis job of the tile column / row that covers it
+// (FrameT::cslot / rslot, [(cls * 2 + (tile index & 1)) * 64 + pixel]: the at most two tile columns that cover a pixel are
+// neighbours, so they differ in parity and never share a slot): valid | tile index << 16 | source sample.
+constexpr uint32_t SLOT_VALID = 0x80000000u;
+// pre_row / pre_sx of a screen row / column the background does not cover, as the base pass sees them (see raster_band_fast)
+constexpr uint32_t BG_HOLE = 0x40000000u;
+
+// What the base pass reads per screen row (one 16-byte word): the (at most two) tile rows that cover it, top-most first.
+// ra / rb index rows of FrameT::rowcell (WINR = the always-empty row: "none"); cov bit 2 * j + cls: tile row j (0 = a,
+// 1 = b) covers this screen row for tiles of shape class cls; syw = sy * tex_w per class (class 0 | class 1 << 16).
+struct alignas(16) RowFast {
+    uint32_t sywa, sywb;
+    int32_t pre_row;   // background: tex_offset + sy * tex_w under this row, -1: not covered
+    uint32_t meta;     // ra | rb << 8 | cov << 16
+};
+// rowcell entry: atlas offset of the tile texture + source x | ambiguous << 28 | shape class << 29 | present << 31.
+// Ambiguous: two tiles of different shape classes share the entry's tile row under this column, so which one is on
+// top depends on the screen row (the slow path decides).
+constexpr uint32_t RC_ADDR_MASK = 0x0fffffffu, RC_AMBIGUOUS = 1u << 28, RC_PRESENT = 0x80000000u;
 
 // Frame description of ONE environment, in shared memory. MAXP = capacity of the post-blit list (per game),
 // ROT = whether the game ever rotates a blit (bossfight, caveflyer, jumper HUD).
-template <int MAXP, bool ROT, int NCLS>
+template <int MAXP, bool ROT, int NCLS, int WINR_>
 struct FrameT {
-    static constexpr int MAX_POST = MAXP, NROT = ROT ? MAXP : 1;
+    static constexpr int MAX_POST = MAXP, NROT = ROT ? MAXP : 1, WINR = WINR_;
     static constexpr bool ROTATES = ROT;
-    alignas(16) uint8_t band_rgb[RENDER_THREADS / 32][BAND_BYTES];   // per warp: the band it is drawing, packed RGB rows
+    alignas(128) uint32_t band_px[RENDER_THREADS / 32][BAND_PX];     // per warp: the band it is drawing, RGBA words (packed to RGB in place before the store)
+    alignas(16) uint32_t rowcell[(WINR_ + 1) * OBS_W];                // [tile row of the window][screen column], + the always-empty row
+    RowFast rowf[OBS_H];
+    alignas(8) uint64_t mbar[RENDER_THREADS / 32];                    // per warp: mbarrier of its TMA bulk loads
+    uint32_t mbar_phase[RENDER_THREADS / 32];
     // ---- the view: everything the rasteriser needs of background + tile layer
     alignas(16) uint32_t col_cw[OBS_W];         // ColDesc fields, indexed by col_slot(X)
     uint32_t col_csx[OBS_W];
     int32_t col_pre[OBS_W];
     RowDesc rowd[OBS_H];
-    uint32_t cell[(MAX_WIN + 1) * MAX_WIN];     // window cells (+1 row: branch-free reads)
+    uint32_t cell[(WINR_ + 1) * MAX_WIN];       // window cells (+1 row: branch-free reads)
     FastBlit fpre[MAX_PRE];
     int npre;
     int wide;                                   // the frame needs the general ordered path for every pixel (never observed)
     int pre_blend;                              // background texture carries alpha
     // ---- per frame
     int reuse;                                  // the base image comes from the env's cache: the view is not built
+    int overflow;                               // the tile window has more rows than WINR (a sizing error: reported as fault bit 8)
     FastBlit fpost[MAXP];
     BlitRot post_rot[NROT];
     Blit pre[MAX_PRE];
     int npost;
     // tile layer: window origin (tile coordinates, y in render space), extents, descriptors per texture shape class
     int tx0, ty0, ncol, nrow, nclass;
-    Axis col[NCLS][MAX_WIN];
+    Axis col[NCLS][MAX_WIN];                    // (read by the general ordered path only)
     Axis row[NCLS][MAX_WIN];
-    uint32_t rowmask[2][MAX_WIN + 1];           // [cls][tile row]: bit cx set = a class-cls tile at window column cx
-    int cov_lo[2 * OBS_W], cov_hi[2 * OBS_W];   // [0,64): per screen column, [64,128): per screen row: covering tile range
+    alignas(16) uint32_t cslot[NCLS * 2 * OBS_W];   // candidate slots of the screen columns / rows, see SLOT_VALID
+    uint32_t rslot[NCLS * 2 * OBS_W];
     uint16_t bandmask[MAXP];                    // post blit k touches band b <=> bit b
     uint8_t live[256];                          // live_list(): ids of the live sprites in set order
     int wcount[2][RENDER_THREADS / 32];         // emit_post_blits: visible blits per warp (double-buffered by round)
@@ -353,10 +379,14 @@ PG2_DEV void tile_window(const Camera& cam, int* lower_x, int* lower_y, int* upp
     *upper_y = f2i(ceilf(__fadd_rn(ay, aw)));
 }
 
-// Games whose camera and tile map are fixed within an episode (G::STATIC_VIEW: maze, chaser) keep the BASE IMAGE of an env
-// (clear + background + tile layer, 12 288 B of packed RGB) in HBM: the first frame of an episode draws and stores it, the
-// following frames load it band by band instead of describing and rasterising the tile layer again.
-constexpr size_t VIEW_CACHE_BYTES = OBS_BYTES;
+// Games whose camera and tile map are fixed within an episode (G::STATIC_VIEW: maze, chaser, bossfight) keep the BASE
+// IMAGE of an env (clear + background + tile layer, 64x64 RGBA words = the band buffers' own format) in HBM: the first
+// frame of an episode draws and stores it, the following frames load it band by band (one TMA bulk load each) instead
+// of describing and rasterising the tile layer again.
+constexpr size_t VIEW_CACHE_BYTES = (size_t)OBS_W * OBS_H * 4;
+constexpr int BAND_CACHE_BYTES = BAND_PX * 4;
+
+struct alignas(16) Word16 { uint32_t a, b, c, d; };
 
 // Start of a frame (every thread; followed by a __syncthreads() before the game's frame builder runs). `reuse`: the base
 // image comes from the env's cache (G::STATIC_VIEW), so the view is not built.
@@ -364,19 +394,40 @@ template <class F>
 PG2_DEV void frame_begin(F& f, bool reuse = false) {   // `reuse` is only looked at by thread 0 (which knows the env)
     const int tid = threadIdx.x;
     if (tid == 0) {
-        f.npost = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1; f.next_band = 0; f.reuse = reuse ? 1 : 0;
+        f.npost = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1; f.next_band = 0; f.reuse = reuse ? 1 : 0; f.overflow = 0;
         if (!reuse) { f.npre = 0; f.wide = 0; f.pre_blend = 0; }
     }
-    for (int k = tid; k < 2 * OBS_W; k += blockDim.x) { f.cov_lo[k] = 255; f.cov_hi[k] = -1; }
+    // cslot and rslot are adjacent: one run of 16-byte words
+    for (int k = tid; k < (int)(sizeof(f.cslot) + sizeof(f.rslot)) / 16; k += blockDim.x) ((Word16*)f.cslot)[k] = Word16{ 0u, 0u, 0u, 0u };
 }
 
-// One band of the base image: band buffer <-> cache (16-byte words, 3 per lane, coalesced).
-struct alignas(16) Word16 { uint32_t a, b, c, d; };
-PG2_DEV void band_from_cache(uint8_t* buf, const uint8_t* __restrict__ cache_band, int lane) {
-    for (int i = lane; i < BAND_BYTES / 16; i += WARP_LANES) ((Word16*)buf)[i] = ((const Word16*)cache_band)[i];
+// One band of the base image: cache -> band buffer as ONE 2 048-byte TMA bulk load (async proxy, completion on the
+// warp's mbarrier), band buffer -> cache as 16-byte words (first frame of an episode only).
+template <class F>
+PG2_DEV void band_from_cache(F& f, int warp, uint32_t* buf, const uint8_t* __restrict__ cache_band, int lane) {
+#ifdef PG2_HOSTSIM
+    memcpy(buf, cache_band, BAND_CACHE_BYTES);
+    (void)f; (void)warp; (void)lane;
+#else
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&f.mbar[warp]);
+    const uint32_t phase = f.mbar_phase[warp];
+    __syncwarp();   // every lane has read the phase and is done with the buffer (generic proxy)
+    if (lane == 0) {
+        f.mbar_phase[warp] = phase ^ 1u;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of the buffer -> async proxy
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(BAND_CACHE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(cache_band), "n"(BAND_CACHE_BYTES), "r"(bar) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+#endif
 }
-PG2_DEV void band_to_cache(const uint8_t* buf, uint8_t* __restrict__ cache_band, int lane) {
-    for (int i = lane; i < BAND_BYTES / 16; i += WARP_LANES) ((Word16*)cache_band)[i] = ((const Word16*)buf)[i];
+PG2_DEV void band_to_cache(const uint32_t* buf, uint8_t* __restrict__ cache_band, int lane) {
+    for (int i = lane; i < BAND_CACHE_BYTES / 16; i += WARP_LANES) ((Word16*)cache_band)[i] = ((const Word16*)buf)[i];
 }
 
 // Background + tile layer of a frame (the "pre" blit of render_game and System_Tilemap::render, tilemap.cpp:294-320),
@@ -387,14 +438,15 @@ PG2_DEV void band_to_cache(const uint8_t* buf, uint8_t* __restrict__ cache_band,
 //     meanwhile), all running the same instruction stream;
 //   - the window's cells (tile_at(x, y): tile texture id or NO_TILE; x = window column + lx, y = render-space tile row)
 //     and the per-row presence bitmaps, one warp per tile row.
-// Every tile axis also registers itself in the covering range of the screen columns / rows it touches
-// (cov_lo / cov_hi, initialised by frame_begin).
+// Every tile axis also registers itself, with its source samples, in the candidate slots of the screen columns / rows it
+// covers (cslot / rslot, zeroed by frame_begin).
 template <class F, class ClassTex, class TileAt>
 PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int nclass, int lx, int ly, int ncol, int nrow,
                               ClassTex class_tex, TileAt tile_at, int bg_tex, float bg_x, float bg_y, float bg_scale) {
     const int tid = threadIdx.x, lane = tid % WARP_LANES, warp = tid / WARP_LANES;
     const int nwarps = ((int)blockDim.x + WARP_LANES - 1) / WARP_LANES;
     if (f.reuse) return;   // the base image comes from the env's cache: no descriptors, cells or background needed
+    if (nrow > F::WINR) { nrow = F::WINR; if (tid == 0) f.overflow = 1; }
     const int per = ncol + nrow, njobs = 2 + nclass * per;
     if (tid == 0) { f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = nclass; f.npre = 1; }
     for (int job = (int)blockDim.x - 1 - tid; job < njobs; job += blockDim.x) {
@@ -416,35 +468,48 @@ PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int n
             continue;
         }
         if (is_row) f.row[cls][idx] = a; else f.col[cls][idx] = a;
-        if (a.visible && a.d0 > -65536 && a.d0 < 65536 && a.dlen < 65536) {   // register in the covering ranges
-            const int p0 = max(a.d0, 0), p1 = min(a.d0 + a.dlen - 1, OBS_W - 1), o = is_row ? OBS_W : 0;
-            for (int pp = p0; pp <= p1; pp++) { atomicMin(&f.cov_lo[o + pp], idx); atomicMax(&f.cov_hi[o + pp], idx); }
+        if (a.visible && a.d0 > -65536 && a.d0 < 65536 && a.dlen < 65536) {
+            // register in the candidate slot of every screen column / row this tile column / row covers, with the source
+            // sample under it (rows: already multiplied by the texture width); a slot that was taken means three tiles
+            // cover one pixel: the frame goes the general ordered way
+            const int p0 = max(a.d0, 0), p1 = min(a.d0 + a.dlen - 1, OBS_W - 1);
+            uint32_t* slot = (is_row ? f.rslot : f.cslot) + (cls * 2 + (idx & 1)) * OBS_W;
+            const uint32_t mul = is_row ? (uint32_t)ti.w : 1u, lim = is_row ? 0xffffu : 0xffu;
+            uint32_t acc = a.inc / 2u + (uint32_t)(p0 - a.d0) * a.inc;
+            bool bad = false;
+            for (int pp = p0; pp <= p1; pp++, acc += a.inc) {
+                const uint32_t v = ((uint32_t)a.s0 + (acc >> 16)) * mul;
+                if (v > lim) bad = true;
+                if (atomicExch(&slot[pp], SLOT_VALID | (uint32_t)idx << 16 | (v & 0xffffu)) != 0u) bad = true;
+            }
+            if (bad) f.wide = 1;
         }
     }
     for (int cls = tid; cls < nclass; cls += blockDim.x) f.class_w[cls] = tex[class_tex(cls)].w;
-    // window cells: one warp per tile row, lanes = tile columns (rows >= nrow are never referenced: the always-empty
-    // row MAX_WIN stands in for them, see frame_finalize)
-    for (int ry = warp; ry < nrow; ry += nwarps) {
-        uint32_t m0 = 0u, m1 = 0u;
-        for (int cx = lane; cx < MAX_WIN; cx += WARP_LANES) {
-            const uint32_t tt = cx < ncol ? (uint32_t)tile_at(lx + cx, ly + ry) : (uint32_t)NO_TILE;
-            const uint32_t w = tt != NO_TILE ? f.tileword[tt & (MAX_TILE_TEX - 1)] : 0u;
-            f.cell[ry * MAX_WIN + cx] = w;
-            m0 |= lane_ballot(w != 0u && !(w >> 29 & 1u), cx);
-            m1 |= lane_ballot((w >> 29 & 1u) != 0u, cx);
+    // window cells: lanes = tile columns, two tile rows per warp pass when the window is at most 16 columns wide
+    // (cells right of the window stay unwritten: nothing valid ever points at them)
+    const int cpr = ncol <= 16 ? 16 : 32, rpp = 32 / cpr;
+    for (int ry0 = warp * rpp; ry0 < nrow; ry0 += nwarps * rpp)
+        for (int l = lane; l < 32; l += WARP_LANES) {
+            const int ry = ry0 + l / cpr, cx = l % cpr;
+            if (ry < nrow) {
+                const uint32_t tt = cx < ncol ? (uint32_t)tile_at(lx + cx, ly + ry) : (uint32_t)NO_TILE;
+                f.cell[ry * MAX_WIN + cx] = tt != NO_TILE ? f.tileword[tt & (MAX_TILE_TEX - 1)] : 0u;
+            }
         }
-        if (lane == 0) { f.rowmask[0][ry] = m0; f.rowmask[1][ry] = m1; }
-    }
 }
 
 // ---- per-pixel evaluation ---------------------------------------------------------------------
 
-// After the game's frame builder (and a __syncthreads()): ColDesc / RowDesc of every screen column / row.
+// After the game's frame builder (and a __syncthreads()): the per-column / per-row tables of the base pass, from the
+// candidate slots the axis jobs filled. Job k < 64: screen column k (ColDesc, background x, rowcell entries of the even
+// tile rows); job 64 + k: screen row k (RowDesc, RowFast) and the rowcell entries of column k for the odd tile rows.
 template <class G, class F>
 PG2_DEV_NOINLINE void frame_finalize(F& f) {
     if (f.reuse) { __syncthreads(); return; }
+    constexpr int NCLS = G::TILE_CLASSES;
     const int tid = threadIdx.x;
-    const int npre = f.npre, nclass = f.nclass;
+    const int npre = f.npre, nrow = f.nrow;
     // the fast path handles ONE un-rotated background with alpha_mod 255
     const bool pre_ok = npre == 0 || (npre == 1 && !f.pre[0].rotated && f.pre[0].alpha_mod == 255);
     if (tid == 0) {
@@ -459,49 +524,102 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
     for (int k = tid; k < 2 * OBS_W; k += blockDim.x) {
         const bool is_row = k >= OBS_W;
         const int p = k & (OBS_W - 1);
-        const int lo = f.cov_lo[k], hi = f.cov_hi[k];
-        uint32_t word = 0u, smp[2] = { 0u, 0u };
-        if (lo <= hi) {
-            word = (uint32_t)lo;
+        // the column's candidates (always needed: both jobs of a column build rowcell entries)
+        const uint32_t* cs = f.cslot + p;
+        uint32_t cw[NCLS][2];
+        int clo = 255, chi = -1;
+#pragma unroll
+        for (int cls = 0; cls < NCLS; cls++)
+#pragma unroll
+            for (int par = 0; par < 2; par++) {
+                const uint32_t w = G::HAS_TILES ? cs[(cls * 2 + par) * OBS_W] : 0u;
+                cw[cls][par] = w;
+                if (w) { const int idx = (int)(w >> 16 & 31u); clo = min(clo, idx); chi = max(chi, idx); }
+            }
+        if (chi - clo > 1) f.wide = 1;
+        // candidate j of class cls = the slot of parity (clo + j) & 1
+        uint32_t cword = chi >= 0 ? (uint32_t)clo : 0u, csx = 0u;
+        uint32_t cj[NCLS][2];
+#pragma unroll
+        for (int cls = 0; cls < NCLS; cls++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const uint32_t w = chi >= 0 ? ((clo + j) & 1 ? cw[cls][1] : cw[cls][0]) : 0u;
+                cj[cls][j] = w;
+                if (w) { cword |= (j ? 0xau : 0x5u) << (8 + 4 * cls); csx |= (w & 255u) << (8 * (cls * 2 + j)); }
+            }
+        if (!is_row) {
+            int32_t pv = -1;
+            if (npre >= 1 && pre_ok) {
+                const Blit& b = f.pre[0];
+                if (b.ax.visible && b.ay.visible && (unsigned)(p - b.ax.d0) < (unsigned)b.ax.dlen) pv = axis_sample(b.ax, p, b.flip_h != 0);
+            }
+            const int slot = col_slot(p);
+            f.col_cw[slot] = cword; f.col_csx[slot] = csx; f.col_pre[slot] = pv;
+        } else {
+            const uint32_t* rs = f.rslot + p;
+            uint32_t rwv[NCLS][2];
+            int lo = 255, hi = -1;
+#pragma unroll
+            for (int cls = 0; cls < NCLS; cls++)
+#pragma unroll
+                for (int par = 0; par < 2; par++) {
+                    const uint32_t w = G::HAS_TILES ? rs[(cls * 2 + par) * OBS_W] : 0u;
+                    rwv[cls][par] = w;
+                    if (w) { const int idx = (int)(w >> 16 & 31u); lo = min(lo, idx); hi = max(hi, idx); }
+                }
             if (hi - lo > 1) f.wide = 1;
-            for (int cls = 0; cls < nclass; cls++)
+            uint32_t word = hi >= 0 ? (uint32_t)lo : 0u, smp[2] = { 0u, 0u };
+#pragma unroll
+            for (int cls = 0; cls < NCLS; cls++)
+#pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    if (lo + j > hi) continue;
-                    const Axis& a = is_row ? f.row[cls][lo + j] : f.col[cls][lo + j];
-                    if (!a.visible || (unsigned)(p - a.d0) >= (unsigned)a.dlen) continue;
-                    const uint32_t v = (uint32_t)axis_sample(a, p, false);
-                    if (is_row) {
-                        const uint32_t w = (uint32_t)f.class_w[cls];
-                        if (v * w > 0xffffu) f.wide = 1;
-                        smp[cls] |= ((v * w) & 0xffffu) << (16 * j);
-                        word |= (j ? 0xcu : 0x3u) << (8 + 4 * cls);
-                    } else {
-                        if (v > 0xffu) f.wide = 1;
-                        smp[0] |= (v & 0xffu) << (8 * (cls * 2 + j));
-                        word |= (j ? 0xau : 0x5u) << (8 + 4 * cls);
+                    const uint32_t w = hi >= 0 ? ((lo + j) & 1 ? rwv[cls][1] : rwv[cls][0]) : 0u;
+                    if (w) { word |= (j ? 0xcu : 0x3u) << (8 + 4 * cls); smp[cls] |= (w & 0xffffu) << (16 * j); }
+                }
+            int32_t pv = -1;
+            if (npre >= 1 && pre_ok) {
+                const Blit& b = f.pre[0];
+                if (b.ax.visible && b.ay.visible && (unsigned)(p - b.ay.d0) < (unsigned)b.ay.dlen)
+                    pv = (int32_t)(b.tex_offset + (uint32_t)axis_sample(b.ay, p, false) * b.tex_w);
+            }
+            RowDesc rd;
+            rd.rw = word | ((hi >= 0 ? (uint32_t)lo : 0u) * MAX_WIN) << 16; rd.pre_row = pv; rd.syw[0] = smp[0]; rd.syw[1] = smp[1];
+            f.rowd[p] = rd;
+            // the base pass's view of the row: tile row a = the top-most covering one (candidate ja), b = the one below
+            RowFast rf;
+            const uint32_t ja = lo < hi ? 1u : 0u;
+            const uint32_t v0 = word >> 8 & 15u, v1 = word >> 12 & 15u;            // class 0 / 1: 0x3 = candidate row 0, 0xc = row 1
+            const uint32_t cova = (v0 >> (2u * ja) & 1u) | (v1 >> (2u * ja) & 1u) << 1;
+            const uint32_t covb = ja ? ((v0 & 1u) | (v1 & 1u) << 1) : 0u;
+            rf.sywa = (smp[0] >> (16u * ja) & 0xffffu) | (smp[1] >> (16u * ja) & 0xffffu) << 16;
+            rf.sywb = ja ? ((smp[0] & 0xffffu) | (smp[1] & 0xffffu) << 16) : 0u;
+            rf.pre_row = pv < 0 ? (int32_t)BG_HOLE : pv;
+            const uint32_t ra = hi >= 0 ? (uint32_t)lo + ja : (uint32_t)F::WINR, rb = ja ? (uint32_t)lo : (uint32_t)F::WINR;
+            rf.meta = ra | rb << 8 | (cova | covb << 2) << 16;
+            f.rowf[p] = rf;
+        }
+        // rowcell[tile row][column p]: the top-most tile of the tile row under this screen column (painter's order within a
+        // tile row = ascending tile column), texture offset + source x folded in; even tile rows by the column job, odd
+        // ones by the row job of the same index
+        if (G::HAS_TILES) {
+            const bool two = clo < chi;
+            for (int r = is_row ? 1 : 0; r < nrow; r += 2) {
+                uint32_t e = 0u;
+                if (chi >= 0) {
+                    const uint32_t w0 = f.cell[r * MAX_WIN + clo], w1 = two ? f.cell[r * MAX_WIN + clo + 1] : 0u;
+                    const uint32_t c0 = NCLS > 1 ? w0 >> 29 & 1u : 0u, c1 = NCLS > 1 ? w1 >> 29 & 1u : 0u;
+                    const uint32_t s0 = NCLS > 1 && c0 ? cj[NCLS - 1][0] : cj[0][0], s1 = NCLS > 1 && c1 ? cj[NCLS - 1][1] : cj[0][1];
+                    const bool ok0 = w0 != 0u && s0 != 0u, ok1 = w1 != 0u && s1 != 0u;
+                    if (ok1) {
+                        e = (w1 & ~(1u << 28)) + (s1 & 255u);
+                        if (NCLS > 1 && ok0 && c0 != c1) e |= RC_AMBIGUOUS;
+                    } else if (ok0) {
+                        e = (w0 & ~(1u << 28)) + (s0 & 255u);
                     }
                 }
-        }
-        int32_t pv = -1;
-        if (npre >= 1 && pre_ok) {
-            const Blit& b = f.pre[0];
-            const Axis& a = is_row ? b.ay : b.ax;
-            if (b.ax.visible && b.ay.visible && (unsigned)(p - a.d0) < (unsigned)a.dlen) {
-                int s = axis_sample(a, p, is_row ? false : (b.flip_h != 0));
-                pv = is_row ? (int32_t)(b.tex_offset + (uint32_t)s * b.tex_w) : s;
+                f.rowcell[r * OBS_W + p] = e;
             }
-        }
-        if (is_row) {
-            RowDesc rd;
-            rd.rw = word | ((lo <= hi ? (uint32_t)lo : 0u) * MAX_WIN) << 16; rd.pre_row = pv; rd.syw[0] = smp[0]; rd.syw[1] = smp[1];
-            const int r0 = lo <= hi ? lo : MAX_WIN;       // row MAX_WIN is always empty
-            const int r1 = lo < hi ? lo + 1 : MAX_WIN;
-            rd.rm[0][0] = f.rowmask[0][r0]; rd.rm[0][1] = f.rowmask[0][r1];
-            rd.rm[1][0] = f.rowmask[1][r0]; rd.rm[1][1] = f.rowmask[1][r1];
-            f.rowd[p] = rd;
-        } else {
-            const int slot = col_slot(p);
-            f.col_cw[slot] = word; f.col_csx[slot] = smp[0]; f.col_pre[slot] = pv;
         }
     }
     __syncthreads();
@@ -556,13 +674,18 @@ PG2_DEV uint32_t blend_packed(uint32_t color, uint32_t texel, uint32_t blend, ui
 }
 
 // Tile candidates of a pixel as a 4-bit set (candidate q = jr * 2 + jc <=> tile (rlo + jr, clo + jc)): a tile is
-// there and the axes of its shape class cover the pixel. Painter's order = ascending q.
-template <int NCLASS>
-PG2_DEV uint32_t tile_candidates(const RowDesc& rd, uint32_t cw) {
-    const uint32_t clo = cw & 31u, v = cw & rd.rw;
-    uint32_t p = (((rd.rm[0][0] >> clo) & 3u) | ((rd.rm[0][1] >> clo) & 3u) << 2) & (v >> 8);
-    if (NCLASS > 1) p |= (((rd.rm[1][0] >> clo) & 3u) | ((rd.rm[1][1] >> clo) & 3u) << 2) & (v >> 12);
-    return p & 15u;
+// there and the axes of its shape class cover the pixel. Painter's order = ascending q. (Slow path only.)
+template <int NCLASS, class F>
+PG2_DEV uint32_t tile_candidates(const F& f, const RowDesc& rd, uint32_t cw) {
+    const uint32_t v = cw & rd.rw, base = (rd.rw >> 16) + (cw & 31u);
+    uint32_t p = 0u;
+#pragma unroll
+    for (uint32_t q = 0; q < 4u; q++) {
+        const uint32_t w = f.cell[base + (q >> 1) * MAX_WIN + (q & 1u)];
+        const uint32_t cls = NCLASS > 1 ? w >> 29 & 1u : 0u;
+        if (w != 0u && (v >> (8u + 4u * cls) >> q & 1u)) p |= 1u << q;
+    }
+    return p;
 }
 
 template <class F>
@@ -599,7 +722,7 @@ PG2_DEV_COLD uint32_t shade_base_ordered(const F& f, const uint32_t* __restrict_
     if (!f.wide) {
         const RowDesc rd = f.rowd[Y];
         const ColDesc cd = load_col(f, X);
-        uint32_t p = tile_candidates<G::TILE_CLASSES>(rd, cd.cw);
+        uint32_t p = tile_candidates<G::TILE_CLASSES>(f, rd, cd.cw);
         for (uint32_t q = 0; q < 4u; q++)
             if (p >> q & 1u) {
                 texel = __ldg(atlas + tile_texel_index<G::TILE_CLASSES>(f, rd, cd, q));
@@ -607,9 +730,8 @@ PG2_DEV_COLD uint32_t shade_base_ordered(const F& f, const uint32_t* __restrict_
             }
         return color;
     }
-    const int rlo = f.cov_lo[OBS_W + Y], rhi = f.cov_hi[OBS_W + Y], clo = f.cov_lo[X], chi = f.cov_hi[X];
-    for (int ry = rlo; ry <= rhi; ry++)
-        for (int cx = clo; cx <= chi; cx++) {
+    for (int ry = 0; ry < f.nrow; ry++)       // (never observed: every tile of the window is tested against the pixel)
+        for (int cx = 0; cx < f.ncol; cx++) {
             const uint32_t w = f.cell[ry * MAX_WIN + cx];
             if (!w) continue;
             const uint32_t cls = (w >> 29) & 1u;
@@ -645,56 +767,126 @@ PG2_DEV_COLD uint32_t shade_base_continue(const F& f, const uint32_t* __restrict
     return a ? shade_base_ordered<G>(f, atlas, X, Y) : 0u;
 }
 
-// Base pass of one band: clear + background + tile layer of 8 rows, packed into the warp's band buffer.
+// A pixel the base pass could not decide from its table: all tile candidates top-down, then the background.
+#ifdef PG2_HOSTSIM
+static long g_dbg_slow = 0, g_dbg_quads = 0, g_dbg_quads_slow = 0, g_dbg_rb = 0;   // host-sim statistics (scripts/sim_check.py)
+#endif
 template <class G, class F>
-PG2_DEV void raster_band_base(F& f, const uint32_t* __restrict__ atlas, int band, int lane, uint8_t* buf) {
-    constexpr int NCLASS = G::TILE_CLASSES;
-    const bool wide = f.wide != 0;
-    for (int it = 0; it < BAND_ROWS / 2; it++)
-        for (int l = lane; l < 32; l += WARP_LANES) {
-            const int Y = band * BAND_ROWS + it * 2 + (l >> 4), X0 = (l & 15) * 4;
-            uint32_t color[4];
-            if (!wide) {
-                const RowDesc rd = f.rowd[Y];
-                uint32_t cand[4], texel[4];
+PG2_DEV_COLD uint32_t shade_base_slow(const F& f, const uint32_t* __restrict__ atlas, int X, int Y) {
+#ifdef PG2_HOSTSIM
+    g_dbg_slow++;
+#endif
+    const RowDesc rd = f.rowd[Y];
+    const uint32_t p = G::HAS_TILES ? tile_candidates<G::TILE_CLASSES>(f, rd, load_col(f, X).cw) : 0u;
+    return shade_base_continue<G>(f, atlas, X, Y, p);
+}
+
+// Base pass of one band: clear + background + tile layer of 8 rows as RGBA words in the warp's band buffer.
+// A thread owns PG2_BASE_PX consecutive pixels of a row: 16-byte reads of the top tile row's rowcell entries, per pixel
+// one add + one select + one texel fetch (independent fetches in flight), 16-byte stores. The second covering tile row is only looked at on the few screen rows that have one.
+// A pixel the background does not cover reads the atlas' black texel (index 0 = the clear colour): pre_row / pre_sx of
+// an uncovered row / column are BG_HOLE, which no sum of real indices reaches.
+#ifndef PG2_BASE_PX
+#define PG2_BASE_PX 4   // pixels per thread in the base pass (4 or 8; measured: 4 is 8-10 % faster, fewer live registers)
+#endif
+template <class G, class F>
+PG2_DEV void raster_band_fast(F& f, const uint32_t* __restrict__ atlas, int band, int lane, uint32_t* buf) {
+    constexpr int NCLASS = G::TILE_CLASSES, PX = PG2_BASE_PX, LPR = OBS_W / PX, RPP = 32 / LPR;   // lanes per row, rows per pass
+    for (int l = lane; l < 32; l += WARP_LANES) {
+        const int X0 = (l % LPR) * PX;
+        uint32_t pre_sx[PX];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    ColDesc cd;   // col_slot(X0 + i) = (l & 15) + 16 * i
-                    cd.cw = f.col_cw[(l & 15) + 16 * i]; cd.csx = f.col_csx[(l & 15) + 16 * i]; cd.pre_sx = f.col_pre[(l & 15) + 16 * i];
-                    const uint32_t p = G::HAS_TILES ? tile_candidates<NCLASS>(rd, cd.cw) : 0u;
-                    cand[i] = p;
-                    const uint32_t tidx = G::HAS_TILES ? tile_texel_index<NCLASS>(f, rd, cd, bfind(p | 1u)) : 0u;
-                    const bool bg_ok = (rd.pre_row | cd.pre_sx) >= 0;
-                    const uint32_t idx = p ? tidx : (uint32_t)rd.pre_row + (uint32_t)cd.pre_sx;
-                    texel[i] = (p || bg_ok) ? __ldg(atlas + idx) : 0xff000000u;   // nothing there: the clear colour
-                }
+        for (int i = 0; i < PX; i++) { const int32_t v = f.col_pre[col_slot(X0 + i)]; pre_sx[i] = v < 0 ? BG_HOLE : (uint32_t)v; }
+        for (int it = 0; it < BAND_ROWS / RPP; it++) {
+            const int yl = it * RPP + l / LPR, Y = band * BAND_ROWS + yl;
+            const RowFast rf = f.rowf[Y];
+            uint32_t at[PX], texel[PX], flags = 0u;
 #pragma unroll
-                for (int i = 0; i < 4; i++) color[i] = texel[i];
-                // opaque-copy textures carry A = 255 in the atlas: ONE test covers the common case of four opaque texels
-                if (((texel[0] & texel[1] & texel[2] & texel[3]) >> 24) != 255u) {
+            for (int i = 0; i < PX; i++) {
+                const uint32_t v = (uint32_t)rf.pre_row + pre_sx[i];
+                at[i] = v >= BG_HOLE ? 0u : v;
+            }
+            if (G::HAS_TILES) {
+                const uint32_t ra = rf.meta & 255u, rb = rf.meta >> 8 & 255u;
+                if (rb != (uint32_t)F::WINR) {   // a second tile row covers this screen row: the lower one first, then a on top
+                    uint32_t eb[PX];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const uint32_t a = texel[i] >> 24;
-                        if (a != 255u) {   // transparent: next candidate below; translucent: blend in reference order
-                            if (a != 0u) color[i] = shade_base_ordered<G>(f, atlas, X0 + i, Y);
-                            else color[i] = cand[i] ? shade_base_continue<G>(f, atlas, X0 + i, Y, cand[i] & ~(1u << bfind(cand[i]))) : 0u;
-                        }
+                    for (int i = 0; i < PX; i += 4) { const Word16 w = *(const Word16*)&f.rowcell[rb * OBS_W + X0 + i]; eb[i] = w.a; eb[i + 1] = w.b; eb[i + 2] = w.c; eb[i + 3] = w.d; }
+#pragma unroll
+                    for (int i = 0; i < PX; i++) {
+                        const uint32_t e = eb[i];
+                        if (NCLASS > 1) {
+                            const uint32_t cls = e >> 29 & 1u;
+                            if ((int32_t)e < 0 && (rf.meta >> (18u + cls) & 1u)) at[i] = (e & RC_ADDR_MASK) + (cls ? rf.sywb >> 16 : rf.sywb & 0xffffu);
+                        } else if ((int32_t)e < 0) at[i] = (e & RC_ADDR_MASK) + rf.sywb;
+                        flags |= e;
                     }
                 }
-            } else {
+                uint32_t ea[PX];
 #pragma unroll
-                for (int i = 0; i < 4; i++) color[i] = shade_base_ordered<G>(f, atlas, X0 + i, Y);
+                for (int i = 0; i < PX; i += 4) { const Word16 w = *(const Word16*)&f.rowcell[ra * OBS_W + X0 + i]; ea[i] = w.a; ea[i + 1] = w.b; ea[i + 2] = w.c; ea[i + 3] = w.d; }
+#pragma unroll
+                for (int i = 0; i < PX; i++) {
+                    const uint32_t e = ea[i];
+                    if (NCLASS > 1) {
+                        const uint32_t cls = e >> 29 & 1u;
+                        if ((int32_t)e < 0 && (rf.meta >> (16u + cls) & 1u)) at[i] = (e & RC_ADDR_MASK) + (cls ? rf.sywa >> 16 : rf.sywa & 0xffffu);
+                    } else if ((int32_t)e < 0) at[i] = (e & RC_ADDR_MASK) + rf.sywa;
+                    flags |= e;
+                }
             }
-            uint32_t* out = (uint32_t*)(buf + 3 * ((it * 2 + (l >> 4)) * OBS_W + X0));
-            out[0] = byte_perm(color[0], color[1], 0x4210u);
-            out[1] = byte_perm(color[1], color[2], 0x5421u);
-            out[2] = byte_perm(color[2], color[3], 0x6542u);
+            uint32_t all = 0xffffffffu;
+#pragma unroll
+            for (int i = 0; i < PX; i++) { texel[i] = __ldg(atlas + at[i]); all &= texel[i]; }
+            // opaque-copy textures carry A = 255 in the atlas: ONE test covers the common case of all-opaque texels
+#ifdef PG2_HOSTSIM
+            g_dbg_quads++;
+            if (G::HAS_TILES && (rf.meta >> 8 & 255u) != (uint32_t)F::WINR) g_dbg_rb++;
+            if ((all >> 24) != 255u || (flags & RC_AMBIGUOUS) != 0u) g_dbg_quads_slow++;
+#endif
+            if ((all >> 24) != 255u || (flags & RC_AMBIGUOUS) != 0u) {
+                for (int i = 0; i < PX; i++)
+                    if ((flags & RC_AMBIGUOUS) != 0u || (texel[i] >> 24) != 255u) texel[i] = shade_base_slow<G>(f, atlas, X0 + i, Y);
+            }
+#pragma unroll
+            for (int i = 0; i < PX; i += 4) {
+                Word16 o; o.a = texel[i]; o.b = texel[i + 1]; o.c = texel[i + 2]; o.d = texel[i + 3];
+                *(Word16*)&buf[yl * OBS_W + X0 + i] = o;
+            }
         }
+    }
+}
+
+template <class G, class F>
+PG2_DEV void raster_band_base(F& f, const uint32_t* __restrict__ atlas, int band, int lane, uint32_t* buf) {
+    if (f.wide != 0) {   // general ordered path for every pixel (never observed)
+        for (int it = 0; it < BAND_ROWS / 2; it++)
+            for (int l = lane; l < 32; l += WARP_LANES) {
+                const int yl = it * 2 + (l >> 4), X0 = (l & 15) * 4;
+#pragma unroll
+                for (int i = 0; i < 4; i++) buf[yl * OBS_W + X0 + i] = shade_base_ordered<G>(f, atlas, X0 + i, band * BAND_ROWS + yl);
+            }
+        return;
+    }
+    raster_band_fast<G>(f, atlas, band, lane, buf);
+}
+
+// x / 255 for two 16-bit lanes at once (each lane <= 65 534: exact, no carry between the lanes).
+PG2_DEV uint32_t div255x2(uint32_t v) { return ((v + 0x00010001u + ((v >> 8) & 0x00ff00ffu)) >> 8) & 0x00ff00ffu; }
+PG2_DEV uint32_t div255(uint32_t v) { return (v + 1u + (v >> 8)) >> 8; }
+
+// SRC-over of one texel with effective alpha a in [1, 254] onto an RGBA word: blend_texel's integer arithmetic
+// (premultiply by a, then dst * (255 - a) / 255), red and blue in one multiply.
+PG2_DEV uint32_t blend_word(uint32_t dst, uint32_t texel, uint32_t a) {
+    const uint32_t ia = 255u - a;
+    const uint32_t trb = div255x2((texel & 0x00ff00ffu) * a), tg = div255((texel >> 8 & 255u) * a);
+    const uint32_t drb = div255x2((dst & 0x00ff00ffu) * ia), dg = div255((dst >> 8 & 255u) * ia);
+    return (trb + drb) | (tg + dg) << 8;
 }
 
 // One post blit onto the rows [Y0, Y0 + 8) (the band buffer): lanes = an 8x4 patch of the destination rectangle.
 template <class F>
-PG2_DEV void draw_blit_band(F& f, const uint32_t* __restrict__ atlas, int k, int Y0, int lane, uint8_t* buf) {
+PG2_DEV void draw_blit_band(F& f, const uint32_t* __restrict__ atlas, int k, int Y0, int lane, uint32_t* buf) {
     const FastBlit fb = f.fpost[k];
     const BlitRot* rot = &f.post_rot[F::ROTATES ? k : 0];
     int x0 = fb.x0, y0 = fb.y0, x1 = fb.x0 + fb.w - 1, y1 = fb.y0 + fb.h - 1;
@@ -710,23 +902,30 @@ PG2_DEV void draw_blit_band(F& f, const uint32_t* __restrict__ atlas, int k, int
                 const int X = xb + (l & 7), Y = yb + (l >> 3);
                 uint32_t texel;
                 if (X <= x1 && Y <= y1 && fast_texel<F::ROTATES>(fb, rot, atlas, X, Y, &texel)) {
-                    const uint32_t a = layer_alpha(texel, blend, alpha_mod);
-                    uint8_t* px = buf + 3 * ((Y - Y0) * OBS_W + X);
-                    if (a == 255u) { px[0] = (uint8_t)texel; px[1] = (uint8_t)(texel >> 8); px[2] = (uint8_t)(texel >> 16); }
-                    else if (a != 0u) {
-                        uint32_t r = px[0], g = px[1], b = px[2];
-                        blend_texel(r, g, b, texel, blend, alpha_mod);
-                        px[0] = (uint8_t)r; px[1] = (uint8_t)g; px[2] = (uint8_t)b;
-                    }
+                    const uint32_t a = blend ? layer_alpha(texel, blend, alpha_mod) : 255u;   // an opaque-copy texture ignores the alpha mod
+                    uint32_t* px = buf + (Y - Y0) * OBS_W + X;
+                    if (a == 255u) *px = texel;
+                    else if (a != 0u) *px = blend_word(*px, texel, a);
                 }
             }
     __syncwarp();
 }
 
-// The finished band leaves the SM as one 1 536-byte TMA bulk store shared -> global (async proxy), issued by the warp
-// that drew it; the warp waits for the copy to have READ its band buffer right before it draws into the buffer again,
-// so the drain overlaps the ticket / descriptor work in between.
-PG2_DEV void band_store(uint8_t* __restrict__ dst, const uint8_t* buf, int lane) {
+// The finished band: RGBA -> packed RGB in place (a lane reads 4 pixels and writes 3 words per round; round j's output
+// [384 j, 384 j + 384) lies below every later round's input, and within a round all reads precede the writes), then ONE
+// 1 536-byte TMA bulk store shared -> global (async proxy), issued by the warp that drew the band; the warp waits for the
+// copy to have READ its band buffer right before it draws into the buffer again, so the drain overlaps the ticket /
+// descriptor work in between.
+PG2_DEV void band_store(uint8_t* __restrict__ dst, uint32_t* buf, int lane) {
+    for (int j = 0; j < BAND_PX / 4 / 32; j++)
+        for (int l = lane; l < 32; l += WARP_LANES) {
+            const int g = j * 32 + l;
+            const Word16 w = ((const Word16*)buf)[g];
+            __syncwarp();
+            buf[3 * g] = byte_perm(w.a, w.b, 0x4210u);
+            buf[3 * g + 1] = byte_perm(w.b, w.c, 0x5421u);
+            buf[3 * g + 2] = byte_perm(w.c, w.d, 0x6542u);
+        }
 #ifdef PG2_HOSTSIM
     memcpy(dst, buf, BAND_BYTES);
 #else
@@ -745,8 +944,8 @@ PG2_DEV void band_store(uint8_t* __restrict__ dst, const uint8_t* buf, int lane)
 // cache_img != nullptr (G::STATIC_VIEW): the env's base image; f.reuse says whether to load it or to (draw and) store it.
 template <class G, class F>
 PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas, uint8_t* __restrict__ dst, uint8_t* __restrict__ cache_img = nullptr) {
-    const int lane = threadIdx.x % WARP_LANES;
-    uint8_t* buf = f.band_rgb[threadIdx.x / WARP_LANES % (RENDER_THREADS / 32)];
+    const int lane = threadIdx.x % WARP_LANES, warp = threadIdx.x / WARP_LANES % (RENDER_THREADS / 32);
+    uint32_t* buf = f.band_px[warp];
     const int npost = f.npost;
     for (;;) {
         int band = 0;
@@ -754,11 +953,10 @@ PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas, 
         band = warp_bcast(band);
         if (band >= NUM_BANDS) break;
         if (cache_img != nullptr && f.reuse) {
-            __syncwarp();
-            band_from_cache(buf, cache_img + band * BAND_BYTES, lane);
+            band_from_cache(f, warp, buf, cache_img + band * BAND_CACHE_BYTES, lane);
         } else {
             raster_band_base<G>(f, atlas, band, lane, buf);
-            if (cache_img != nullptr) { __syncwarp(); band_to_cache(buf, cache_img + band * BAND_BYTES, lane); }
+            if (cache_img != nullptr) { __syncwarp(); band_to_cache(buf, cache_img + band * BAND_CACHE_BYTES, lane); }
         }
         __syncwarp();
         for (int base = 0; base < npost; base += 32) {
@@ -789,7 +987,14 @@ PG2_DEV void frame_init_tiletex(F& f, const TexInfo* __restrict__ tex) {
         }
         f.tileword[t] = w;
     }
-    for (int k = threadIdx.x; k < 2; k += blockDim.x) f.rowmask[k][MAX_WIN] = 0u;   // the always-empty tile row
+    for (int k = threadIdx.x; k < OBS_W; k += blockDim.x) f.rowcell[F::WINR * OBS_W + k] = 0u;
+    for (int w = threadIdx.x; w < RENDER_THREADS / 32; w += blockDim.x) {
+        f.mbar_phase[w] = 0u;
+#ifndef PG2_HOSTSIM
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&f.mbar[w])) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+    }
     __syncthreads();
 }
 

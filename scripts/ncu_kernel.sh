@@ -7,5 +7,6 @@ for w in $WORK; do
   python scripts/ncu_raw.py $R.ncu-rep > ${R}_raw.txt 2>&1
   python scripts/ncu_lines.py $R.ncu-rep 70 > ${R}_lines.txt 2>&1
   python scripts/ncu_samples.py $R.ncu-rep 40 > ${R}_samples.txt 2>&1
-  rm -f $R.ncu-rep
+  python scripts/ncu_funcs.py $R.ncu-rep $n > ${R}_funcs.txt 2>&1
+  [ -z "$KEEP_REP" ] && rm -f $R.ncu-rep
 done

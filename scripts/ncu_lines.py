@@ -6,7 +6,7 @@ txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "c
 rows = list(csv.reader(io.StringIO(txt)))
 out = []; h = None; sect = 0; files = []
 for r in rows:
-    if r and r[0] == "File Name": files.append(r[1]); continue
+    if r and r[0] in ("File Name", "File Path"): files.append(r[1]); continue
     if r and r[0] == "Line No": h = r; sect += 1; continue
     if h and len(r) > 8 and r[0].isdigit():
         i = h.index("Instructions Executed"); s = h.index("# Samples")

@@ -89,6 +89,7 @@ static std::vector<uint8_t> g_sort_table;
 extern "C" {
 
 const char* hs_last_error() { return g_err.c_str(); }
+void hs_debug_counters(long* out) { out[0] = pg2::g_dbg_slow; out[1] = pg2::g_dbg_quads; out[2] = pg2::g_dbg_quads_slow; out[3] = pg2::g_dbg_rb; }
 
 void* hs_create(const char* game, int n, int seed, int max_ep, const char* assets) {
     std::string g = game;
