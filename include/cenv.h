@@ -15,11 +15,19 @@
  *                 "num_devices" (INT, default 1: devices device .. device + num_devices - 1 each own a
  *                 contiguous slice of the envs; env i is seeded seed + i whatever the device count),
  *                 "max_episode_steps" (INT, default 0 = never truncate),
- *                 "auto_reset" (INT, default 1 when num_envs > 1, else 0)
+ *                 "auto_reset" (INT, default 1 when num_envs > 1, else 0),
+ *                 "host_copy" (INT, default 1; 0: observations stay device-resident — cenv_step / cenv_reset return
+ *                 when the kernels have finished, without the device -> host copy of "screen"; rewards and flags are
+ *                 still copied)
  *   actions       key "action", INT, value_buffer_size == num_envs
  *   observations  key "screen", BYTE, num_envs * 12288 values (env-major, 64x64x3 RGB)
  *   step infos    (num_envs > 1 only) "reward" FLOAT[num_envs], "terminated" BYTE[num_envs],
- *                 "truncated" BYTE[num_envs]; the scalar step_data fields mirror env 0
+ *                 "truncated" BYTE[num_envs]; the scalar step_data fields mirror env 0;
+ *                 device-resident results (also reset infos): "screen_device", "reward_device", "terminated_device",
+ *                 "truncated_device", "stream" — INT[2 * num_devices], the (low, high) 32-bit halves of the CUDA device
+ *                 address of each device shard's buffer (uint8 [count * 12288] / float [count] / uint8 [count]) and of
+ *                 the cudaStream_t its kernels run on; the same addresses come from cenv_device_buffer(key, shard).
+ *                 Host result buffers are page-locked.
  * With num_envs == 1 and no extension option the behaviour is the reference's.
  */
 #ifndef PG2_CENV_H
@@ -115,6 +123,10 @@ CENV_API int32_t cenv_reset(cenv_option* options, int32_t options_size);
 CENV_API int32_t cenv_step(cenv_key_value* actions, int32_t actions_size);
 CENV_API int32_t cenv_render();
 CENV_API void cenv_close();
+
+/* Extension (not in the reference): CUDA device address of the result buffer `key` ("screen" | "reward" | "terminated" |
+ * "truncated" | "stream") of device shard `device_index`; NULL if unknown / not made. */
+CENV_API void* cenv_device_buffer(const char* key, int32_t device_index);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,12 @@ PG2_API int32_t pg2_step_device(pg2_engine* e, const int32_t* actions_device);
  * terminated / truncated: num_envs uint8. */
 PG2_API int32_t pg2_fetch(pg2_engine* e, uint8_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated);
 
+/* pg2_fetch without the wait: copies enqueued on the engine's stream, completed by pg2_sync (asynchronous only into
+ * page-locked memory). pg2_host_alloc / pg2_host_free: page-locked host memory for such buffers (NULL on failure). */
+PG2_API int32_t pg2_fetch_async(pg2_engine* e, uint8_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated);
+PG2_API void* pg2_host_alloc(size_t bytes);
+PG2_API void pg2_host_free(void* p);
+
 /* Depth-1 pipelined stepping for host-buffer callers: enqueues step t (H2D of its actions, the kernels, D2H of
  * its results into the given host buffers — pinned for true overlap — on a second stream) and returns when the
  * results of step t-1, written to the buffers passed to the PREVIOUS call, are complete. Alternate two sets of

@@ -7,8 +7,9 @@
 //   cenv_reset  optional "seed" option, reset(), render, copy observation   (coinrun.cpp:308-339)
 //   cenv_step   key "action" INT, step, render, copy observation            (coinrun.cpp:341-391)
 //   cenv_close  frees the library-owned buffers                             (coinrun.cpp:413-441)
-// Extension (documented in include/cenv.h): "num_envs", "device", "max_episode_steps",
-// "auto_reset" make-options; batched "action"/"screen" buffers; per-env results as step infos.
+// Extension (documented in include/cenv.h): "num_envs", "device", "num_devices", "max_episode_steps", "auto_reset",
+// "host_copy" make-options; batched "action"/"screen" buffers; per-env results and the DEVICE addresses of the
+// result buffers as step / reset infos (+ the exported getter cenv_device_buffer). Host result buffers are pinned.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -50,23 +51,53 @@ pg2_engine* g_engine = nullptr;   // == g_engines[0] (non-null <=> made)
 int g_num_envs = 1;
 int g_window_w = 512, g_window_h = 512;
 
+int g_host_copy = 1;              // make-option "host_copy": 0 = observations stay in HBM (read them through the device pointers)
+
 cenv_key_value g_observation;    // shared by reset_data and step_data, like the reference
 cenv_key_value g_obs_space, g_act_space;
-cenv_key_value g_infos[3];
+enum { INFO_REWARD, INFO_TERMINATED, INFO_TRUNCATED, INFO_SCREEN_DEV, INFO_REWARD_DEV, INFO_TERMINATED_DEV, INFO_TRUNCATED_DEV, INFO_STREAM, NUM_INFOS };
+cenv_key_value g_infos[NUM_INFOS];
 float g_box[2] = { 0.0f, 255.0f };
 int32_t g_nvec[1] = { kNumActions };
-std::vector<uint8_t> g_obs, g_term, g_trunc, g_frame;
-std::vector<float> g_reward;
+// host result buffers: page-locked (pg2_host_alloc), so the device -> host copies run at full PCIe speed and asynchronously
+uint8_t *g_obs = nullptr, *g_term = nullptr, *g_trunc = nullptr;
+float* g_reward = nullptr;
+std::vector<uint8_t> g_frame;
 std::vector<int32_t> g_actions, g_seeds;
+std::vector<int32_t> g_devptr[5];   // per info: (lo, hi) 32-bit halves of one address per device
 
+void free_host() {
+    pg2_host_free(g_obs); pg2_host_free(g_reward); pg2_host_free(g_term); pg2_host_free(g_trunc);
+    g_obs = g_term = g_trunc = nullptr; g_reward = nullptr;
+}
+
+// addresses of the device-resident results (they alternate between two buffer sets only in pg2_step_pipelined mode,
+// which this library does not use: constant for the lifetime of the environment)
+void publish_device_pointers() {
+    for (int k = 0; k < 5; k++) g_devptr[k].assign(2 * g_engines.size(), 0);
+    for (size_t d = 0; d < g_engines.size(); d++) {
+        const void* p[5] = { pg2_obs_device(g_engines[d]), pg2_reward_device(g_engines[d]), pg2_terminated_device(g_engines[d]),
+                             pg2_truncated_device(g_engines[d]), pg2_stream(g_engines[d]) };
+        for (int k = 0; k < 5; k++) {
+            const uint64_t a = (uint64_t)(uintptr_t)p[k];
+            g_devptr[k][2 * d] = (int32_t)(uint32_t)(a & 0xffffffffu);
+            g_devptr[k][2 * d + 1] = (int32_t)(uint32_t)(a >> 32);
+        }
+    }
+}
+
+// results of the last step / reset -> host buffers. Every device's copies are enqueued first (asynchronous, pinned
+// destination), then waited for: the transfers of different devices overlap.
 int fetch() {
     for (size_t d = 0; d < g_engines.size(); d++) {
         const size_t o = (size_t)g_first[d];
-        if (pg2_fetch(g_engines[d], g_obs.data() + o * kObsBytes, g_reward.data() + o, g_term.data() + o, g_trunc.data() + o)) {
+        if (pg2_fetch_async(g_engines[d], g_host_copy ? g_obs + o * kObsBytes : nullptr, g_reward + o, g_term + o, g_trunc + o)) {
             fprintf(stderr, "[procgen2_b200] %s\n", pg2_last_error());
             return 1;
         }
     }
+    for (size_t d = 0; d < g_engines.size(); d++)
+        if (pg2_sync(g_engines[d])) { fprintf(stderr, "[procgen2_b200] %s\n", pg2_last_error()); return 1; }
     return 0;
 }
 
@@ -74,6 +105,7 @@ void destroy_all() {
     for (pg2_engine* e : g_engines) pg2_destroy(e);
     g_engines.clear(); g_first.clear(); g_count.clear();
     g_engine = nullptr;
+    free_host();
 }
 
 }  // namespace
@@ -86,7 +118,7 @@ int32_t cenv_make(const char* /*render_mode*/, cenv_option* options, int32_t opt
     destroy_all();
     unsigned int seed = (unsigned int)time(nullptr);     // coinrun.cpp:130
     int device = 0, num_devices = 1, max_episode_steps = 0, auto_reset = -1;
-    g_num_envs = 1;
+    g_num_envs = 1; g_host_copy = 1;
     for (int i = 0; i < options_size; i++) {
         std::string name(options[i].name);
         if (options[i].value_type != CENV_VALUE_TYPE_INT) continue;
@@ -99,6 +131,7 @@ int32_t cenv_make(const char* /*render_mode*/, cenv_option* options, int32_t opt
         else if (name == "num_devices") num_devices = v;
         else if (name == "max_episode_steps") max_episode_steps = v;
         else if (name == "auto_reset") auto_reset = v;
+        else if (name == "host_copy") g_host_copy = v != 0;
     }
     if (g_num_envs < 1 || (long long)g_num_envs * kObsBytes > 2147483647LL) {
         fprintf(stderr, "[procgen2_b200] num_envs out of range for an int32 cenv buffer size\n");
@@ -132,10 +165,18 @@ int32_t cenv_make(const char* /*render_mode*/, cenv_option* options, int32_t opt
     }
     g_engine = g_engines[0];
 
-    g_obs.assign((size_t)g_num_envs * kObsBytes, 0);
-    g_reward.assign(g_num_envs, 0.0f);
-    g_term.assign(g_num_envs, 0);
-    g_trunc.assign(g_num_envs, 0);
+    g_obs = (uint8_t*)pg2_host_alloc((size_t)g_num_envs * kObsBytes);
+    g_reward = (float*)pg2_host_alloc(sizeof(float) * (size_t)g_num_envs);
+    g_term = (uint8_t*)pg2_host_alloc((size_t)g_num_envs);
+    g_trunc = (uint8_t*)pg2_host_alloc((size_t)g_num_envs);
+    if (!g_obs || !g_reward || !g_term || !g_trunc) {
+        fprintf(stderr, "[procgen2_b200] cenv_make: cannot allocate the pinned host buffers: %s\n", pg2_last_error());
+        destroy_all();
+        return 1;
+    }
+    memset(g_obs, 0, (size_t)g_num_envs * kObsBytes); memset(g_reward, 0, sizeof(float) * (size_t)g_num_envs);
+    memset(g_term, 0, (size_t)g_num_envs); memset(g_trunc, 0, (size_t)g_num_envs);
+    publish_device_pointers();
     g_actions.assign(g_num_envs, 0);
     g_seeds.assign(g_num_envs, 0);
     g_frame.assign((size_t)g_window_w * g_window_h * 3, 0);
@@ -150,26 +191,34 @@ int32_t cenv_make(const char* /*render_mode*/, cenv_option* options, int32_t opt
     make_data.action_spaces = &g_act_space;
 
     g_observation = { "screen", CENV_VALUE_TYPE_BYTE, g_num_envs * kObsBytes, {} };
-    g_observation.value_buffer.b = g_obs.data();
+    g_observation.value_buffer.b = g_obs;
 
     reset_data.observations_size = 1;
     reset_data.observations = &g_observation;
-    reset_data.infos_size = 0;
-    reset_data.infos = nullptr;
 
     step_data.observations_size = 1;
     step_data.observations = &g_observation;
     step_data.reward.f = 0.0f;
     step_data.terminated = false;
     step_data.truncated = false;
-    g_infos[0] = { "reward", CENV_VALUE_TYPE_FLOAT, g_num_envs, {} };
-    g_infos[0].value_buffer.f = g_reward.data();
-    g_infos[1] = { "terminated", CENV_VALUE_TYPE_BYTE, g_num_envs, {} };
-    g_infos[1].value_buffer.b = g_term.data();
-    g_infos[2] = { "truncated", CENV_VALUE_TYPE_BYTE, g_num_envs, {} };
-    g_infos[2].value_buffer.b = g_trunc.data();
-    step_data.infos_size = g_num_envs > 1 ? 3 : 0;
-    step_data.infos = g_num_envs > 1 ? g_infos : nullptr;
+    g_infos[INFO_REWARD] = { "reward", CENV_VALUE_TYPE_FLOAT, g_num_envs, {} };
+    g_infos[INFO_REWARD].value_buffer.f = g_reward;
+    g_infos[INFO_TERMINATED] = { "terminated", CENV_VALUE_TYPE_BYTE, g_num_envs, {} };
+    g_infos[INFO_TERMINATED].value_buffer.b = g_term;
+    g_infos[INFO_TRUNCATED] = { "truncated", CENV_VALUE_TYPE_BYTE, g_num_envs, {} };
+    g_infos[INFO_TRUNCATED].value_buffer.b = g_trunc;
+    static const char* const dev_keys[5] = { "screen_device", "reward_device", "terminated_device", "truncated_device", "stream" };
+    for (int k = 0; k < 5; k++) {
+        g_infos[INFO_SCREEN_DEV + k] = { dev_keys[k], CENV_VALUE_TYPE_INT, (int32_t)g_devptr[k].size(), {} };
+        g_infos[INFO_SCREEN_DEV + k].value_buffer.i = g_devptr[k].data();
+    }
+    // the reference's single environment reports no infos (coinrun.cpp:200-202); the batched / device-resident
+    // extension adds the per-env results and the device addresses
+    const bool extended = g_num_envs > 1 || !g_host_copy;
+    step_data.infos_size = extended ? NUM_INFOS : 0;
+    step_data.infos = extended ? g_infos : nullptr;
+    reset_data.infos_size = extended ? 5 : 0;
+    reset_data.infos = extended ? g_infos + INFO_SCREEN_DEV : nullptr;
 
     render_data.value_type = CENV_VALUE_TYPE_BYTE;
     render_data.value_buffer_width = g_window_w;
@@ -240,7 +289,22 @@ int32_t cenv_render() {
 
 void cenv_close() {
     destroy_all();
-    g_obs.clear(); g_frame.clear();
+    g_frame.clear();
+}
+
+// Device address of a result buffer of device shard `device_index` (0 .. num_devices - 1): key = "screen" (uint8
+// [count * 12288]), "reward" (float [count]), "terminated" / "truncated" (uint8 [count]) or "stream" (the cudaStream_t the
+// shard's kernels run on). The same addresses are published as the INT-pair infos "<key>_device". NULL if unknown.
+void* cenv_device_buffer(const char* key, int32_t device_index) {
+    if (!g_engine || !key || device_index < 0 || (size_t)device_index >= g_engines.size()) return nullptr;
+    pg2_engine* e = g_engines[device_index];
+    std::string k(key);
+    if (k == "screen") return pg2_obs_device(e);
+    if (k == "reward") return pg2_reward_device(e);
+    if (k == "terminated") return pg2_terminated_device(e);
+    if (k == "truncated") return pg2_truncated_device(e);
+    if (k == "stream") return pg2_stream(e);
+    return nullptr;
 }
 
 }  // extern "C"

@@ -65,23 +65,114 @@ __global__ void k_seed(CommonState c, int N, uint32_t base_seed, const int32_t* 
     seed_body(c, env, seeds ? (uint32_t)seeds[env] : base_seed + (uint32_t)env, init_persistent != 0);
 }
 
-// Device counters (int[4]): [0], [1] = length of the reset list, indexed by step parity (k_step of step t appends to
-// [t & 1] and zeroes the other one, which the previous step has consumed); [2] = frame ticket of the main render,
-// [3] = frame ticket of the tail render (both zeroed by k_step / before a full reset).
+// Level prefetch (G::PREFETCH_LEVELS): the NEXT level of every env is generated one episode ahead into a shadow copy of the
+// state (k_reset on the shadow state, asynchronous, second stream). When an env finishes, the warp that stepped it copies the
+// shadow's reset-written fields over the live ones right in k_step's tail (swap_env) and the env goes onto the generator's
+// list, which prepares the level after that. Field table: one entry per copied SoA field.
+struct SwapField { char* live; const char* shadow; int esz, per_env, env_major; };
+constexpr int MAX_SWAP_FIELDS = 64;
+struct SwapTable { SwapField f[MAX_SWAP_FIELDS]; int n; };
+struct SwapArgs {
+    SwapTable table;          // table.n == 0: no level prefetch
+    CommonState shadow_c;
+    const int* gen_done;      // [N] levels delivered by the generator (beyond the first)
+    int* used;                // [N] levels taken
+};
+
+// One warp, one finished env: wait until the generator has delivered the level this env is about to take (ready <=>
+// gen_done >= used; almost always true on arrival — the generator had a whole episode; the poll is bounded so that a logic
+// error can never hang the GPU: fault bit 4 instead), then copy the fields.
+__device__ __noinline__ void swap_env(const SwapArgs& a, const CommonState& live_c, int env, int N, int lane) {
+    if (lane == 0) {
+        const int need = a.used[env];
+        const volatile int* g = a.gen_done + env;
+        int spins = 0;
+        while (*g < need && spins < (1 << 18)) { __nanosleep(200); spins++; }
+        if (*g < need) live_c.fault[env] |= 4;
+        __threadfence();
+    }
+    __syncwarp();
+    // Loads are issued in batches before their stores (the compiler cannot prove that a store does not alias the next load,
+    // which would serialise one memory round trip per element): env-major fields (tile map, MT19937 words) 8 elements per
+    // lane at a time, slot-major fields (<= 32 elements each, usually 1) four fields at a time.
+    for (int i = 0; i < a.table.n; i++) {
+        const SwapField f = a.table.f[i];
+        if (!f.env_major) continue;
+        const size_t off = (size_t)env * f.per_env * f.esz;
+        const int bytes = f.per_env * f.esz;
+        if (((off | (size_t)bytes) & 3) == 0) {
+            uint32_t* dst = (uint32_t*)(f.live + off);
+            const uint32_t* src = (const uint32_t*)(f.shadow + off);
+            for (int b0 = 0; b0 < bytes / 4; b0 += 256) {
+                uint32_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const int idx = b0 + k * 32 + lane; v[k] = idx < bytes / 4 ? src[idx] : 0u; }
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const int idx = b0 + k * 32 + lane; if (idx < bytes / 4) dst[idx] = v[k]; }
+            }
+        } else {
+            for (int b0 = 0; b0 < bytes; b0 += 256) {
+                uint8_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const int idx = b0 + k * 32 + lane; v[k] = idx < bytes ? (uint8_t)f.shadow[off + idx] : (uint8_t)0; }
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const int idx = b0 + k * 32 + lane; if (idx < bytes) f.live[off + idx] = (char)v[k]; }
+            }
+        }
+    }
+    for (int i0 = 0; i0 < a.table.n; i0 += 4) {
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            v[k] = 0u;
+            if (i0 + k >= a.table.n) continue;
+            const SwapField f = a.table.f[i0 + k];
+            if (f.env_major || lane >= f.per_env || f.per_env > 32) continue;
+            const size_t off = ((size_t)lane * N + env) * f.esz;
+            v[k] = f.esz == 4 ? *(const uint32_t*)(f.shadow + off) : f.esz == 1 ? (uint32_t)(uint8_t)f.shadow[off] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k >= a.table.n) continue;
+            const SwapField f = a.table.f[i0 + k];
+            if (f.env_major) continue;
+            if (f.per_env <= 32 && (f.esz == 4 || f.esz == 1)) {
+                if (lane < f.per_env) {
+                    const size_t off = ((size_t)lane * N + env) * f.esz;
+                    if (f.esz == 4) *(uint32_t*)(f.live + off) = v[k]; else f.live[off] = (char)v[k];
+                }
+            } else {   // long pools / odd element sizes: element j at [j * N + env]
+                for (int j = lane; j < f.per_env; j += 32) {
+                    const size_t off = ((size_t)j * N + env) * f.esz;
+                    for (int bb = 0; bb < f.esz; bb++) f.live[off + bb] = f.shadow[off + bb];
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {   // what reset_body does besides the level
+        a.used[env] += 1;   // read by this env's next swap only
+        live_c.ep_steps[env] = 0; live_c.view_valid[env] = 0;
+        live_c.fault[env] |= a.shadow_c.fault[env];
+    }
+}
+
+// Finished envs are appended to `list` (ballot + one atomic per warp on *count) and flagged in `pending` (an overlapped
+// render skips them). The kernel also zeroes *zero_a / zero_b[0..1]: the list counter the NEXT step appends to (that step's
+// consumer of the old value has finished by stream order) and the render's frame tickets.
 //
 // `epw` = environments per warp (power of two, 1..32): lanes [0, epw) of every warp own one environment each.
 // Lane-aware games use epw = 1 (a whole warp per environment, per-entity loops strided over the lanes); the others
-// pack several environments into a warp once the batch is large. Finished envs are appended to the reset list
-// (ballot + one atomic per warp) and flagged in `pending` (the overlapped render skips them).
+// pack several environments into a warp once the batch is large.
 template <class G>
 __global__ void __launch_bounds__(128) k_step(typename G::State s, CommonState c, const int32_t* __restrict__ actions,
                                               float* __restrict__ reward, uint8_t* __restrict__ terminated,
-                                              uint8_t* __restrict__ truncated, int* __restrict__ reset_list,
-                                              uint8_t* __restrict__ pending, int* __restrict__ counters, int parity,
-                                              int N, int max_episode_steps, int auto_reset, int epw) {
+                                              uint8_t* __restrict__ truncated, int* __restrict__ list, int* __restrict__ count,
+                                              uint8_t* __restrict__ pending, int* __restrict__ zero_a, int* __restrict__ zero_b,
+                                              int N, int max_episode_steps, int auto_reset, int epw, const __grid_constant__ SwapArgs swap) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = gtid & 31;
-    if (gtid == 0) { counters[parity ^ 1] = 0; counters[2] = 0; counters[3] = 0; }
+    if (gtid == 0) { *zero_a = 0; zero_b[0] = 0; zero_b[1] = 0; }
     bool done = false;
     int env;
     if (epw == 1) {   // a whole warp per environment (warp-uniform branch)
@@ -100,9 +191,13 @@ __global__ void __launch_bounds__(128) k_step(typename G::State s, CommonState c
     unsigned m = __ballot_sync(0xffffffffu, done);
     if (m) {
         int base = 0;
-        if (lane == 0) base = atomicAdd(&counters[parity], __popc(m));
+        if (lane == 0) base = atomicAdd(count, __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (done) reset_list[base + __popc(m & ((1u << lane) - 1u))] = env;
+        if (done) list[base + __popc(m & ((1u << lane) - 1u))] = env;
+        if (swap.table.n > 0) {   // level prefetch: the finished envs take their next level now
+            __syncwarp();
+            for (unsigned mm = m; mm; mm &= mm - 1u) swap_env(swap, c, __shfl_sync(0xffffffffu, env, __ffs(mm) - 1), N, lane);
+        }
     }
 }
 
@@ -121,67 +216,10 @@ __global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::
     for (int w = blockIdx.x * RESET_WARPS_PER_CTA + warp_in_cta; w < count; w += total_warps) {
         int env = reset_list ? reset_list[w] : w;
         reset_body<G>(s, c, env, mt, arena, lane);
-        if (gen_done != nullptr) {   // level prefetch: publish "the next level of env exists" (k_swap_wait polls it)
+        if (gen_done != nullptr) {   // level prefetch: publish "the next level of env exists" (swap_env polls it)
             __threadfence();
             __syncwarp();
             if (lane == 0) atomicAdd(&gen_done[env], 1);
-        }
-    }
-}
-
-// Level prefetch (G::PREFETCH_LEVELS): the NEXT level of every env is generated one episode ahead into a shadow copy of the
-// state; when an env finishes, k_swap copies the shadow's reset-written fields over the live ones (one warp per finished
-// env) and hands the env to the asynchronous generator (k_reset on the shadow state, second stream), which prepares the
-// level after that. Field table: one entry per copied SoA field.
-struct SwapField { char* live; const char* shadow; int esz, per_env, env_major; };
-constexpr int MAX_SWAP_FIELDS = 64;
-struct SwapTable { SwapField f[MAX_SWAP_FIELDS]; int n; };
-
-// One thread per finished env: wait until the generator has delivered the level this env is about to take (gen_done counts
-// delivered levels beyond the first, used counts levels taken: ready <=> gen_done >= used). Almost always true on arrival —
-// the generator had a whole episode; the poll is bounded so that a logic error can never hang the GPU (fault bit 4 instead).
-__global__ void k_swap_wait(const int* __restrict__ list, const int* __restrict__ count, const int* gen_done, const int* __restrict__ used,
-                            CommonState live_c) {
-    const int n = *count;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const int env = list[k], need = used[env];
-        const volatile int* g = gen_done + env;
-        int spins = 0;
-        while (*g < need && spins < (1 << 18)) { __nanosleep(200); spins++; }
-        if (*g < need) live_c.fault[env] |= 4;
-        __threadfence();
-    }
-}
-
-__global__ void __launch_bounds__(128) k_swap(SwapTable t, CommonState live_c, CommonState shadow_c, const int* __restrict__ list,
-                                              const int* __restrict__ count, int* __restrict__ prep_list, int* __restrict__ prep_count, int N,
-                                              int* __restrict__ used) {
-    const int n = *count, lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *prep_count = n;
-    // one warp per (finished env, field): the copies are independent, so the swap costs a couple of memory round trips
-    for (int item = warp; item < n * t.n; item += nwarps) {
-        const int k = item / t.n, i = item - k * t.n;
-        const int env = list[k];
-        const SwapField f = t.f[i];
-        if (f.env_major) {   // per_env contiguous elements: copy as bytes / words
-            const size_t off = (size_t)env * f.per_env * f.esz;
-            const int bytes = f.per_env * f.esz;
-            if (((off | (size_t)bytes) & 3) == 0) for (int b = lane; b < bytes / 4; b += 32) ((uint32_t*)(f.live + off))[b] = ((const uint32_t*)(f.shadow + off))[b];
-            else for (int b = lane; b < bytes; b += 32) f.live[off + b] = f.shadow[off + b];
-        } else {             // element j at [j * N + env]
-            for (int j = lane; j < f.per_env; j += 32) {
-                const size_t off = ((size_t)j * N + env) * f.esz;
-                if (f.esz == 4) *(uint32_t*)(f.live + off) = *(const uint32_t*)(f.shadow + off);
-                else if (f.esz == 1) f.live[off] = f.shadow[off];
-                else for (int b = 0; b < f.esz; b++) f.live[off + b] = f.shadow[off + b];
-            }
-        }
-        if (i == 0 && lane == 0) {   // once per env: the list entry for the generator + what reset_body does besides the level
-            prep_list[k] = env;
-            used[env] += 1;                                   // read by the next step's k_swap_wait only
-            live_c.ep_steps[env] = 0; live_c.view_valid[env] = 0;
-            live_c.fault[env] |= shadow_c.fault[env];
         }
     }
 }
@@ -265,7 +303,8 @@ struct EngineBase {
     virtual size_t state_bytes_per_env() = 0;
     virtual size_t state_alloc_bytes() = 0;     // bytes of state_mem
     virtual uint32_t game_tag() = 0;
-    virtual int init_shadow() = 0;              // level prefetch: regenerate every env's next level (after state was written)
+    virtual int init_shadow() = 0;
+    virtual int destroy_graphs() = 0;           // the captured step graphs (they hold pointers into this engine's buffers)              // level prefetch: regenerate every env's next level (after state was written)
 
     int device = 0, N = 0, max_episode_steps = 0, auto_reset = 1;
     uint32_t base_seed = 0;
@@ -315,10 +354,10 @@ struct EngineBase {
     int* prep_list = nullptr;        // [PREP_SLOTS][N]: private copy of a step's reset list for the asynchronous generator
     int* prep_count = nullptr;       // [PREP_SLOTS]
     int* gen_done = nullptr;         // [N] levels delivered by the generator (beyond the first)
-    int* gen_used = nullptr;         // [N] levels taken by k_swap
+    int* gen_used = nullptr;         // [N] levels taken (swap_env)
     int prep_slot = 0;
     cudaStream_t prep_streams[4] = { nullptr, nullptr, nullptr, nullptr };   // one per slot: the launches overlap
-    cudaEvent_t ev_swapped = nullptr, ev_prepared[PREP_SLOTS] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev_prepared[PREP_SLOTS] = { nullptr, nullptr, nullptr, nullptr };
     SwapTable swap_table;
     uint8_t* view_cache = nullptr;   // G::STATIC_VIEW: VIEW_CACHE_BYTES per env (k_render keeps the view of an episode)
     // optional per-kernel timing
@@ -369,11 +408,12 @@ struct EngineBase {
         cudaFree(state_mem); cudaFree(common_mem); cudaFree(obs); cudaFree(reward); cudaFree(terminated);
         cudaFree(truncated); cudaFree(actions); cudaFree(seeds_dev); cudaFree(reset_list); cudaFree(reset_count); cudaFree(view_cache);
         for (int j = 0; j < PREP_SLOTS; j++) if (prep_streams[j]) { cudaStreamSynchronize(prep_streams[j]); cudaStreamDestroy(prep_streams[j]); }
-        if (ev_swapped) cudaEventDestroy(ev_swapped);
         for (int j = 0; j < PREP_SLOTS; j++) if (ev_prepared[j]) cudaEventDestroy(ev_prepared[j]);
         cudaFree(shadow_state_mem); cudaFree(shadow_common_mem); cudaFree(prep_list); cudaFree(prep_count); cudaFree(gen_done); cudaFree(gen_used);
         cudaFree(texinfo); cudaFree(atlas); cudaFree(pending);
-        if (reset_stream) { cudaStreamSynchronize(reset_stream); cudaStreamDestroy(reset_stream); cudaEventDestroy(ev_stepped); cudaEventDestroy(ev_reset_done); }
+        if (reset_stream) { cudaStreamSynchronize(reset_stream); cudaStreamDestroy(reset_stream); cudaEventDestroy(ev_reset_done); }
+        if (ev_stepped) cudaEventDestroy(ev_stepped);
+        destroy_graphs();
         if (actions_pinned) cudaFreeHost(actions_pinned);
         if (pipelined) {
             // slot 0 aliases the primary buffers (freed above)
@@ -444,15 +484,17 @@ struct Engine : EngineBase {
                 PG2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
                 for (int j = 0; j < PREP_SLOTS; j++) PG2_CUDA(cudaStreamCreateWithPriority(&prep_streams[j], cudaStreamNonBlocking, hi));
             }
-            PG2_CUDA(cudaEventCreateWithFlags(&ev_swapped, cudaEventDisableTiming));
             for (int j = 0; j < PREP_SLOTS; j++) PG2_CUDA(cudaEventCreateWithFlags(&ev_prepared[j], cudaEventDisableTiming));
             if (build_swap_table()) return 1;
         }
+        memset(&swap_args, 0, sizeof(swap_args));
+        if (prefetch) { swap_args.table = swap_table; swap_args.shadow_c = shadow_common; swap_args.gen_done = gen_done; swap_args.used = gen_used; }
+        PG2_CUDA(cudaEventCreateWithFlags(&ev_stepped, cudaEventDisableTiming));
+        if (const char* o = getenv("PG2_GRAPH")) use_graph = atoi(o) != 0;
         overlap_reset = G::SLOW_RESET && auto_reset && !prefetch;
         if (const char* o = getenv("PG2_OVERLAP_RESET")) overlap_reset = atoi(o) != 0 && auto_reset && !prefetch;
         if (overlap_reset) {
             PG2_CUDA(cudaStreamCreateWithFlags(&reset_stream, cudaStreamNonBlocking));
-            PG2_CUDA(cudaEventCreateWithFlags(&ev_stepped, cudaEventDisableTiming));
             PG2_CUDA(cudaEventCreateWithFlags(&ev_reset_done, cudaEventDisableTiming));
         }
         PG2_CUDA(cudaMallocHost(&actions_pinned, sizeof(int32_t) * N));
@@ -484,7 +526,7 @@ struct Engine : EngineBase {
         return 0;
     }
 
-    // Fields k_swap copies from the shadow state: every field of the game state and mt / mti / sprites_valid (+ the camera
+    // Fields swap_env copies from the shadow state: every field of the game state and mt / mti / sprites_valid (+ the camera
     // where reset() sets it), except the ones the game lists as persisting across reset() (G::reset_keeps()).
     int build_swap_table() {
         swap_table.n = 0;
@@ -521,6 +563,7 @@ struct Engine : EngineBase {
         PG2_CUDA(cudaMemcpyAsync(shadow_common_mem, common_mem, CommonState::bytes(N), cudaMemcpyDeviceToDevice, stream));
         k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(shadow_st, shadow_common, nullptr, nullptr, N);
         launches++;
+        PG2_CUDA(cudaMemsetAsync(prep_count, 0, PREP_SLOTS * sizeof(int), stream));
         PG2_CUDA(cudaMemsetAsync(gen_done, 0, sizeof(int) * (size_t)N, stream));   // ready <=> gen_done >= used
         PG2_CUDA(cudaMemsetAsync(gen_used, 0, sizeof(int) * (size_t)N, stream));
         for (int j = 0; j < PREP_SLOTS; j++) PG2_CUDA(cudaEventRecord(ev_prepared[j], stream));
@@ -569,43 +612,83 @@ struct Engine : EngineBase {
         return 0;
     }
 
-    // One step = k_step -> k_reset (finished envs) -> k_render. With overlap_reset the level generation of the few
-    // finished envs runs on a second stream WHILE the main stream renders all other envs; a short tail render
-    // of the reset envs follows. Timing marks: [0] k_step, [1] exposed reset (+ tail render), [2] (main) render.
+    // ---- one step -------------------------------------------------------------------------------------------------
+    // k_step -> k_reset (finished envs) -> k_render on the main stream. Level-prefetch games have no k_reset on that
+    // path: finished envs take their pre-generated level inside k_step (swap_env), and the level after that is generated on
+    // a second stream while the following steps run — up to PREP_SLOTS generator launches in flight, each with a private
+    // list (k_step appends to the slot's list directly); an env that finishes again before its next level exists
+    // (episodes shorter than a generation) is waited for individually.
+    // The main-stream sequence is captured ONCE per (step parity, list slot, output buffer set) into a CUDA graph and
+    // replayed: one launch per step; only the pointer to the caller's actions is re-pointed (PG2_GRAPH=0: eager launches).
+    // With overlap_reset (PG2_PREFETCH=0 on the slow-generator games) the level generation of the few finished envs runs
+    // WHILE a second stream renders all other envs, a short tail render of the reset envs follows (eager only).
+    // Timing marks (pg2_profile, eager): [0] k_step, [1] exposed reset (+ tail render), [2] (main) render.
+    SwapArgs swap_args;             // table.n == 0 when the engine does not prefetch levels
+    const int32_t* ka_actions = nullptr;
+    int *ka_list = nullptr, *ka_count = nullptr, *ka_zero_a = nullptr, *ka_zero_b = nullptr;
+    void* step_kargs[16];
+    struct StepGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; cudaGraphNode_t step_node = nullptr; const int32_t* actions = nullptr; uint8_t* obs = nullptr; };
+    StepGraph graphs[2 * PREP_SLOTS];
+    bool use_graph = true;
+
+    void bind_step_args(const int32_t* actions_dev, int slot) {
+        ka_actions = actions_dev;
+        if (prefetch) {
+            ka_list = prep_list + (size_t)slot * N; ka_count = prep_count + slot; ka_zero_a = prep_count + (slot + 1) % PREP_SLOTS;
+        } else {
+            ka_list = reset_list; ka_count = reset_count + parity; ka_zero_a = reset_count + (parity ^ 1);
+        }
+        ka_zero_b = reset_count + 2;
+        void* v[16] = { &st, &common, &ka_actions, &reward, &terminated, &truncated, &ka_list, &ka_count, &pending, &ka_zero_a, &ka_zero_b,
+                        &N, &max_episode_steps, &auto_reset, &step_epw, &swap_args };
+        memcpy(step_kargs, v, sizeof(v));
+    }
+    cudaKernelNodeParams step_node_params() {
+        cudaKernelNodeParams p{};
+        p.func = (void*)k_step<G>;
+        p.gridDim = dim3(step_grid()); p.blockDim = dim3(128); p.sharedMemBytes = 0;
+        p.kernelParams = step_kargs; p.extra = nullptr;
+        return p;
+    }
+    // the main-stream kernels of one step (eager or under stream capture)
+    int enqueue_main(bool prof) {
+        if (prof) prof_mark();
+        PG2_CUDA(cudaLaunchKernel((const void*)k_step<G>, dim3(step_grid()), dim3(128), step_kargs, 0, stream));
+        launches++;
+        if (prof) prof_mark();
+        if (!prefetch) {
+            k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count + parity, N);
+            launches++;
+        }
+        if (prof) prof_mark();
+        launch_render(0, reset_count + 2, stream);
+        if (prof) prof_mark();
+        return 0;
+    }
+    int destroy_graphs() override {
+        for (auto& g : graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph); g = StepGraph(); }
+        return 0;
+    }
+
     int step_device(const int32_t* actions_dev) override {
         parity ^= 1;
         const bool prof = profiling;
         if (prof && prof_events.size() >= 4096) prof_collect();
-        if (prof) prof_mark();
-        k_step<G><<<step_grid(), 128, 0, stream>>>(st, common, actions_dev, reward, terminated, truncated, reset_list, pending,
-                                                     reset_count, parity, N, max_episode_steps, auto_reset, step_epw);
-        launches++;
-        if (prof) prof_mark();
+        const int slot = prep_slot;
         if (prefetch) {
-            // finished envs take the level that was generated ahead of time (k_swap: a field-wise copy), every env is
-            // rendered, and the level after that is generated on the second stream while the following steps run: up to
-            // PREP_SLOTS generator launches are in flight, each with a private copy of its step's reset list; an env that
-            // finishes again before its next level exists (episodes shorter than a generation) is waited for individually
-            const int slot = prep_slot;
             prep_slot = (prep_slot + 1) % PREP_SLOTS;
-            PG2_CUDA(cudaStreamWaitEvent(stream, ev_prepared[slot], 0));   // the launch that last used this slot's list is done
-            int* pl = prep_list + (size_t)slot * N;
-            int* pc = prep_count + slot;
-            k_swap_wait<<<num_sms, 128, 0, stream>>>(reset_list, reset_count + parity, gen_done, gen_used, common);
-            k_swap<<<num_sms * 8, 128, 0, stream>>>(swap_table, common, shadow_common, reset_list, reset_count + parity, pl, pc, N, gen_used);
-            launches += 2;
-            PG2_CUDA(cudaEventRecord(ev_swapped, stream));
-            if (prof) prof_mark();
-            // generator first (high-priority stream), then the render: both become runnable when k_swap ends
-            PG2_CUDA(cudaStreamWaitEvent(prep_streams[slot], ev_swapped, 0));
-            k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), prep_streams[slot]>>>(shadow_st, shadow_common, pl, pc, N, gen_done);
-            launches++;
-            PG2_CUDA(cudaEventRecord(ev_prepared[slot], prep_streams[slot]));
-            launch_render(0, reset_count + 2, stream);
-            if (prof) prof_mark();
-        } else if (overlap_reset) {
+            // the generator launches that last read this slot's list / the next slot's counter are done
+            PG2_CUDA(cudaStreamWaitEvent(stream, ev_prepared[slot], 0));
+            PG2_CUDA(cudaStreamWaitEvent(stream, ev_prepared[(slot + 1) % PREP_SLOTS], 0));
+        }
+        bind_step_args(actions_dev, slot);
+        if (overlap_reset) {
             // k_reset stays on the main stream (first in line after k_step, so its few long-running CTAs get their
             // shared memory before the render fills the SMs); the render of all OTHER envs runs on the second stream
+            if (prof) prof_mark();
+            PG2_CUDA(cudaLaunchKernel((const void*)k_step<G>, dim3(step_grid()), dim3(128), step_kargs, 0, stream));
+            launches++;
+            if (prof) prof_mark();
             PG2_CUDA(cudaEventRecord(ev_stepped, stream));
             PG2_CUDA(cudaStreamWaitEvent(reset_stream, ev_stepped, 0));
             k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count + parity, N);
@@ -618,12 +701,48 @@ struct Engine : EngineBase {
             launch_render(2, reset_count + 3, stream);
             launches++;
             if (prof) prof_mark();
+        } else if (prof || !use_graph) {
+            if (enqueue_main(prof)) return 1;
         } else {
-            k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), stream>>>(st, common, reset_list, reset_count + parity, N);
+            StepGraph& g = graphs[parity | slot << 1];
+            if (g.exec && g.obs != obs) { cudaGraphExecDestroy(g.exec); cudaGraphDestroy(g.graph); g = StepGraph(); }   // the output buffers moved (pipelined stepping started)
+            if (!g.exec) {
+                cudaGraph_t graph = nullptr;
+                const int64_t launches0 = launches;
+                PG2_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                const int rc = enqueue_main(false);
+                const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+                launches = launches0;
+                if (rc || ce != cudaSuccess || !graph) return fail(std::string("step graph capture failed: ") + cudaGetErrorString(ce));
+                size_t nn = 0;
+                PG2_CUDA(cudaGraphGetNodes(graph, nullptr, &nn));
+                std::vector<cudaGraphNode_t> nodes(nn);
+                PG2_CUDA(cudaGraphGetNodes(graph, nodes.data(), &nn));
+                for (auto node : nodes) {
+                    cudaGraphNodeType ty;
+                    cudaKernelNodeParams kp{};
+                    if (cudaGraphNodeGetType(node, &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel &&
+                        cudaGraphKernelNodeGetParams(node, &kp) == cudaSuccess && kp.func == (void*)k_step<G>) g.step_node = node;
+                }
+                if (!g.step_node) { cudaGraphDestroy(graph); return fail("step graph: k_step node not found"); }
+                PG2_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+                g.graph = graph;   // kept: the node handle used to re-point `actions` belongs to it
+                g.actions = actions_dev; g.obs = obs;
+            } else if (g.actions != actions_dev) {
+                cudaKernelNodeParams kp = step_node_params();
+                PG2_CUDA(cudaGraphExecKernelNodeSetParams(g.exec, g.step_node, &kp));
+                g.actions = actions_dev;
+            }
+            PG2_CUDA(cudaGraphLaunch(g.exec, stream));
+            launches += prefetch ? 2 : 3;
+        }
+        if (prefetch) {
+            // the level after the one just taken: generated on the slot's own (high-priority) stream from here on
+            PG2_CUDA(cudaEventRecord(ev_stepped, stream));
+            PG2_CUDA(cudaStreamWaitEvent(prep_streams[slot], ev_stepped, 0));
+            k_reset<G><<<reset_grid(N), 32 * RESET_WARPS_PER_CTA, reset_smem(), prep_streams[slot]>>>(shadow_st, shadow_common, ka_list, ka_count, N, gen_done);
             launches++;
-            if (prof) prof_mark();
-            launch_render(0, reset_count + 2, stream);
-            if (prof) prof_mark();
+            PG2_CUDA(cudaEventRecord(ev_prepared[slot], prep_streams[slot]));
         }
         PG2_CUDA(cudaGetLastError());
         return 0;
@@ -708,6 +827,26 @@ int32_t pg2_fetch(pg2_engine* e, uint8_t* obs, float* reward, uint8_t* terminate
     PG2_CUDA(cudaStreamSynchronize(b->stream));
     return 0;
 }
+
+// pg2_fetch without the wait: the copies are enqueued on the engine's stream (truly asynchronous only into page-locked
+// memory, pg2_host_alloc); pg2_sync completes them.
+int32_t pg2_fetch_async(pg2_engine* e, uint8_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated) {
+    EngineBase* b = e->impl.get();
+    PG2_ON_DEVICE(b->device);
+    if (obs) PG2_CUDA(cudaMemcpyAsync(obs, b->obs, (size_t)b->N * OBS_BYTES, cudaMemcpyDeviceToHost, b->stream));
+    if (reward) PG2_CUDA(cudaMemcpyAsync(reward, b->reward, sizeof(float) * b->N, cudaMemcpyDeviceToHost, b->stream));
+    if (terminated) PG2_CUDA(cudaMemcpyAsync(terminated, b->terminated, b->N, cudaMemcpyDeviceToHost, b->stream));
+    if (truncated) PG2_CUDA(cudaMemcpyAsync(truncated, b->truncated, b->N, cudaMemcpyDeviceToHost, b->stream));
+    return 0;
+}
+
+// Page-locked host memory for result / action buffers (cudaHostAlloc, portable across devices); NULL on failure.
+void* pg2_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { g_error = "pg2_host_alloc: cudaHostAlloc failed"; cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pg2_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // Depth-1 pipelined stepping: enqueue step t (H2D of its actions, the three kernels, D2H of its results into the
 // given host buffers on a second stream) and return once the results of step t-1 — written to the buffers passed

@@ -224,3 +224,35 @@ def test_gpu_level_generation_many_seeds(game, oracle_available):
                                               err_msg="%s reset frame %d" % (game, rnd))
         for r in refs:
             r.close()
+
+
+# ---- (e) the captured step graph ----------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("game", ["coinrun", "bossfight", "maze", "jumper"])
+def test_step_graph_equals_eager(game, monkeypatch):
+    """One CUDA-graph launch per step (k_step node re-pointed at the caller's action buffer every step) against the eager
+    three-launch sequence (PG2_GRAPH=0), with short episodes so that resets / level swaps happen inside the graph, and with
+    the action tensor at a different device address every step."""
+    import torch
+    from procgen2_b200.engine import BatchedEnv
+    n, T = 160, 90
+    rs = np.random.RandomState(33)
+    acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
+    monkeypatch.setenv("PG2_GRAPH", "0")
+    a = BatchedEnv(game, n, seed=71, max_episode_steps=12)
+    monkeypatch.setenv("PG2_GRAPH", "1")
+    b = BatchedEnv(game, n, seed=71, max_episode_steps=12)
+    a.reset(); b.reset()
+    dev_acts = torch.from_numpy(acts).cuda()
+    for t in range(T):
+        a.step(acts[t])
+        b.step_torch(dev_acts[t])          # a view: a new device pointer each step
+        oa, ra, da, ta = a.fetch(truncated=True)
+        ob, rb, db, tb = b.fetch(truncated=True)
+        np.testing.assert_array_equal(oa, ob, err_msg="pixels, step %d" % t)
+        np.testing.assert_array_equal(ra, rb); np.testing.assert_array_equal(da, db); np.testing.assert_array_equal(ta, tb)
+    b.sync()
+    for name in ("mt", "mti", "fault"):
+        np.testing.assert_array_equal(a.read_field(name)[0], b.read_field(name)[0])
+    _assert_no_fault(b)
+    a.close(); b.close()
