@@ -45,6 +45,10 @@ typedef struct {
     const char* assets_path;     /* packed asset blob; NULL -> $PG2_ASSETS or <lib dir>/../data/assets.bin */
     int32_t auto_reset;          /* 1: finished envs run reset() on device inside the same step (observation =
                                     reset frame); 0: reference behaviour, the caller calls pg2_reset */
+    int32_t distribution_mode;   /* level-generator mode of the game's tilemap Config (games/<g>/tilemap.h: compile-time in
+                                    the reference): -1 = the reference's default, 0 easy, 1 hard, 2 memory / extreme.
+                                    Built: every game's default, + easy for coinrun (a no-op there, tilemap.cpp:148) and
+                                    climber (tilemap.cpp:118); anything else makes pg2_create fail */
 } pg2_config;
 
 PG2_API int32_t pg2_create(const pg2_config* cfg, pg2_engine** out);
@@ -58,6 +62,11 @@ PG2_API int32_t pg2_reset(pg2_engine* e, const int32_t* seeds);
  * the device inside the call) / DEVICE memory. Asynchronous: results stay in HBM. */
 PG2_API int32_t pg2_step(pg2_engine* e, const int32_t* actions_host);
 PG2_API int32_t pg2_step_device(pg2_engine* e, const int32_t* actions_device);
+
+/* cenv_render (games/coinrun/coinrun.cpp:393-411): environment `env`'s current scene drawn again at width x height with the
+ * window size as camera_size (render_game(false): camera_scale = game_zoom * width / 64), as width * height * 3 RGB
+ * bytes (row-major) in HOST memory. A cold path for the human viewer; synchronous. */
+PG2_API int32_t pg2_render_human(pg2_engine* e, int32_t env, int32_t width, int32_t height, uint8_t* out_rgb);
 
 /* Copy results of the last step/reset to host buffers (any pointer may be NULL) and wait.
  * obs: num_envs*12288 uint8 (64x64x3 RGB, row-major), reward: num_envs float,

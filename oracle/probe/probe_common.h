@@ -2,7 +2,8 @@
  * Read-only probes into the reference's process globals, linked into oracle/_ref/lib<Game>.so
  * next to the unmodified reference sources so that parity tests can compare more than pixels:
  * the MT19937 position/state (RNG stream parity), the complete tile map (level layout parity)
- * and a few floats of game state. Nothing here writes to the reference's state. */
+ * and a few floats of game state. Nothing here writes to the reference's state — except pg2o_set_easy_mode (coinrun,
+ * climber), which flips the generator's compile-time Config::easy_mode before cenv_make for the distribution-mode tests. */
 #pragma once
 #include <random>
 #include <sstream>

@@ -43,6 +43,11 @@ class StepData(ctypes.Structure):
                 ("infos_size", ctypes.c_int32), ("infos", ctypes.POINTER(KeyValue))]
 
 
+class RenderData(ctypes.Structure):
+    _fields_ = [("value_type", ctypes.c_int32), ("value_buffer_width", ctypes.c_int32), ("value_buffer_height", ctypes.c_int32),
+                ("value_buffer_channels", ctypes.c_int32), ("value_buffer", _Buffer)]
+
+
 class ResetData(ctypes.Structure):
     _fields_ = [("observations_size", ctypes.c_int32), ("observations", ctypes.POINTER(KeyValue)),
                 ("infos_size", ctypes.c_int32), ("infos", ctypes.POINTER(KeyValue))]
@@ -69,7 +74,7 @@ class RefEnv:
     """One reference environment (one private copy of lib<Game>.so)."""
     _count = 0
 
-    def __init__(self, game, seed):
+    def __init__(self, game, seed, width=None, height=None, easy_mode=None):
         d = _prepare()
         RefEnv._count += 1
         self.game = game
@@ -79,8 +84,14 @@ class RefEnv:
         self.lib.cenv_make.argtypes = [ctypes.c_char_p, ctypes.POINTER(Option), ctypes.c_int32]
         self.lib.cenv_reset.argtypes = [ctypes.POINTER(Option), ctypes.c_int32]
         self.lib.cenv_step.argtypes = [ctypes.POINTER(KeyValue), ctypes.c_int32]
-        opt = Option(b"seed", 0, _Value(i=int(seed)))
-        assert self.lib.cenv_make(b"", ctypes.byref(opt), 1) == 0
+        if easy_mode is not None:   # compile-time Config::easy_mode of the generator (coinrun, climber), set through the probe
+            self.probe("pg2o_set_easy_mode", None, [ctypes.c_int])(1 if easy_mode else 0)
+        opts = [(b"seed", int(seed))] + ([(b"width", int(width))] if width else []) + ([(b"height", int(height))] if height else [])
+        arr = (Option * len(opts))()
+        for i, (k, v) in enumerate(opts):
+            arr[i].name, arr[i].value_type, arr[i].value = k, 0, _Value(i=v)
+        assert self.lib.cenv_make(b"", arr, len(opts)) == 0
+        self.render_data = RenderData.in_dll(self.lib, "render_data")
         self.step_data = StepData.in_dll(self.lib, "step_data")
         self.reset_data = ResetData.in_dll(self.lib, "reset_data")
         self._a = ctypes.c_int32(0)
@@ -93,12 +104,19 @@ class RefEnv:
         lib, self.lib = self.lib, None
         if lib is not None:
             import _ctypes
-            self.step_data = self.reset_data = None
+            self.step_data = self.reset_data = self.render_data = None
             _ctypes.dlclose(lib._handle)
 
     def _obs(self, kv):
         n = kv.value_buffer_size
         return np.ctypeslib.as_array(kv.value_buffer.b, shape=(n,)).reshape(64, 64, 3).copy()
+
+    def render(self):
+        """cenv_render: the human-mode frame [height, width, 3]."""
+        self.lib.cenv_render()
+        rd = self.render_data
+        n = rd.value_buffer_width * rd.value_buffer_height * rd.value_buffer_channels
+        return np.ctypeslib.as_array(rd.value_buffer.b, shape=(n,)).reshape(rd.value_buffer_height, rd.value_buffer_width, 3).copy()
 
     def reset(self, seed=None):
         if seed is None:

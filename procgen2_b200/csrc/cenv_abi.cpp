@@ -117,7 +117,7 @@ int32_t cenv_get_env_version() { return kVersion; }
 int32_t cenv_make(const char* /*render_mode*/, cenv_option* options, int32_t options_size) {
     destroy_all();
     unsigned int seed = (unsigned int)time(nullptr);     // coinrun.cpp:130
-    int device = 0, num_devices = 1, max_episode_steps = 0, auto_reset = -1;
+    int device = 0, num_devices = 1, max_episode_steps = 0, auto_reset = -1, distribution_mode = -1;
     g_num_envs = 1; g_host_copy = 1;
     for (int i = 0; i < options_size; i++) {
         std::string name(options[i].name);
@@ -132,6 +132,7 @@ int32_t cenv_make(const char* /*render_mode*/, cenv_option* options, int32_t opt
         else if (name == "max_episode_steps") max_episode_steps = v;
         else if (name == "auto_reset") auto_reset = v;
         else if (name == "host_copy") g_host_copy = v != 0;
+        else if (name == "distribution_mode") distribution_mode = v;
     }
     if (g_num_envs < 1 || (long long)g_num_envs * kObsBytes > 2147483647LL) {
         fprintf(stderr, "[procgen2_b200] num_envs out of range for an int32 cenv buffer size\n");
@@ -154,6 +155,7 @@ int32_t cenv_make(const char* /*render_mode*/, cenv_option* options, int32_t opt
         cfg.max_episode_steps = max_episode_steps;
         cfg.assets_path = nullptr;
         cfg.auto_reset = auto_reset;
+        cfg.distribution_mode = distribution_mode;
         pg2_engine* e = nullptr;
         if (pg2_create(&cfg, &e)) {
             fprintf(stderr, "[procgen2_b200] cenv_make failed (device %d): %s\n", device + d, pg2_last_error());
@@ -274,16 +276,14 @@ int32_t cenv_step(cenv_key_value* actions, int32_t actions_size) {
     return 0;
 }
 
-// Human-mode frame. The reference re-renders the scene at window resolution
-// (coinrun.cpp:393-411); that cold path is a "next" row: until then the
-// frame is env 0's observation, nearest-neighbour enlarged to width x height.
+// Human-mode frame: env 0's scene drawn again at window resolution with the window size as camera_size
+// (render_game(false) + read-out, coinrun.cpp:393-411) — on the device (pg2_render_human).
 int32_t cenv_render() {
     if (!g_engine) return 1;
-    for (int y = 0; y < g_window_h; y++)
-        for (int x = 0; x < g_window_w; x++) {
-            int sx = x * 64 / g_window_w, sy = y * 64 / g_window_h;
-            memcpy(&g_frame[3 * ((size_t)x + (size_t)g_window_w * y)], &g_obs[3 * (sx + 64 * sy)], 3);
-        }
+    if (pg2_render_human(g_engine, 0, g_window_w, g_window_h, g_frame.data())) {
+        fprintf(stderr, "[procgen2_b200] cenv_render failed: %s\n", pg2_last_error());
+        return 1;
+    }
     return 0;
 }
 

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -272,6 +273,17 @@ __global__ void __launch_bounds__(RENDER_THREADS, PG2_RENDER_MIN_CTAS) k_render(
     if ((threadIdx.x & 31) == 0) frame_store_wait();   // every warp issued bulk stores of its own
 }
 
+// Human-mode frame of one env (cenv_render): every CTA shades a contiguous slice of the width x height frame.
+template <class G>
+__global__ void __launch_bounds__(RENDER_THREADS) k_render_human(typename G::State s, CommonState c, int env, const TexInfo* __restrict__ tex,
+                                                                 const uint32_t* __restrict__ atlas, uint8_t* __restrict__ out, int width, int height) {
+    __shared__ FrameOf<G> f;
+    frame_init_tiletex<G>(f, tex);
+    const int total = width * height, per = (total + gridDim.x - 1) / gridDim.x;
+    const int first = blockIdx.x * per, last = min(total, first + per);
+    render_human_body<G>(s, c, env, f, tex, atlas, out, width, height, first, last);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host engine
 
@@ -299,6 +311,7 @@ struct EngineBase {
     virtual ~EngineBase() {}
     virtual int reset(const int32_t* seeds) = 0;
     virtual int step_device(const int32_t* actions_dev) = 0;
+    virtual int render_human(int env, int width, int height, uint8_t* out_host) = 0;
     virtual bool find_field(const char* name, void** ptr, int* esz, int* pe) = 0;
     virtual size_t state_bytes_per_env() = 0;
     virtual size_t state_alloc_bytes() = 0;     // bytes of state_mem
@@ -451,6 +464,10 @@ struct Engine : EngineBase {
         PG2_CUDA(cudaMalloc(&common_mem, CommonState::bytes(N)));
         PG2_CUDA(cudaMemsetAsync(common_mem, 0, CommonState::bytes(N), stream));
         common = CommonState::bind(common_mem, N);
+        if (cfg->distribution_mode >= 0 && !G::mode_supported(cfg->distribution_mode))
+            return fail("pg2_create: distribution_mode " + std::to_string(cfg->distribution_mode) + " is not available for this game "
+                        "(0 easy, 1 hard, 2 memory / extreme; built: every game's reference default, + easy for coinrun and climber)");
+        common.mode = cfg->distribution_mode;
         PG2_CUDA(cudaMalloc(&obs, (size_t)N * OBS_BYTES));
         PG2_CUDA(cudaMemsetAsync(obs, 0, (size_t)N * OBS_BYTES, stream));
         PG2_CUDA(cudaMalloc(&reward, sizeof(float) * N));
@@ -474,6 +491,7 @@ struct Engine : EngineBase {
             PG2_CUDA(cudaMalloc(&shadow_common_mem, CommonState::bytes(N)));
             shadow_st = G::State::bind(shadow_state_mem, N);
             shadow_common = CommonState::bind(shadow_common_mem, N);
+            shadow_common.mode = common.mode;
             PG2_CUDA(cudaMalloc(&prep_list, sizeof(int) * PREP_SLOTS * (size_t)N));
             PG2_CUDA(cudaMalloc(&prep_count, PREP_SLOTS * sizeof(int)));
             PG2_CUDA(cudaMemsetAsync(prep_count, 0, PREP_SLOTS * sizeof(int), stream));
@@ -748,6 +766,22 @@ struct Engine : EngineBase {
         return 0;
     }
 
+    // cenv_render: the env's scene at window resolution (render_game(false)), copied to host memory
+    int render_human(int env, int width, int height, uint8_t* out_host) override {
+        if (env < 0 || env >= N || width < 1 || height < 1 || (long long)width * height > (1 << 26)) return fail("pg2_render_human: bad arguments");
+        const size_t bytes = (size_t)width * height * 3;
+        uint8_t* dev = nullptr;
+        PG2_CUDA(cudaMalloc(&dev, bytes));
+        const int grid = std::max(1, std::min(num_sms * 2, (width * height + 1023) / 1024));
+        k_render_human<G><<<grid, RENDER_THREADS, 0, stream>>>(st, common, env, texinfo, atlas, dev, width, height);
+        launches++;
+        cudaError_t ce = cudaMemcpyAsync(out_host, dev, bytes, cudaMemcpyDeviceToHost, stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream);
+        cudaFree(dev);
+        if (ce != cudaSuccess) return fail(std::string("pg2_render_human: ") + cudaGetErrorString(ce));
+        return 0;
+    }
+
     bool find_field(const char* name, void** ptr, int* esz, int* pe) override {
         return st.find(name, ptr, esz, pe) || common.find(name, ptr, esz, pe);
     }
@@ -810,6 +844,12 @@ int32_t pg2_step(pg2_engine* e, const int32_t* actions_host) {
     memcpy(b->actions_pinned, actions_host, sizeof(int32_t) * b->N);
     PG2_CUDA(cudaMemcpyAsync(b->actions, b->actions_pinned, sizeof(int32_t) * b->N, cudaMemcpyHostToDevice, b->stream));
     return b->step_device(b->actions);
+}
+
+int32_t pg2_render_human(pg2_engine* e, int32_t env, int32_t width, int32_t height, uint8_t* out_rgb) {
+    if (!e || !out_rgb) return fail("pg2_render_human: null argument");
+    PG2_ON_DEVICE(e->impl->device);
+    return e->impl->render_human(env, width, height, out_rgb);
 }
 
 int32_t pg2_step_device(pg2_engine* e, const int32_t* actions_device) {

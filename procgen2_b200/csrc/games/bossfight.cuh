@@ -55,6 +55,8 @@ struct BossFight {
     static const char* reset_keeps() { return ""; }
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 1;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
+    static bool mode_supported(int mode) { return mode == 1; }
     static constexpr bool HAS_TILES = false;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = true;    // fixed camera, no tile layer: the background image is cached per env
     static constexpr int MB = 64, NEX = 8, AB = 32, MAX_BAR = 4;
@@ -506,13 +508,13 @@ struct BossFight {
     template <class F>
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int N = s.N;
-        const Camera cam{ 0.0f, 0.0f, 1.0f };
+        const Camera cam{ 0.0f, 0.0f, __fdiv_rn(__fmul_rn(1.0f, f.view_w), 64.0f), f.view_w, f.view_h };   // game_zoom * width / obs_width
         const double PI = 3.14159265358979323846;
-        {   // background only, no tile layer
+        {   // background only, no tile layer (bossfight.cpp:424: centred, scaled to the camera height)
             const int bg = T_BG0 + s.bg_index[env];
-            const float sc = __fdiv_rn(__fmul_rn(__fdiv_rn(1.0f, (float)tex[bg].h), 64.0f), 1.0f);
-            const float half = __fmul_rn(__fdiv_rn(-64.0f, 1.0f), 0.5f);
-            build_tile_layer(f, cam, tex, 1, 0, 0, 0, 0, [](int) { return 0; }, [](int, int) { return (int)NO_TILE; }, bg, half, half, sc);
+            const float sc = __fdiv_rn(__fmul_rn(__fdiv_rn(1.0f, (float)tex[bg].h), cam.h), cam.scale);
+            const float half_x = __fmul_rn(__fdiv_rn(-cam.w, cam.scale), 0.5f), half_y = __fmul_rn(__fdiv_rn(-cam.h, cam.scale), 0.5f);
+            build_tile_layer(f, cam, tex, 1, 0, 0, 0, 0, [](int) { return 0; }, [](int, int) { return (int)NO_TILE; }, bg, half_x, half_y, sc);
         }
         const int m_num = s.m_num_bullets[env], m_next = s.m_next_bullet[env];
         const int e_num = s.m_num_expl[env], e_next = s.m_next_expl[env];

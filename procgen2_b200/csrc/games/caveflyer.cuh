@@ -51,6 +51,8 @@ struct CaveFlyer {
     static const char* reset_keeps() { return " cam_x cam_y "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 11;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
+    static bool mode_supported(int mode) { return mode == 1; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = false;   // the camera follows the agent: the base image changes every frame (a camera-keyed cache measured slower)
     enum Obj { O_NONE = 0, O_OBSTACLE, O_TARGET, O_ENEMY };
@@ -365,7 +367,7 @@ struct CaveFlyer {
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x, N = s.N;
         const double PI = 3.14159265358979323846;
-        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(0.5f, 64.0f), 64.0f) };
+        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(0.5f, f.view_w), 64.0f), f.view_w, f.view_h };
         int lx, ly, ux, uy;
         tile_window(cam, &lx, &ly, &ux, &uy);
         const int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);

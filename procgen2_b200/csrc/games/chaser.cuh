@@ -51,6 +51,8 @@ struct Chaser {
     static const char* reset_keeps() { return ""; }
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 14;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int DEFAULT_MODE = 0;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
+    static bool mode_supported(int mode) { return mode == 0; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = true;    // fixed camera and tile map within an episode: the base image (background + tiles) is cached per env
     static constexpr int TILE_STRIDE = 128, FREE_STRIDE = 64;
@@ -359,7 +361,7 @@ struct Chaser {
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x, N = s.N;
         // game_zoom = width * pixels_to_unit / map_width (chaser.cpp:401)
-        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(64.0f, PIXELS_TO_UNIT), (float)W) };
+        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(f.view_w, PIXELS_TO_UNIT), (float)W), f.view_w, f.view_h };
         int lx, ly, ux, uy;
         tile_window(cam, &lx, &ly, &ux, &uy);
         const int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);

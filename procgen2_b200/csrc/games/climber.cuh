@@ -49,6 +49,8 @@ struct Climber {
     static const char* reset_keeps() { return " cam_y "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 2;   // wall_mid textures are 64x64, one wall_top texture is 64x53
     static constexpr int WIN_ROWS = 23;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
+    static bool mode_supported(int mode) { return mode == 0 || mode == 1; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = false;   // the camera follows the agent: the base image changes every frame (a camera-keyed cache measured slower)
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID };
@@ -229,7 +231,7 @@ struct Climber {
         int curr_x = w.rng.uniform_int(2, W - 3);
         int curr_y = 1;
         const int margin_x = 3;
-        const float enemy_prob = 0.5f;
+        const float enemy_prob = w.mode == 0 ? 0.2f : 0.5f;   // cfg.easy_mode ? .2 : .5 (tilemap.cpp:118)
         const float max_dyf = __fdiv_rn(__fmul_rn(1.5f, 1.5f), __fmul_rn(2.0f, 0.2f));
         const int max_dy = f2i(__fsub_rn(max_dyf, 0.5f));
 
@@ -311,7 +313,7 @@ struct Climber {
     template <class F>
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x, N = s.N;
-        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(0.2f, 64.0f), 64.0f) };
+        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(0.2f, f.view_w), 64.0f), f.view_w, f.view_h };
         int lx, ly, ux, uy;
         tile_window(cam, &lx, &ly, &ux, &uy);
         const int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);

@@ -4,7 +4,8 @@
 //               System_Sprite_Render::update :7-39; System_Tilemap::get_collision tilemap.cpp:323-396
 //   level gen   System_Tilemap::regenerate tilemap.cpp:97-292 (+ spawn helpers :52-95), reset() coinrun.cpp:472-507
 //   frame       render_game coinrun.cpp:443-470; tilemap.cpp:294-321; common_systems.cpp:41-63, 254-278, 315-337
-// Compile-time mode of the reference: easy_mode = false, all allow_* = true (tilemap.h:40-46).
+// Compile-time mode of the reference: easy_mode = false, all allow_* = true (tilemap.h:40-46). easy_mode only feeds
+// `allow_monsters` (tilemap.cpp:148), which nothing reads: the "easy" distribution mode generates the same levels.
 #pragma once
 #include "../pg2_common.cuh"
 #include "../pg2_render.cuh"
@@ -64,6 +65,8 @@ struct CoinRun {
     static const char* reset_keeps() { return " cam_x cam_y "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 16;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
+    static bool mode_supported(int mode) { return mode == 0 || mode == 1; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = false;   // the camera follows the agent: the base image changes every frame (a camera-keyed cache measured slower)
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID, LAVA_TOP, LAVA_MID, CRATE };
@@ -462,7 +465,7 @@ struct CoinRun {
     template <class F>
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x, N = s.N;
-        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(0.3f, 64.0f), 64.0f) };   // game_zoom * width / obs_width
+        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(0.3f, f.view_w), 64.0f), f.view_w, f.view_h };   // game_zoom * width / obs_width
         int lx, ly, ux, uy;
         tile_window(cam, &lx, &ly, &ux, &uy);
         const int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);

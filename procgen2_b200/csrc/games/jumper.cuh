@@ -49,6 +49,8 @@ struct Jumper {
     static const char* reset_keeps() { return " cam_x cam_y to_goal_x to_goal_y "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 2;
     static constexpr int WIN_ROWS = 16;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
+    static bool mode_supported(int mode) { return mode == 1; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = false;   // the camera follows the agent: the base image changes every frame (a camera-keyed cache measured slower)
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID, SPIKE };
@@ -364,7 +366,7 @@ struct Jumper {
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x, N = s.N;
         const float zoom = 0.3f;
-        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(zoom, 64.0f), 64.0f) };
+        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(zoom, f.view_w), 64.0f), f.view_w, f.view_h };
         int lx, ly, ux, uy;
         tile_window(cam, &lx, &ly, &ux, &uy);
         const int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);
@@ -422,7 +424,7 @@ struct Jumper {
                 float py = __fmul_rn(__fadd_rn(posy, off_y), UNIT_TO_PIXELS);
                 b.plain(t, px, py, cam, __fmul_rn(__fdiv_rn(UNIT_TO_PIXELS, (float)tex[t].w), agent_scale), 1.0f, s.face_forward[env] == 0);
             } else {   // compass HUD (jumper.cpp:474-509), obs target: width = 64, game_zoom = 0.3
-                const float compass_size = 200.0f, off_x = -32.0f, off_y = 32.0f, width = 64.0f;
+                const float compass_size = 200.0f, off_x = -32.0f, off_y = 32.0f, width = f.view_w;   // (the HUD keeps game_zoom: it does not scale with the window)
                 const float tgx = s.to_goal_x[env], tgy = s.to_goal_y[env];
                 float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(tgx, tgx), __fmul_rn(tgy, tgy)));
                 if (k == o_hud) {

@@ -40,6 +40,8 @@ struct Maze {
     static const char* reset_keeps() { return "  "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 28;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
+    static bool mode_supported(int mode) { return mode == 1; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = true;    // fixed camera and tile map within an episode: the base image (background + tiles) is cached per env
     static constexpr int TILE_STRIDE = 640;
@@ -163,7 +165,7 @@ struct Maze {
     template <class F>
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x;
-        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(64.0f, __fmul_rn(UNIT_TO_PIXELS, (float)WORLD)) };
+        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(f.view_w, __fmul_rn(UNIT_TO_PIXELS, (float)WORLD)), f.view_w, f.view_h };   // maze.cpp:403: zoom from the width
         int lx, ly, ux, uy;
         tile_window(cam, &lx, &ly, &ux, &uy);
         int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);

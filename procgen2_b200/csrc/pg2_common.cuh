@@ -130,10 +130,10 @@ PG2_DEV_CALL Axis make_axis(float pos, float cam, float cs, float size, int tex_
 
 // Both axes of Renderer::render_texture in one function body: the two chains are independent, so their long
 // dependent float sequences interleave (twice the instruction-level parallelism of two make_axis calls).
-PG2_DEV_CALL void make_axis_xy(float px, float py, float cam_x, float cam_y, float cs, int tex_w, int tex_h, float scale,
-                                   bool flip_h, Axis* ax, Axis* ay) {
-    *ax = make_axis_inl(px, cam_x, cs, 64.0f, tex_w, scale, flip_h, false);
-    *ay = make_axis_inl(py, cam_y, cs, 64.0f, tex_h, scale, false, true);
+PG2_DEV_CALL void make_axis_xy(float px, float py, float cam_x, float cam_y, float cs, float size_x, float size_y, int tex_w, int tex_h,
+                                   float scale, bool flip_h, Axis* ax, Axis* ay) {
+    *ax = make_axis_inl(px, cam_x, cs, size_x, tex_w, scale, flip_h, false);
+    *ay = make_axis_inl(py, cam_y, cs, size_y, tex_h, scale, false, true);
 }
 
 // Axis of a blit whose float destination rect is given directly and whose source is the whole

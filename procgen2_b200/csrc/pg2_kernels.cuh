@@ -53,6 +53,7 @@ PG2_DEV void reset_body(const typename G::State& s, const CommonState& c, int en
     WarpCtx ctx;
     ctx.rng.mt = mt; ctx.rng.idx = c.mti[env]; ctx.rng.lane = lane;
     ctx.lane = lane; ctx.arena = arena; ctx.arena_off = 0; ctx.arena_cap = G::RESET_ARENA;
+    ctx.mode = c.mode < 0 ? G::DEFAULT_MODE : c.mode;
     G::regenerate(s, c, env, ctx);
     __syncwarp();
     for (int i = lane; i < MT_N; i += WARP_LANES) gmt[i] = mt[i];
@@ -98,6 +99,26 @@ PG2_DEV void render_body(const typename G::State& s, const CommonState& c, int e
     PG2_PHASE_MARK(4);
     if (img && !f.reuse && threadIdx.x == 0) c.view_valid[env] = 1;   // read by later launches only
     if (f.overflow && threadIdx.x == 0) c.fault[env] |= 8;            // tile window taller than G::WIN_ROWS: the frame is wrong
+}
+
+// render_game(false) + the RGB read-out of cenv_render (coinrun.cpp:393-411, 443-470) for ONE env: a frame of any size
+// with the window size as camera_size, drawn pixel by pixel along the general ordered path (cold path: the human
+// viewer). Every CTA of the launch describes the frame for itself and shades the pixels [first, last) of the
+// row-major frame; out = width * height * 3 bytes.
+template <class G>
+PG2_DEV void render_human_body(const typename G::State& s, const CommonState& c, int env, FrameOf<G>& f, const TexInfo* __restrict__ tex,
+                               const uint32_t* __restrict__ atlas, uint8_t* __restrict__ out, int width, int height, int first, int last) {
+    frame_begin(f, false);
+    __syncthreads();
+    if (threadIdx.x == 0) { f.view_w = (float)width; f.view_h = (float)height; f.human = 1; }
+    __syncthreads();
+    G::build_frame(s, c, env, f, tex);
+    __syncthreads();
+    frame_finalize<G>(f);
+    for (int p = first + (int)threadIdx.x; p < last; p += (int)blockDim.x) {
+        const uint32_t color = shade_human_pixel<G>(f, atlas, p % width, p / width);
+        out[3 * (size_t)p] = (uint8_t)color; out[3 * (size_t)p + 1] = (uint8_t)(color >> 8); out[3 * (size_t)p + 2] = (uint8_t)(color >> 16);
+    }
 }
 
 }  // namespace pg2

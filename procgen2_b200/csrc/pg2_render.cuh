@@ -128,6 +128,8 @@ struct FrameT {
     int wide;                                   // the frame needs the general ordered path for every pixel (never observed)
     int pre_blend;                              // background texture carries alpha
     // ---- per frame
+    float view_w, view_h;                       // camera_size of this frame: 64x64, or the window size of a human-mode frame
+    int human;                                  // human-mode frame (render_game(false)): general ordered path, any size
     int reuse;                                  // the base image comes from the env's cache: the view is not built
     int overflow;                               // the tile window has more rows than WINR (a sizing error: reported as fault bit 8)
     FastBlit fpost[MAXP];
@@ -188,14 +190,16 @@ PG2_DEV_CALL void sincos_deg(double deg, double* s, double* c) {
 // Work item k of a frame builder runs on the first lane of warp k (any thread when simulated).
 PG2_DEV bool is_role(int k) { return (int)threadIdx.x == (k * 32) % (int)blockDim.x; }
 
-struct Camera { float x, y, scale; };   // gr.camera_position / gr.camera_scale; camera_size is 64x64
+// gr.camera_position / gr.camera_scale / gr.camera_size (renderer.h:18-20). The size is 64x64 for observations and the
+// window size for the human-mode frame of cenv_render (render_game(false), coinrun.cpp:451-455).
+struct Camera { float x, y, scale, w = 64.0f, h = 64.0f; };
 
 // Renderer::render_texture (renderer.cpp:5-82)
 PG2_DEV Blit make_blit(const TexInfo* tex, int tex_id, float px, float py, const Camera& cam,
                                           float scale, float alpha = 1.0f, bool flip_h = false) {
     TexInfo t = tex[tex_id];
     Blit b;
-    make_axis_xy(px, py, cam.x, cam.y, cam.scale, t.w, t.h, scale, flip_h, &b.ax, &b.ay);
+    make_axis_xy(px, py, cam.x, cam.y, cam.scale, cam.w, cam.h, t.w, t.h, scale, flip_h, &b.ax, &b.ay);
     if (!b.ay.visible) b.ax.visible = 0;
     b.tex_offset = t.offset; b.tex_w = t.w; b.blend = (uint8_t)t.blend;
     // `SDL_SetTextureAlphaMod(tex, 255 * alpha)`: float -> Uint8 truncation (renderer.cpp:57)
@@ -210,8 +214,8 @@ PG2_DEV Blit make_blit_rotated(const TexInfo* tex, int tex_id, float px, float p
                                                   float rotation, float scale, float alpha, BlitRot* rot) {
     TexInfo t = tex[tex_id];
     Blit b;
-    float dx = __fadd_rn(__fmul_rn(__fsub_rn(px, cam.x), cam.scale), 32.0f);
-    float dy = __fadd_rn(__fmul_rn(__fsub_rn(py, cam.y), cam.scale), 32.0f);
+    float dx = __fadd_rn(__fmul_rn(__fsub_rn(px, cam.x), cam.scale), __fmul_rn(cam.w, 0.5f));
+    float dy = __fadd_rn(__fmul_rn(__fsub_rn(py, cam.y), cam.scale), __fmul_rn(cam.h, 0.5f));
     float dw = __fmul_rn(__fmul_rn((float)t.w, scale), cam.scale);
     float dh = __fmul_rn(__fmul_rn((float)t.h, scale), cam.scale);
     b.ax = make_axis_direct(dx, dw, t.w);
@@ -369,14 +373,14 @@ PG2_DEV int live_list(F& f, int n, Fn id_or_neg) {
 
 // Tile window of System_Tilemap::render (tilemap.cpp:294-302): inclusive tile index range.
 PG2_DEV void tile_window(const Camera& cam, int* lower_x, int* lower_y, int* upper_x, int* upper_y) {
-    float hx = __fdiv_rn(__fmul_rn(64.0f, 0.5f), cam.scale);
+    float hx = __fdiv_rn(__fmul_rn(cam.w, 0.5f), cam.scale), hy = __fdiv_rn(__fmul_rn(cam.h, 0.5f), cam.scale);
     float ax = __fmul_rn(__fsub_rn(cam.x, hx), PIXELS_TO_UNIT);
-    float ay = __fmul_rn(__fsub_rn(cam.y, hx), PIXELS_TO_UNIT);
-    float aw = __fdiv_rn(__fmul_rn(64.0f, PIXELS_TO_UNIT), cam.scale);
+    float ay = __fmul_rn(__fsub_rn(cam.y, hy), PIXELS_TO_UNIT);
+    float aw = __fdiv_rn(__fmul_rn(cam.w, PIXELS_TO_UNIT), cam.scale), ah = __fdiv_rn(__fmul_rn(cam.h, PIXELS_TO_UNIT), cam.scale);
     *lower_x = f2i(floorf(ax));
     *lower_y = f2i(floorf(ay));
     *upper_x = f2i(ceilf(__fadd_rn(ax, aw)));
-    *upper_y = f2i(ceilf(__fadd_rn(ay, aw)));
+    *upper_y = f2i(ceilf(__fadd_rn(ay, ah)));
 }
 
 // Games whose camera and tile map are fixed within an episode (G::STATIC_VIEW: maze, chaser, bossfight) keep the BASE
@@ -395,6 +399,7 @@ PG2_DEV void frame_begin(F& f, bool reuse = false) {   // `reuse` is only looked
     const int tid = threadIdx.x;
     if (tid == 0) {
         f.npost = 0; f.ncol = 0; f.nrow = 0; f.nclass = 1; f.next_band = 0; f.reuse = reuse ? 1 : 0; f.overflow = 0;
+        f.view_w = (float)OBS_W; f.view_h = (float)OBS_H; f.human = 0;
         if (!reuse) { f.npre = 0; f.wide = 0; f.pre_blend = 0; }
     }
     // cslot and rslot are adjacent: one run of 16-byte words
@@ -457,7 +462,7 @@ PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int n
         const TexInfo ti = tex[bg ? bg_tex : class_tex(cls)];
         const float scale = bg ? bg_scale : __fdiv_rn(UNIT_TO_PIXELS, (float)ti.w);
         const float pos = bg ? (is_row ? bg_y : bg_x) : __fmul_rn((float)((is_row ? ly : lx) + idx), UNIT_TO_PIXELS);
-        const Axis a = make_axis(pos, is_row ? cam.y : cam.x, cam.scale, 64.0f, is_row ? ti.h : ti.w, scale, false, is_row);
+        const Axis a = make_axis(pos, is_row ? cam.y : cam.x, cam.scale, is_row ? cam.h : cam.w, is_row ? ti.h : ti.w, scale, false, is_row);
         if (bg) {
             if (is_row) f.pre[0].ay = a;
             else {   // the x-axis job also fills the rest of the blit (make_blit, alpha 1, no flip)
@@ -468,6 +473,7 @@ PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int n
             continue;
         }
         if (is_row) f.row[cls][idx] = a; else f.col[cls][idx] = a;
+        if (f.human) continue;   // window-size frame: drawn by the general ordered path from the axes themselves
         if (a.visible && a.d0 > -65536 && a.d0 < 65536 && a.dlen < 65536) {
             // register in the candidate slot of every screen column / row this tile column / row covers, with the source
             // sample under it (rows: already multiplied by the texture width); a slot that was taken means three tiles
@@ -520,6 +526,11 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
         Blit b = f.pre[k];
         if (!b.ay.visible) b.ax.visible = 0;   // make_blit's rule (the two axes were built by different threads)
         f.fpre[k] = make_fast(b);
+    }
+    if (f.human) {   // window-size frame: no 64-pixel tables, every pixel goes the general ordered way
+        if (tid == 0) f.wide = 1;
+        __syncthreads();
+        return;
     }
     for (int k = tid; k < 2 * OBS_W; k += blockDim.x) {
         const bool is_row = k >= OBS_W;
@@ -767,6 +778,37 @@ PG2_DEV_COLD uint32_t shade_base_continue(const F& f, const uint32_t* __restrict
     return a ? shade_base_ordered<G>(f, atlas, X, Y) : 0u;
 }
 
+// x / 255 for two 16-bit lanes at once (each lane <= 65 534: exact, no carry between the lanes).
+PG2_DEV uint32_t div255x2(uint32_t v) { return ((v + 0x00010001u + ((v >> 8) & 0x00ff00ffu)) >> 8) & 0x00ff00ffu; }
+PG2_DEV uint32_t div255(uint32_t v) { return (v + 1u + (v >> 8)) >> 8; }
+
+// SRC-over of one texel with effective alpha a in [1, 254] onto an RGBA word: blend_texel's integer arithmetic
+// (premultiply by a, then dst * (255 - a) / 255), red and blue in one multiply.
+PG2_DEV uint32_t blend_word(uint32_t dst, uint32_t texel, uint32_t a) {
+    const uint32_t ia = 255u - a;
+    const uint32_t trb = div255x2((texel & 0x00ff00ffu) * a), tg = div255((texel >> 8 & 255u) * a);
+    const uint32_t drb = div255x2((dst & 0x00ff00ffu) * ia), dg = div255((dst >> 8 & 255u) * ia);
+    return (trb + drb) | (tg + dg) << 8;
+}
+
+// Human-mode frame (cenv_render, render_game(false)): one pixel of a frame of any size — clear, background, every tile of
+// the window and every post blit in the reference's order with full blending. The frame was described with the window
+// size as camera_size (f.human: no 64-pixel tables are built), f.wide is set.
+template <class G, class F>
+PG2_DEV uint32_t shade_human_pixel(const F& f, const uint32_t* __restrict__ atlas, int X, int Y) {
+    uint32_t color = shade_base_ordered<G>(f, atlas, X, Y);
+    for (int k = 0; k < f.npost; k++) {
+        const FastBlit fb = f.fpost[k];
+        uint32_t texel;
+        if (fast_texel<F::ROTATES>(fb, &f.post_rot[F::ROTATES ? k : 0], atlas, X, Y, &texel)) {
+            const uint32_t a = (fb.flags & 1u) ? layer_alpha(texel, 1u, fb.alpha_mod) : 255u;
+            if (a == 255u) color = texel;
+            else if (a != 0u) color = blend_word(color, texel, a);
+        }
+    }
+    return color;
+}
+
 // A pixel the base pass could not decide from its table: all tile candidates top-down, then the background.
 #ifdef PG2_HOSTSIM
 static long g_dbg_slow = 0, g_dbg_quads = 0, g_dbg_quads_slow = 0, g_dbg_rb = 0;   // host-sim statistics (scripts/sim_check.py)
@@ -869,19 +911,6 @@ PG2_DEV void raster_band_base(F& f, const uint32_t* __restrict__ atlas, int band
         return;
     }
     raster_band_fast<G>(f, atlas, band, lane, buf);
-}
-
-// x / 255 for two 16-bit lanes at once (each lane <= 65 534: exact, no carry between the lanes).
-PG2_DEV uint32_t div255x2(uint32_t v) { return ((v + 0x00010001u + ((v >> 8) & 0x00ff00ffu)) >> 8) & 0x00ff00ffu; }
-PG2_DEV uint32_t div255(uint32_t v) { return (v + 1u + (v >> 8)) >> 8; }
-
-// SRC-over of one texel with effective alpha a in [1, 254] onto an RGBA word: blend_texel's integer arithmetic
-// (premultiply by a, then dst * (255 - a) / 255), red and blue in one multiply.
-PG2_DEV uint32_t blend_word(uint32_t dst, uint32_t texel, uint32_t a) {
-    const uint32_t ia = 255u - a;
-    const uint32_t trb = div255x2((texel & 0x00ff00ffu) * a), tg = div255((texel >> 8 & 255u) * a);
-    const uint32_t drb = div255x2((dst & 0x00ff00ffu) * ia), dg = div255((dst >> 8 & 255u) * ia);
-    return (trb + drb) | (tg + dg) << 8;
 }
 
 // One post blit onto the rows [Y0, Y0 + 8) (the band buffer): lanes = an 8x4 patch of the destination rectangle.

@@ -31,6 +31,7 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 #define PG2_DEFINE_STATE(NAME, FIELDS)                                   \
     struct NAME {                                                        \
         int N;                                                           \
+        int mode = -1;   /* distribution mode of the level generator (CommonState only; -1: the reference's default) */ \
         FIELDS(PG2_FIELD_DECL)                                           \
         static size_t bytes(int n) {                                     \
             size_t total = 0;                                            \

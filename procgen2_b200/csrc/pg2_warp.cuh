@@ -23,6 +23,7 @@ struct WarpCtx {
     char* arena;       // per-warp shared-memory scratch
     int arena_off;
     int arena_cap;     // bytes available (G::RESET_ARENA)
+    int mode;          // distribution mode (tilemap.h Config of the game): 0 easy, 1 hard, 2 memory / extreme
 
     template <class T>
     PG2_DEV_NOINLINE T* alloc(int count) {

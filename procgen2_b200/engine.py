@@ -21,7 +21,7 @@ GAMES = ("bossfight", "caveflyer", "chaser", "climber", "coinrun", "jumper", "ma
 class _Config(ctypes.Structure):
     _fields_ = [("game", ctypes.c_char_p), ("num_envs", ctypes.c_int32), ("seed", ctypes.c_int32),
                 ("first_env", ctypes.c_int32), ("device", ctypes.c_int32), ("max_episode_steps", ctypes.c_int32),
-                ("assets_path", ctypes.c_char_p), ("auto_reset", ctypes.c_int32)]
+                ("assets_path", ctypes.c_char_p), ("auto_reset", ctypes.c_int32), ("distribution_mode", ctypes.c_int32)]
 
 
 _lib = None
@@ -84,12 +84,13 @@ class BatchedEnv:
     env i is seeded ``seed + first_env + i`` and reproduces a reference process created with
     that seed (cenv_make -> cenv_reset -> cenv_step..., reset on terminate)."""
 
-    def __init__(self, game, num_envs, seed=0, device=0, first_env=0, max_episode_steps=0, assets_path=None, auto_reset=True):
+    def __init__(self, game, num_envs, seed=0, device=0, first_env=0, max_episode_steps=0, assets_path=None, auto_reset=True,
+                 distribution_mode=-1):
         L = load_library()
         self.game, self.num_envs, self.device = game, int(num_envs), int(device)
         self._assets = assets_path.encode() if assets_path else None
         cfg = _Config(game.encode(), self.num_envs, int(np.int32(np.uint32(seed & 0xffffffff))), int(first_env), self.device,
-                      int(max_episode_steps), self._assets, 1 if auto_reset else 0)
+                      int(max_episode_steps), self._assets, 1 if auto_reset else 0, int(distribution_mode))
         h = ctypes.c_void_p()
         _check(L.pg2_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h

@@ -27,6 +27,7 @@ struct SimBase {
     virtual void reset_all(const int32_t* seeds) = 0;
     virtual void step(const int32_t* actions) = 0;
     virtual bool find_field(const char* name, void** ptr, int* esz, int* pe) = 0;
+    virtual void render_human(int env, int width, int height, uint8_t* out) = 0;
     int N = 0, max_episode_steps = 0;
     std::vector<uint8_t> obs, terminated, truncated;
     std::vector<float> reward;
@@ -43,12 +44,13 @@ struct Sim : SimBase {
     std::vector<uint32_t> atlas;
     std::unique_ptr<FrameOf<G>> frame;
 
-    bool init(int n, uint32_t base_seed, int max_ep, const char* assets, std::string* err) {
+    bool init(int n, uint32_t base_seed, int max_ep, const char* assets, std::string* err, int mode = -1) {
         N = n; max_episode_steps = max_ep;
         state_mem.assign(G::State::bytes(N), 0);
         common_mem.assign(CommonState::bytes(N), 0);
         st = G::State::bind(state_mem.data(), N);
         c = CommonState::bind(common_mem.data(), N);
+        c.mode = mode;
         arena.assign(G::RESET_ARENA, 0);
         view_cache.assign((size_t)N * VIEW_CACHE_BYTES, 0);
         mt_scratch.assign(MT_N, 0);
@@ -81,6 +83,9 @@ struct Sim : SimBase {
     bool find_field(const char* name, void** ptr, int* esz, int* pe) override {
         return st.find(name, ptr, esz, pe) || c.find(name, ptr, esz, pe);
     }
+    void render_human(int env, int width, int height, uint8_t* out) override {
+        render_human_body<G>(st, c, env, *frame, tex.data(), atlas.data(), out, width, height, 0, width * height);
+    }
 };
 
 static std::string g_err;
@@ -91,13 +96,15 @@ extern "C" {
 const char* hs_last_error() { return g_err.c_str(); }
 void hs_debug_counters(long* out) { out[0] = pg2::g_dbg_slow; out[1] = pg2::g_dbg_quads; out[2] = pg2::g_dbg_quads_slow; out[3] = pg2::g_dbg_rb; }
 
-void* hs_create(const char* game, int n, int seed, int max_ep, const char* assets) {
+void* hs_create_mode(const char* game, int n, int seed, int max_ep, const char* assets, int mode);
+void* hs_create(const char* game, int n, int seed, int max_ep, const char* assets) { return hs_create_mode(game, n, seed, max_ep, assets, -1); }
+void* hs_create_mode(const char* game, int n, int seed, int max_ep, const char* assets, int mode) {
     std::string g = game;
     if (g_sort_table.empty()) { g_sort_table = build_sort_perm(SORT_MAXN); g_sort_perm = g_sort_table.data(); }
     SimBase* out = nullptr;
     bool ok = false;
 #define PG2_TRY_GAME(NAME, TYPE) \
-    if (g == NAME) { auto* s = new Sim<TYPE>(); out = s; ok = s->init(n, (uint32_t)seed, max_ep, assets, &g_err); }
+    if (g == NAME) { auto* s = new Sim<TYPE>(); out = s; ok = s->init(n, (uint32_t)seed, max_ep, assets, &g_err, mode); }
     PG2_FOR_EACH_GAME(PG2_TRY_GAME)
 #undef PG2_TRY_GAME
     if (!out) { g_err = "unknown game " + g; return nullptr; }
@@ -107,6 +114,7 @@ void* hs_create(const char* game, int n, int seed, int max_ep, const char* asset
 void hs_destroy(void* h) { delete (SimBase*)h; }
 void hs_reset(void* h, const int32_t* seeds) { ((SimBase*)h)->reset_all(seeds); }
 void hs_step(void* h, const int32_t* actions) { ((SimBase*)h)->step(actions); }
+void hs_render_human(void* h, int env, int width, int height, uint8_t* out) { ((SimBase*)h)->render_human(env, width, height, out); }
 const uint8_t* hs_obs(void* h) { return ((SimBase*)h)->obs.data(); }
 const float* hs_reward(void* h) { return ((SimBase*)h)->reward.data(); }
 const uint8_t* hs_terminated(void* h) { return ((SimBase*)h)->terminated.data(); }

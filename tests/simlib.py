@@ -19,9 +19,12 @@ def lib():
         L = ctypes.CDLL(hb.build())
         L.hs_create.restype = ctypes.c_void_p
         L.hs_create.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
+        L.hs_create_mode.restype = ctypes.c_void_p
+        L.hs_create_mode.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
         L.hs_destroy.argtypes = [ctypes.c_void_p]
         L.hs_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.hs_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.hs_render_human.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         for n, t in (("hs_obs", ctypes.c_uint8), ("hs_reward", ctypes.c_float), ("hs_terminated", ctypes.c_uint8), ("hs_truncated", ctypes.c_uint8)):
             getattr(L, n).restype = ctypes.POINTER(t)
             getattr(L, n).argtypes = [ctypes.c_void_p]
@@ -33,10 +36,10 @@ def lib():
 
 
 class HostSim:
-    def __init__(self, game, num_envs, seed, max_episode_steps=0):
+    def __init__(self, game, num_envs, seed, max_episode_steps=0, distribution_mode=-1):
         L = lib()
         self.n = num_envs
-        self.h = L.hs_create(game.encode(), num_envs, seed, max_episode_steps, ASSETS.encode())
+        self.h = L.hs_create_mode(game.encode(), num_envs, seed, max_episode_steps, ASSETS.encode(), distribution_mode)
         if not self.h:
             raise RuntimeError(L.hs_last_error().decode())
 
@@ -57,6 +60,11 @@ class HostSim:
         a = np.ascontiguousarray(actions, np.int32)
         lib().hs_step(self.h, a.ctypes.data)
         return self._out()
+
+    def render_human(self, env, width, height):
+        out = np.empty((height, width, 3), np.uint8)
+        lib().hs_render_human(self.h, env, width, height, out.ctypes.data)
+        return out
 
     def field(self, name):
         L = lib()

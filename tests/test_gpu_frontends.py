@@ -130,3 +130,64 @@ def test_vector_env_matches_oracle(game, oracle_available):
     assert torch.equal(f1, f2)
     assert env.render().shape == (64, 64, 3)
     env.close()
+
+
+@pytest.mark.parametrize("game", ["coinrun", "bossfight", "jumper", "maze"])
+def test_cenv_render_matches_oracle(game, oracle_available):
+    """cenv_render of the drop-in library = the reference's human-mode frame (512x512 default window and a custom size),
+    rendered on the device."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref did not travel")
+    from oracle import ref_env
+    from procgen2_b200.build import game_lib_path
+    from procgen2_b200.cenv import CEnv
+    for opts in ({}, {"width": 200, "height": 200}):
+        env = CEnv(game_lib_path(game), options=dict(seed=515, **opts))
+        ref = ref_env.RefEnv(game, 515, **opts)
+        obs, _ = env.reset()
+        np.testing.assert_array_equal(obs["screen"].reshape(64, 64, 3), ref.reset())
+        rs = np.random.RandomState(1)
+        for t in range(20):
+            a = int(rs.randint(0, 15))
+            obs, _, term, _, _ = env.step(a)
+            o, w, d = ref.step(a)
+            if d:
+                o = ref.reset(); obs, _ = env.reset()
+            np.testing.assert_array_equal(obs["screen"].reshape(64, 64, 3), o)
+            if t % 6 == 5:
+                fr = env.render()
+                assert fr.shape == ((512, 512, 3) if not opts else (200, 200, 3))
+                np.testing.assert_array_equal(fr, ref.render(), err_msg="%s step %d" % (game, t))
+        env.close(); ref.close()
+
+
+def test_distribution_mode_option(oracle_available):
+    """cenv make-option "distribution_mode": climber easy (0) on the GPU against the reference with Config::easy_mode set;
+    a (game, mode) pair that is not built is refused loudly."""
+    from procgen2_b200.engine import BatchedEnv
+    with pytest.raises(RuntimeError, match="distribution_mode"):
+        BatchedEnv("maze", 4, distribution_mode=2)
+    if not oracle_available:
+        pytest.skip("oracle/_ref did not travel")
+    from oracle import ref_env
+    n, seed, T = 32, 9100, 90
+    rs = np.random.RandomState(12)
+    acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
+    env = BatchedEnv("climber", n, seed=seed, max_episode_steps=30, distribution_mode=0)
+    refs = [ref_env.RefEnv("climber", seed + i, easy_mode=True) for i in range(n)]
+    env.reset()
+    np.testing.assert_array_equal(env.fetch()[0], np.stack([r.reset() for r in refs]))
+    age = np.zeros(n, np.int64)
+    for t in range(T):
+        env.step(acts[t])
+        o, rw, d, _ = env.fetch()
+        for i, r in enumerate(refs):
+            oo, w, dd = r.step(acts[t, i])
+            age[i] += 1
+            if dd or age[i] >= 30:
+                oo = r.reset(); age[i] = 0
+            assert w == rw[i] and dd == d[i]
+            np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))
+    for r in refs:
+        r.close()
+    env.close()

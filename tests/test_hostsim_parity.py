@@ -131,3 +131,65 @@ def test_maze_timeout_live_oracle(oracle_available):
     assert episodes >= 1
     for r in refs:
         r.close()
+
+
+@pytest.mark.parametrize("game", IMPLEMENTED)
+def test_human_render_live_oracle(game, oracle_available):
+    """cenv_render (render_game(false), coinrun.cpp:393-411): the scene drawn again with the window size as camera_size —
+    square windows interleaved with stepping (the observations must not be disturbed), a non-square one at the end
+    (there the reference's own step logic would afterwards see the window aspect, SURVEY Q11: not interleaved)."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_env
+    n, seed = 2, 77
+    for (W, H) in ((96, 96), (160, 100)):
+        sim = SimAdapter(game, n, seed)
+        refs = [ref_env.RefEnv(game, seed + i, width=W, height=H) for i in range(n)]
+        np.testing.assert_array_equal(sim.reset(), np.stack([r.reset() for r in refs]))
+        rs = np.random.RandomState(3)
+        for t in range(24):
+            a = rs.randint(0, 15, size=n).astype(np.int32)
+            o, _, _ = sim.step(a)
+            for i, r in enumerate(refs):
+                oo, w, d = r.step(a[i])
+                np.testing.assert_array_equal(o[i], r.reset() if d else oo)
+            if (W == H and t % 8 == 7) or t == 23:
+                for i, r in enumerate(refs):
+                    np.testing.assert_array_equal(sim.sim.render_human(i, W, H), r.render(), err_msg="%s %dx%d step %d env %d" % (game, W, H, t, i))
+        for r in refs:
+            r.close()
+
+
+@pytest.mark.parametrize("game", ["climber", "coinrun"])
+def test_easy_distribution_mode_live_oracle(game, oracle_available):
+    """Make-option distribution_mode = 0 (easy) against the reference with its compile-time Config::easy_mode flipped
+    (climber: enemy probability .2 instead of .5, tilemap.cpp:118; coinrun: the flag only feeds a variable nothing reads,
+    tilemap.cpp:148 — same levels as hard)."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_env
+    n, seed, T = 6, 9100, 120
+    rs = np.random.RandomState(12)
+    acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
+    sim = SimAdapter(game, n, seed, max_episode_steps=30, distribution_mode=0)
+    refs = [ref_env.RefEnv(game, seed + i, easy_mode=True) for i in range(n)]
+    np.testing.assert_array_equal(sim.reset(), np.stack([r.reset() for r in refs]))
+    age = np.zeros(n, np.int64)
+    for t in range(T):
+        o, rw, d = sim.step(acts[t])
+        for i, r in enumerate(refs):
+            oo, w, dd = r.step(acts[t, i])
+            age[i] += 1
+            if dd or age[i] >= 30:
+                oo = r.reset(); age[i] = 0
+            assert w == rw[i] and dd == d[i]
+            np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))
+    f = sim.fields()
+    for i, r in enumerate(refs):
+        st, pos = r.rng_state()
+        assert pos == f["mti"][i]
+        np.testing.assert_array_equal(st, f["mt"][i])
+        r.close()
+    if game == "climber":   # the mode does change climber's levels (fewer enemies): easy and hard runs part ways
+        easy, hard = SimAdapter(game, n, seed, distribution_mode=0), SimAdapter(game, n, seed, distribution_mode=1)
+        assert any(not np.array_equal(easy.reset(), hard.reset()) for _ in range(6))
