@@ -176,7 +176,16 @@ __global__ void __launch_bounds__(128) k_step(typename G::State s, CommonState c
     if (gtid == 0) { *zero_a = 0; zero_b[0] = 0; zero_b[1] = 0; }
     bool done = false;
     int env;
-    if (epw == 1) {   // a whole warp per environment (warp-uniform branch)
+    if (epw == 1 && G::LANE_AWARE && G::STEP_LANES < 32) {   // a lane group per environment, 32 / STEP_LANES environments per warp
+        constexpr int L = G::STEP_LANES;
+        env = gtid / L;
+        const int gl = lane % L;
+        const uint32_t gmask = (L >= 32 ? 0xffffffffu : ((1u << L) - 1u)) << (lane / L * L);
+        if (env < N) {
+            done = step_body<G>(s, c, env, actions[env], reward, terminated, truncated, max_episode_steps, StepCtx{ gl, L, gmask }) && auto_reset && gl == 0;
+            if (gl == 0) pending[env] = done;
+        }
+    } else if (epw == 1) {   // a whole warp per environment (warp-uniform branch)
         env = gtid >> 5;
         if (env < N) {
             done = step_body<G>(s, c, env, actions[env], reward, terminated, truncated, max_episode_steps, StepCtx{ lane, 32 }) && auto_reset && lane == 0;
@@ -589,7 +598,11 @@ struct Engine : EngineBase {
         return 0;
     }
 
-    int step_grid() const { int warps = (N + step_epw - 1) / step_epw; return (warps * 32 + 127) / 128; }
+    int step_grid() const {
+        const int per_warp = (G::LANE_AWARE && step_epw == 1) ? 32 / G::STEP_LANES : step_epw;   // environments per warp
+        const int warps = (N + per_warp - 1) / per_warp;
+        return (warps * 32 + 127) / 128;
+    }
     static int reset_smem() { return RESET_WARPS_PER_CTA * (MT_N * 4 + G::RESET_ARENA); }
     // as many CTAs as fit the SMs' shared memory at once (227 KB per SM, 1 KB reserved per CTA, <= 16): the games with a
     // small level-generation scratch run 8x more resets concurrently than the cave generators

@@ -46,7 +46,8 @@ PG2_DEFINE_STATE(BossFightState, PG2_BOSSFIGHT_FIELDS)
 struct BossFight {
     using State = BossFightState;
     static constexpr int SUB_STEPS = 4;
-    static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
+    static constexpr bool LANE_AWARE = true;    // step(): the bullet rings are walked lane-parallel, the rest is uniform (leader stores)
+    static constexpr int STEP_LANES = 8;        // lanes per environment in k_step: four environments share a warp (measured: 4 / 16 / 32 lanes are 5-15 % slower)
     static constexpr int MAX_POST = 112;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
@@ -55,6 +56,7 @@ struct BossFight {
     static const char* reset_keeps() { return ""; }
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 1;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int BLIT_UNROLL = 2;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
     static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
     static bool mode_supported(int mode) { return mode == 1; }
     static constexpr bool HAS_TILES = false;     // the frame has a tile layer
@@ -99,19 +101,22 @@ struct BossFight {
 
     // ---------------------------------------------------------------------------------------
     // System_Mob_AI::fire (common_systems.cpp:75-88)
-    struct MobPool {
+    struct MobPool {   // every lane keeps the (identical) counters, the leader stores
         const State& s; int env, N;
         int next_bullet, num_bullets, next_expl, num_expl;
+        bool leader;
         PG2_DEV void fire(float x, float y, float rotation, float speed) {
             if (num_bullets < MB) {
                 int i = next_bullet * N + env;
                 float sn, cs;
                 glibc_sincosf(rotation, &sn, &cs);
-                s.mb_rot[i] = rotation;
-                s.mb_vx[i] = __fmul_rn(cs, speed);
-                s.mb_vy[i] = __fmul_rn(-sn, speed);
-                s.mb_x[i] = x; s.mb_y[i] = y;
-                s.mb_frame[i] = 0.0f;
+                if (leader) {
+                    s.mb_rot[i] = rotation;
+                    s.mb_vx[i] = __fmul_rn(cs, speed);
+                    s.mb_vy[i] = __fmul_rn(-sn, speed);
+                    s.mb_x[i] = x; s.mb_y[i] = y;
+                    s.mb_frame[i] = 0.0f;
+                }
                 next_bullet = (next_bullet + 1) % MB;
                 num_bullets++;
             }
@@ -119,18 +124,34 @@ struct BossFight {
         PG2_DEV void explode(float x, float y) {
             if (num_expl < NEX) {
                 int i = next_expl * N + env;
-                s.ex_x[i] = x; s.ex_y[i] = y; s.ex_frame[i] = 0.0f;
+                if (leader) { s.ex_x[i] = x; s.ex_y[i] = y; s.ex_frame[i] = 0.0f; }
                 next_expl = (next_expl + 1) % NEX;
                 num_expl++;
             }
         }
     };
 
+    // A bullet ring is walked newest to oldest, `i < num` with num shrinking by one whenever a bullet is destroyed
+    // (common_systems.cpp:330-372, 560-640): entry i is visited iff i + #destroyed among the entries before it < n0 —
+    // a prefix of the ring, since that sum grows with i. D: bit i = entry i would be destroyed if visited (an entry's own
+    // fate does not depend on the others). Returns the number of visited entries.
+    static PG2_DEV int visited_prefix(uint64_t D, int n0) {
+        if ((D & (n0 >= 64 ? ~0ull : (1ull << n0) - 1ull)) == 0ull) return n0;   // nothing destroyed: the whole ring
+        int lo = 0, hi = n0;   // the largest L <= n0 with (L - 1) + popc(D below L - 1) < n0, by bisection (monotone)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1, i = mid - 1;
+            const int g = i + __popcll(D & ((1ull << i) - 1ull));
+            if (g < n0) lo = mid; else hi = mid - 1;
+        }
+        return lo;
+    }
+
     static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward, const StepCtx& ctx) {
         const int N = s.N;
         const float dt = 1.0f / SUB_STEPS;
         const double PI = 3.14159265358979323846;
         Mt rng; rng.mt = c.mt + (size_t)env * MT_N; rng.idx = c.mti[env];
+        rng.collective = ctx.nlanes != 1; rng.writer = ctx.leader(); rng.sync_mask = ctx.mask;
         const Rect screen{ -2.0f, -2.0f, 4.0f, 4.0f };
 
         float px = s.px[env], py = s.py[env], pvx = s.pvx[env], pvy = s.pvy[env];
@@ -138,7 +159,7 @@ struct BossFight {
         float phase_timer = s.phase_timer[env], attack_timer = s.attack_timer[env];
         int phase_index = s.phase_index[env], weapon_index = s.weapon_index[env], hp = s.hp[env];
         float expl_timer = s.expl_timer[env], damage_timer = s.damage_timer[env], move_timer = s.move_timer[env];
-        MobPool mp{ s, env, N, s.m_next_bullet[env], s.m_num_bullets[env], s.m_next_expl[env], s.m_num_expl[env] };
+        MobPool mp{ s, env, N, s.m_next_bullet[env], s.m_num_bullets[env], s.m_next_expl[env], s.m_num_expl[env], ctx.leader() };
         int a_next = s.a_next_bullet[env], a_num = s.a_num_bullets[env];
         float a_timer = s.a_bullet_timer[env];
         bool alive = s.alive[env] != 0;
@@ -183,9 +204,11 @@ struct BossFight {
                     if (a_timer == 0.0f && a_num < AB) {
                         a_timer = 5.0f;
                         int i = a_next * N + env;
-                        s.ab_vx[i] = 0.0f; s.ab_vy[i] = -0.1f;
-                        s.ab_x[i] = px; s.ab_y[i] = py;
-                        s.ab_frame[i] = 0.0f; s.ab_bouncing[i] = 0; s.ab_bounce_timer[i] = 0.0f;
+                        if (ctx.leader()) {
+                            s.ab_vx[i] = 0.0f; s.ab_vy[i] = -0.1f;
+                            s.ab_x[i] = px; s.ab_y[i] = py;
+                            s.ab_frame[i] = 0.0f; s.ab_bouncing[i] = 0; s.ab_bounce_timer[i] = 0.0f;
+                        }
                         a_next = (a_next + 1) % AB;
                         a_num++;
                     } else {
@@ -198,62 +221,95 @@ struct BossFight {
                     if (check_collision(wc, hazard_rect_at(k, hz_id[k]))) { alive = false; break; }
                 }
 
-                // same software pipelining as the boss's bullets below: bullet i + 1 is fetched before bullet i is stored
-                float af = -1.0f, anx = 0.0f, any_ = 0.0f, anvx = 0.0f, anvy = 0.0f, anbt = 0.0f;
-                bool anb = false;
-                if (a_num > 0) {
-                    const int b0 = ((AB + a_next - 1) % AB) * N + env;
-                    af = s.ab_frame[b0]; anx = s.ab_x[b0]; any_ = s.ab_y[b0]; anvx = s.ab_vx[b0]; anvy = s.ab_vy[b0];
-                    anb = s.ab_bouncing[b0] != 0; anbt = s.ab_bounce_timer[b0];
-                }
-                for (int i = 0; i < a_num; i++) {
-                    int bi = ((AB + a_next - 1 - i) % AB) * N + env;
-                    float frame = af;
-                    float x = anx, y = any_, vx = anvx, vy = anvy;
-                    bool bouncing = anb;
-                    float btimer = anbt;
-                    if (i + 1 < a_num) {
-                        const int bn = ((AB + a_next - 2 - i) % AB) * N + env;
-                        af = s.ab_frame[bn]; anx = s.ab_x[bn]; any_ = s.ab_y[bn]; anvx = s.ab_vx[bn]; anvy = s.ab_vy[bn];
-                        anb = s.ab_bouncing[bn] != 0; anbt = s.ab_bounce_timer[bn];
-                    }
-                    if (frame == -1.0f) continue;
-                    if (frame == 0.0f) {
-                        Rect bw{ __fsub_rn(x, 0.01f), __fsub_rn(y, 0.01f), 0.02f, 0.02f };
-                        if (!check_collision(bw, screen)) { vx = 0.0f; vy = 0.0f; frame = 5.0f; }
-                        else {
+                // The agent's bullets, lane-parallel (ring slot i on lane i % nlanes). Pass 1: what would happen to each bullet
+                // if it is visited (destroyed? bounces off the shield = one RNG draw? hits the unshielded boss?) — none of it
+                // depends on the other bullets; the visited prefix follows from the destroyed bits; the bounce draws are made
+                // in ring order by all lanes; pass 2 applies and stores.
+                ctx.sync();   // the leader's store of a bullet fired above
+                {
+                    const int n0 = a_num;
+                    auto slot = [&](int i) { return ((AB + a_next - 1 - i) % AB) * N + env; };
+                    auto first_hazard = [&](const Rect& bw) {   // index into the hazard list of the first one hit, -1: none
 #pragma unroll
-                            for (int k = 0; k < 8; k++) {
-                                if (k >= nhaz) break;
-                                int h = hz_id[k];
-                                if (check_collision(bw, hazard_rect_at(k, h))) {
-                                    if (h == 1) {
-                                        if (phase_index % 2 == 0) {   // shielded: bounce
-                                            vx = __fmul_rn(rng.uniform_real(-1.0f, 1.0f), 0.05f);
-                                            vy = 0.05f;
-                                            btimer = 10.0f; bouncing = true;
-                                        } else {
-                                            vx = 0.0f; vy = 0.0f; frame = 1.0f;
-                                            if (hp > 0) hp--;
-                                        }
-                                    } else { vx = 0.0f; vy = 0.0f; frame = 1.0f; }
-                                    break;
+                        for (int k = 0; k < 8; k++) {
+                            if (k >= nhaz) break;
+                            if (check_collision(bw, hazard_rect_at(k, hz_id[k]))) return k;
+                        }
+                        return -1;
+                    };
+                    uint64_t D = 0ull, R = 0ull, B = 0ull;
+                    for (int i = ctx.lane; i < n0; i += ctx.nlanes) {
+                        const int bi = slot(i);
+                        float frame = s.ab_frame[bi];
+                        if (frame == -1.0f) continue;
+                        bool bouncing = s.ab_bouncing[bi] != 0;
+                        float btimer = s.ab_bounce_timer[bi];
+                        if (frame == 0.0f) {
+                            const float x = s.ab_x[bi], y = s.ab_y[bi];
+                            Rect bw{ __fsub_rn(x, 0.01f), __fsub_rn(y, 0.01f), 0.02f, 0.02f };
+                            if (!check_collision(bw, screen)) frame = 5.0f;
+                            else {
+                                const int k = first_hazard(bw);
+                                if (k >= 0) {
+                                    if (hz_id[k] == 1) {
+                                        if (phase_index % 2 == 0) { R |= 1ull << i; btimer = 10.0f; bouncing = true; }
+                                        else { frame = 1.0f; B |= 1ull << i; }
+                                    } else frame = 1.0f;
                                 }
                             }
                         }
+                        if (frame >= 5.0f || (bouncing && !(btimer > 0.0f))) D |= 1ull << i;
                     }
-                    x = __fadd_rn(x, __fmul_rn(vx, dt));
-                    y = __fadd_rn(y, __fmul_rn(vy, dt));
-                    bool destroy = false;
-                    if (frame >= 5.0f) destroy = true;
-                    else if (frame >= 1.0f) frame = __fadd_rn(frame, __fmul_rn(0.3f, dt));
-                    if (bouncing) {
-                        if (btimer > 0.0f) btimer = fmaxf(0.0f, __fsub_rn(btimer, dt));
-                        else destroy = true;
+                    D = ctx.or64(D); R = ctx.or64(R); B = ctx.or64(B);
+                    const int nvis = visited_prefix(D, n0);
+                    const uint64_t vis = nvis >= 64 ? ~0ull : (1ull << nvis) - 1ull;
+                    // bounce velocities: one draw per bouncing bullet, in ring order (uniform: every lane draws them all); the
+                    // lane that owns the bullet stores the bounced vx right away and re-reads it in pass 2
+                    for (uint64_t m = R & vis; m; m &= m - 1ull) {
+                        const int i = __ffsll((long long)m) - 1;
+                        const float r = rng.uniform_real(-1.0f, 1.0f);
+                        if (i % ctx.nlanes == ctx.lane) s.ab_vx[slot(i)] = __fmul_rn(r, 0.05f);
                     }
-                    if (destroy) { a_num--; frame = -1.0f; }
-                    s.ab_x[bi] = x; s.ab_y[bi] = y; s.ab_vx[bi] = vx; s.ab_vy[bi] = vy; s.ab_frame[bi] = frame;
-                    s.ab_bouncing[bi] = bouncing; s.ab_bounce_timer[bi] = btimer;
+                    {   // `if (hp > 0) hp--` per bullet that hits the unshielded boss
+                        const int hits = __popcll(B & vis);
+                        if (hits) hp = hp > hits ? hp - hits : 0;
+                    }
+                    for (int i = ctx.lane; i < nvis; i += ctx.nlanes) {
+                        const int bi = slot(i);
+                        float frame = s.ab_frame[bi];
+                        if (frame == -1.0f) continue;
+                        float x = s.ab_x[bi], y = s.ab_y[bi], vx = s.ab_vx[bi], vy = s.ab_vy[bi];
+                        bool bouncing = s.ab_bouncing[bi] != 0;
+                        float btimer = s.ab_bounce_timer[bi];
+                        if (frame == 0.0f) {
+                            Rect bw{ __fsub_rn(x, 0.01f), __fsub_rn(y, 0.01f), 0.02f, 0.02f };
+                            if (!check_collision(bw, screen)) { vx = 0.0f; vy = 0.0f; frame = 5.0f; }
+                            else {
+                                const int k = first_hazard(bw);
+                                if (k >= 0) {
+                                    if (hz_id[k] == 1 && phase_index % 2 == 0) {   // shielded: bounce
+                                        // (vx: the bounced value, stored by the draw loop above)
+                                        vy = 0.05f;
+                                        btimer = 10.0f; bouncing = true;
+                                    } else { vx = 0.0f; vy = 0.0f; frame = 1.0f; }
+                                }
+                            }
+                        }
+                        x = __fadd_rn(x, __fmul_rn(vx, dt));
+                        y = __fadd_rn(y, __fmul_rn(vy, dt));
+                        bool destroy = false;
+                        if (frame >= 5.0f) destroy = true;
+                        else if (frame >= 1.0f) frame = __fadd_rn(frame, __fmul_rn(0.3f, dt));
+                        if (bouncing) {
+                            if (btimer > 0.0f) btimer = fmaxf(0.0f, __fsub_rn(btimer, dt));
+                            else destroy = true;
+                        }
+                        if (destroy) frame = -1.0f;
+                        s.ab_x[bi] = x; s.ab_y[bi] = y; s.ab_vx[bi] = vx; s.ab_vy[bi] = vy; s.ab_frame[bi] = frame;
+                        s.ab_bouncing[bi] = bouncing; s.ab_bounce_timer[bi] = btimer;
+                    }
+                    a_num = n0 - __popcll(D & vis);
+                    ctx.sync();
                 }
                 agent_alive = alive;
             }
@@ -349,48 +405,60 @@ struct BossFight {
                 bx = __fadd_rn(bx, __fmul_rn(bvx, dt));
                 by = __fadd_rn(by, __fmul_rn(bvy, dt));
 
-                // The ring is walked newest to oldest; bullet i + 1 is fetched BEFORE bullet i is stored (a store cannot be
-                // proven not to alias the next load, which would put one L2 round trip between consecutive bullets).
-                float nf = -1.0f, nx = 0.0f, ny = 0.0f, nvx = 0.0f, nvy = 0.0f;
-                if (mp.num_bullets > 0) {
-                    const int b0 = ((MB + mp.next_bullet - 1) % MB) * N + env;
-                    nf = s.mb_frame[b0]; nx = s.mb_x[b0]; ny = s.mb_y[b0]; nvx = s.mb_vx[b0]; nvy = s.mb_vy[b0];
-                }
-                for (int i = 0; i < mp.num_bullets; i++) {
-                    int bi = ((MB + mp.next_bullet - 1 - i) % MB) * N + env;
-                    float frame = nf;
-                    float x = nx, y = ny, vx = nvx, vy = nvy;
-                    if (i + 1 < mp.num_bullets) {   // distinct ring slot: not touched by this iteration's stores
-                        const int bn = ((MB + mp.next_bullet - 2 - i) % MB) * N + env;
-                        nf = s.mb_frame[bn]; nx = s.mb_x[bn]; ny = s.mb_y[bn]; nvx = s.mb_vx[bn]; nvy = s.mb_vy[bn];
-                    }
-                    if (frame == -1.0f) continue;
-                    bool stop = false;
-                    if (frame == 0.0f) {
-                        Rect bw{ __fsub_rn(x, 0.01f), __fsub_rn(y, 0.01f), 0.02f, 0.02f };
-                        if (!check_collision(bw, screen)) { vx = 0.0f; vy = 0.0f; frame = 5.0f; }
-                        else if (check_collision(bw, agent_rect)) {
-                            vx = 0.0f; vy = 0.0f; frame = 1.0f;
-                            alive = false;
-                            stop = true;   // `break` leaves the bullet loop: this bullet is not moved either
-                        } else {
+                // The boss's bullets, lane-parallel like the agent's: pass 1 finds, per bullet, whether a visit destroys it or
+                // hits the agent (that visit ends the walk: `break`, common_systems.cpp:345-352), pass 2 applies and stores.
+                ctx.sync();   // the leader's stores of the bullets fired above
+                {
+                    const int n0 = mp.num_bullets;
+                    auto slot = [&](int i) { return ((MB + mp.next_bullet - 1 - i) % MB) * N + env; };
+                    auto hits_barrier = [&](const Rect& bw) {
 #pragma unroll
-                            for (int k = 0; k < 8; k++) {
-                                if (k >= nhaz) break;
-                                int h = hz_id[k];
-                                if (h == 1) continue;
-                                if (check_collision(bw, hazard_rect_at(k, h))) { vx = 0.0f; vy = 0.0f; frame = 1.0f; break; }
-                            }
+                        for (int k = 0; k < 8; k++) {
+                            if (k >= nhaz) break;
+                            if (hz_id[k] == 1) continue;
+                            if (check_collision(bw, hazard_rect_at(k, hz_id[k]))) return true;
                         }
+                        return false;
+                    };
+                    uint64_t D = 0ull, H = 0ull;
+                    for (int i = ctx.lane; i < n0; i += ctx.nlanes) {
+                        const int bi = slot(i);
+                        float frame = s.mb_frame[bi];
+                        if (frame == -1.0f) continue;
+                        if (frame == 0.0f) {
+                            const float x = s.mb_x[bi], y = s.mb_y[bi];
+                            Rect bw{ __fsub_rn(x, 0.01f), __fsub_rn(y, 0.01f), 0.02f, 0.02f };
+                            if (!check_collision(bw, screen)) frame = 5.0f;
+                            else if (check_collision(bw, agent_rect)) { H |= 1ull << i; frame = 1.0f; }
+                        }
+                        if (frame >= 5.0f) D |= 1ull << i;
                     }
-                    if (!stop) {
-                        x = __fadd_rn(x, __fmul_rn(vx, dt));
-                        y = __fadd_rn(y, __fmul_rn(vy, dt));
-                        if (frame >= 5.0f) { mp.num_bullets--; frame = -1.0f; }
-                        else if (frame >= 1.0f) frame = __fadd_rn(frame, __fmul_rn(0.3f, dt));
+                    D = ctx.or64(D); H = ctx.or64(H);
+                    int nvis = visited_prefix(D, n0);
+                    uint64_t vis = nvis >= 64 ? ~0ull : (1ull << nvis) - 1ull;
+                    int stop_at = -1;   // the visited bullet that hits the agent: stored unmoved, ends the walk
+                    if (H & vis) { stop_at = __ffsll((long long)(H & vis)) - 1; nvis = stop_at + 1; vis = (1ull << nvis) - 1ull; alive = false; }
+                    for (int i = ctx.lane; i < nvis; i += ctx.nlanes) {
+                        const int bi = slot(i);
+                        float frame = s.mb_frame[bi];
+                        if (frame == -1.0f) continue;
+                        float x = s.mb_x[bi], y = s.mb_y[bi], vx = s.mb_vx[bi], vy = s.mb_vy[bi];
+                        if (frame == 0.0f) {
+                            Rect bw{ __fsub_rn(x, 0.01f), __fsub_rn(y, 0.01f), 0.02f, 0.02f };
+                            if (!check_collision(bw, screen)) { vx = 0.0f; vy = 0.0f; frame = 5.0f; }
+                            else if (i == stop_at) { vx = 0.0f; vy = 0.0f; frame = 1.0f; }
+                            else if (hits_barrier(bw)) { vx = 0.0f; vy = 0.0f; frame = 1.0f; }
+                        }
+                        if (i != stop_at) {
+                            x = __fadd_rn(x, __fmul_rn(vx, dt));
+                            y = __fadd_rn(y, __fmul_rn(vy, dt));
+                            if (frame >= 5.0f) frame = -1.0f;
+                            else if (frame >= 1.0f) frame = __fadd_rn(frame, __fmul_rn(0.3f, dt));
+                        }
+                        s.mb_x[bi] = x; s.mb_y[bi] = y; s.mb_vx[bi] = vx; s.mb_vy[bi] = vy; s.mb_frame[bi] = frame;
                     }
-                    s.mb_x[bi] = x; s.mb_y[bi] = y; s.mb_vx[bi] = vx; s.mb_vy[bi] = vy; s.mb_frame[bi] = frame;
-                    if (stop) break;
+                    mp.num_bullets = n0 - __popcll(D & vis & ~(stop_at >= 0 ? 1ull << stop_at : 0ull));
+                    ctx.sync();
                 }
                 for (int i = 0; i < mp.num_expl; i++) {
                     int ei = ((NEX + mp.next_expl - 1 - i) % NEX) * N + env;
@@ -398,24 +466,26 @@ struct BossFight {
                     if (frame == -1.0f) continue;
                     if (frame >= 4.0f) { mp.num_expl--; frame = -1.0f; }
                     else if (frame >= 0.0f) frame = __fadd_rn(frame, __fmul_rn(0.3f, dt));
-                    s.ex_frame[ei] = frame;
+                    if (ctx.leader()) s.ex_frame[ei] = frame;
                 }
                 if (phase_index >= 6) boss_alive = false;
             }
             if (!agent_alive || !boss_alive) break;
         }
 
-        s.px[env] = px; s.py[env] = py; s.pvx[env] = pvx; s.pvy[env] = pvy;
-        s.bx[env] = bx; s.by[env] = by; s.bvx[env] = bvx; s.bvy[env] = bvy;
-        s.phase_timer[env] = phase_timer; s.attack_timer[env] = attack_timer;
-        s.phase_index[env] = phase_index; s.weapon_index[env] = weapon_index; s.hp[env] = hp;
-        s.expl_timer[env] = expl_timer; s.damage_timer[env] = damage_timer; s.move_timer[env] = move_timer;
-        s.m_next_bullet[env] = mp.next_bullet; s.m_num_bullets[env] = mp.num_bullets;
-        s.m_next_expl[env] = mp.next_expl; s.m_num_expl[env] = mp.num_expl;
-        s.a_next_bullet[env] = a_next; s.a_num_bullets[env] = a_num; s.a_bullet_timer[env] = a_timer;
-        s.alive[env] = alive;
-        c.mti[env] = rng.idx;
-        c.sprites_valid[env] = 1;
+        if (ctx.leader()) {
+            s.px[env] = px; s.py[env] = py; s.pvx[env] = pvx; s.pvy[env] = pvy;
+            s.bx[env] = bx; s.by[env] = by; s.bvx[env] = bvx; s.bvy[env] = bvy;
+            s.phase_timer[env] = phase_timer; s.attack_timer[env] = attack_timer;
+            s.phase_index[env] = phase_index; s.weapon_index[env] = weapon_index; s.hp[env] = hp;
+            s.expl_timer[env] = expl_timer; s.damage_timer[env] = damage_timer; s.move_timer[env] = move_timer;
+            s.m_next_bullet[env] = mp.next_bullet; s.m_num_bullets[env] = mp.num_bullets;
+            s.m_next_expl[env] = mp.next_expl; s.m_num_expl[env] = mp.num_expl;
+            s.a_next_bullet[env] = a_next; s.a_num_bullets[env] = a_num; s.a_bullet_timer[env] = a_timer;
+            s.alive[env] = alive;
+            c.mti[env] = rng.idx;
+            c.sprites_valid[env] = 1;
+        }
         // (!agent_alive) * -10.0f + (!boss_alive) * 10.0f
         *reward = __fadd_rn(__fmul_rn((float)(!agent_alive), -10.0f), __fmul_rn((float)(!boss_alive), 10.0f));
         return !agent_alive || !boss_alive;

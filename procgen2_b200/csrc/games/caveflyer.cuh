@@ -43,6 +43,7 @@ struct CaveFlyer {
     static constexpr int W = 40, H = 40, MAX_OBJ = 64, NB = 32, NPART = 10;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = false;   // step() supports warp-per-env (ctx) but measures faster thread-per-env (r01j)
+    static constexpr int STEP_LANES = 32;       // (lane-aware games only) lanes per environment in k_step
     static constexpr int MAX_POST = 112;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
@@ -51,6 +52,7 @@ struct CaveFlyer {
     static const char* reset_keeps() { return " cam_x cam_y "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 11;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int BLIT_UNROLL = 1;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
     static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
     static bool mode_supported(int mode) { return mode == 1; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer

@@ -43,6 +43,7 @@ struct Chaser {
     static constexpr int W = 11, H = 11, MAX_ENTS = 72, NMOB = 3;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = true;    // step(): the point loop is strided over ctx's lanes, the rest is uniform
+    static constexpr int STEP_LANES = 32;       // lanes per environment in k_step
     static constexpr int MAX_POST = 80;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
@@ -51,6 +52,7 @@ struct Chaser {
     static const char* reset_keeps() { return ""; }
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 14;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int BLIT_UNROLL = 1;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
     static constexpr int DEFAULT_MODE = 0;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
     static bool mode_supported(int mode) { return mode == 0; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer

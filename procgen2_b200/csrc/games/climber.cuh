@@ -41,6 +41,7 @@ struct Climber {
     static constexpr int W = 20, H = 64, MAX_ENTS = 40;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = true;    // step(): per-entity loops are strided over ctx's lanes
+    static constexpr int STEP_LANES = 32;       // lanes per environment in k_step
     static constexpr int MAX_POST = 48;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
@@ -49,6 +50,7 @@ struct Climber {
     static const char* reset_keeps() { return " cam_y "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 2;   // wall_mid textures are 64x64, one wall_top texture is 64x53
     static constexpr int WIN_ROWS = 23;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int BLIT_UNROLL = 1;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
     static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
     static bool mode_supported(int mode) { return mode == 0 || mode == 1; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer

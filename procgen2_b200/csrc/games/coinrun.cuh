@@ -57,6 +57,7 @@ struct CoinRun {
     static constexpr int W = 64, H = 64, MAX_ENTS = 40, NPART = 10;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = true;    // step(): per-entity loops are strided over ctx's lanes
+    static constexpr int STEP_LANES = 32;       // lanes per environment in k_step
     static constexpr int MAX_POST = 192;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
@@ -65,6 +66,7 @@ struct CoinRun {
     static const char* reset_keeps() { return " cam_x cam_y "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 16;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int BLIT_UNROLL = 1;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
     static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
     static bool mode_supported(int mode) { return mode == 0 || mode == 1; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer

@@ -32,6 +32,7 @@ struct Maze {
     static constexpr int WORLD = 25;          // world_dim (tilemap.cpp:36)
     static constexpr int TIMEOUT = 500;       // maze.cpp:49
     static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
+    static constexpr int STEP_LANES = 32;       // (lane-aware games only) lanes per environment in k_step
     static constexpr int MAX_POST = 4;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
@@ -40,6 +41,7 @@ struct Maze {
     static const char* reset_keeps() { return "  "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 28;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int BLIT_UNROLL = 1;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
     static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
     static bool mode_supported(int mode) { return mode == 1; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer

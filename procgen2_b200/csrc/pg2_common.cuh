@@ -18,11 +18,15 @@ constexpr int OBS_W = 64, OBS_H = 64, OBS_BYTES = 64 * 64 * 3;
 // How ONE environment's cenv_step is spread over threads: nlanes == 1 (one thread owns the environment:
 // thread-per-env mapping, host-sim) or nlanes == WARP_LANES (a whole warp owns it: per-entity loops are strided
 // over the lanes, everything else is computed redundantly by all lanes, which therefore stay converged).
+// nlanes may also be a PART of a warp (8 or 16 lanes, `mask` = the group's lanes): several environments share a warp, each
+// with its own lane group — the uniform code then issues once for all of them.
 struct StepCtx {
     int lane, nlanes;
-    PG2_DEV bool any(bool p) const { return nlanes == 1 ? p : warp_any(p); }
-    PG2_DEV int sum(int v) const { return nlanes == 1 ? v : warp_sum(v); }
-    PG2_DEV void sync() const { if (nlanes != 1) __syncwarp(); }
+    uint32_t mask = 0xffffffffu;
+    PG2_DEV bool any(bool p) const { return nlanes == 1 ? p : group_any(mask, p); }
+    PG2_DEV int sum(int v) const { return nlanes == 1 ? v : group_sum(mask, v); }
+    PG2_DEV uint64_t or64(uint64_t v) const { return nlanes == 1 ? v : (uint64_t)group_or(mask, (uint32_t)v) | (uint64_t)group_or(mask, (uint32_t)(v >> 32)) << 32; }
+    PG2_DEV void sync() const { if (nlanes != 1) group_sync(mask); }
     PG2_DEV bool leader() const { return lane == 0; }
 };
 

@@ -71,7 +71,7 @@ __device__ unsigned long long g_phase[8];
 #endif
 
 template <class G>
-using FrameOf = FrameT<G::MAX_POST, G::ROTATES, G::TILE_CLASSES, G::WIN_ROWS>;
+using FrameOf = FrameT<G::MAX_POST, G::ROTATES, G::TILE_CLASSES, G::WIN_ROWS, G::BLIT_UNROLL>;
 
 // render_game(true) + RGBA->RGB pack for one env by one CTA (f.tileword filled by frame_init_tiletex before).
 // view_cache (G::STATIC_VIEW games, else nullptr): VIEW_CACHE_BYTES per env = the env's base image;

@@ -26,6 +26,11 @@ constexpr int WARP_LANES = 32;
 __device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 __device__ __forceinline__ int warp_bcast(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+// the same over a lane group (mask = its lanes; every lane of the group calls with the same mask)
+__device__ __forceinline__ bool group_any(uint32_t mask, bool p) { return __any_sync(mask, p) != 0; }
+__device__ __forceinline__ int group_sum(uint32_t mask, int v) { return __reduce_add_sync(mask, v); }
+__device__ __forceinline__ uint32_t group_or(uint32_t mask, uint32_t v) { return __reduce_or_sync(mask, v); }
+__device__ __forceinline__ void group_sync(uint32_t mask) { __syncwarp(mask); }
 // atomicAdd on a counter known to live in shared memory (a generic-address atomic costs an address-space dispatch)
 __device__ __forceinline__ int smem_atomic_inc(int* p) {
     int old;
@@ -84,9 +89,15 @@ inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f;
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int __ffs(uint32_t m) { return __builtin_ffs((int)m); }
 inline int __popc(uint32_t m) { return __builtin_popcount(m); }
+inline int __popcll(uint64_t m) { return __builtin_popcountll(m); }
+inline int __ffsll(long long m) { return __builtin_ffsll(m); }
 inline int __clz(uint32_t m) { return m ? __builtin_clz(m) : 32; }
 inline uint32_t __ballot_sync(uint32_t, int pred) { return pred ? 1u : 0u; }
 inline bool warp_any(bool p) { return p; }
+inline bool group_any(uint32_t, bool p) { return p; }
+inline int group_sum(uint32_t, int v) { return v; }
+inline uint32_t group_or(uint32_t, uint32_t v) { return v; }
+inline void group_sync(uint32_t) {}
 inline int warp_sum(int v) { return v; }
 inline int warp_bcast(int v) { return v; }
 inline float warp_bcast(float v) { return v; }

@@ -108,9 +108,10 @@ constexpr uint32_t RC_ADDR_MASK = 0x0fffffffu, RC_AMBIGUOUS = 1u << 28, RC_PRESE
 
 // Frame description of ONE environment, in shared memory. MAXP = capacity of the post-blit list (per game),
 // ROT = whether the game ever rotates a blit (bossfight, caveflyer, jumper HUD).
-template <int MAXP, bool ROT, int NCLS, int WINR_>
+template <int MAXP, bool ROT, int NCLS, int WINR_, int UNROLL_ = 1>
 struct FrameT {
     static constexpr int MAX_POST = MAXP, NROT = ROT ? MAXP : 1, WINR = WINR_;
+    static constexpr int BLIT_UNROLL = UNROLL_;   // 8x4 patches of an un-rotated post blit whose texel fetches are in flight together
     static constexpr bool ROTATES = ROT;
     alignas(128) uint32_t band_px[RENDER_THREADS / 32][BAND_PX];     // per warp: the band it is drawing, RGBA words (packed to RGB in place before the store)
     alignas(16) uint32_t rowcell[(WINR_ + 1) * OBS_W];                // [tile row of the window][screen column], + the always-empty row
@@ -925,13 +926,44 @@ PG2_DEV void draw_blit_band(F& f, const uint32_t* __restrict__ atlas, int k, int
     }
     x0 = max(x0, 0); x1 = min(x1, OBS_W - 1); y0 = max(y0, Y0); y1 = min(y1, Y0 + BAND_ROWS - 1);
     const uint32_t blend = fb.flags & 1u, alpha_mod = fb.alpha_mod;
+    if (!(F::ROTATES && (fb.flags & 2u))) {
+        // un-rotated: F::BLIT_UNROLL patches side by side per round, all texel fetches issued before the first blend (games with
+        // large sprites: bossfight + 3.5 %; small-sprite games measured 3-10 % slower with it and keep 1)
+        for (int yb = y0; yb <= y1; yb += 4)
+            for (int xb = x0; xb <= x1; xb += 8 * F::BLIT_UNROLL)
+                for (int l = lane; l < 32; l += WARP_LANES) {
+                    const int Y = yb + (l >> 3);
+                    const uint32_t j = (uint32_t)(Y - fb.y0);
+                    const bool row_ok = Y <= y1 && j < fb.h;
+                    const uint32_t row = fb.base + ((fb.hy + j * fb.incy) >> 16) * fb.tex_w;
+                    uint32_t texel[F::BLIT_UNROLL];
+                    bool ok[F::BLIT_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < F::BLIT_UNROLL; u++) {
+                        const int X = xb + 8 * u + (l & 7);
+                        const uint32_t i = (uint32_t)(X - fb.x0);
+                        ok[u] = row_ok && X <= x1 && i < fb.w;
+                        texel[u] = ok[u] ? __ldg(atlas + row + ((fb.hx + i * fb.incx) >> 16)) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < F::BLIT_UNROLL; u++) {
+                        if (!ok[u]) continue;
+                        const uint32_t a = blend ? layer_alpha(texel[u], blend, alpha_mod) : 255u;   // an opaque-copy texture ignores the alpha mod
+                        uint32_t* px = buf + (Y - Y0) * OBS_W + xb + 8 * u + (l & 7);
+                        if (a == 255u) *px = texel[u];
+                        else if (a != 0u) *px = blend_word(*px, texel[u], a);
+                    }
+                }
+        __syncwarp();
+        return;
+    }
     for (int yb = y0; yb <= y1; yb += 4)
         for (int xb = x0; xb <= x1; xb += 8)
             for (int l = lane; l < 32; l += WARP_LANES) {
                 const int X = xb + (l & 7), Y = yb + (l >> 3);
                 uint32_t texel;
                 if (X <= x1 && Y <= y1 && fast_texel<F::ROTATES>(fb, rot, atlas, X, Y, &texel)) {
-                    const uint32_t a = blend ? layer_alpha(texel, blend, alpha_mod) : 255u;   // an opaque-copy texture ignores the alpha mod
+                    const uint32_t a = blend ? layer_alpha(texel, blend, alpha_mod) : 255u;
                     uint32_t* px = buf + (Y - Y0) * OBS_W + X;
                     if (a == 255u) *px = texel;
                     else if (a != 0u) *px = blend_word(*px, texel, a);

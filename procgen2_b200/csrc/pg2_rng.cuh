@@ -18,6 +18,10 @@ constexpr int MT_M = 397;
 struct Mt {
     uint32_t* mt;
     int idx;
+    // warp-per-env step kernels run the generator redundantly on all 32 lanes (identical idx): `collective` makes the
+    // in-place twist of the shared global state a one-lane job (`writer`) followed by a warp barrier
+    bool collective = false, writer = true;
+    uint32_t sync_mask = 0xffffffffu;   // the lanes that run this generator together
 
     PG2_DEV static uint32_t mix(uint32_t u, uint32_t v, uint32_t m) {
         uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
@@ -33,7 +37,10 @@ struct Mt {
     }
 
     PG2_DEV uint32_t next() {
-        if (idx >= MT_N) twist_serial();
+        if (idx >= MT_N) {
+            if (!collective) twist_serial();
+            else { if (writer) twist_serial(); idx = 0; group_sync(sync_mask); }
+        }
         uint32_t y = mt[idx++];
         y ^= (y >> 11);
         y ^= (y << 7) & 0x9d2c5680u;

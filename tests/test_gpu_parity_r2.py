@@ -83,7 +83,7 @@ def test_step_epw_live_oracle(game, epw, oracle_available, monkeypatch):
 
 
 def test_bossfight_16384_sampled_oracle(oracle_available):
-    """BASELINE configs[2] as the engine runs it (16 384 envs => 2 environments per warp chosen by the engine itself):
+    """BASELINE configs[2] as the engine runs it (16 384 envs, warp-per-env step with the bullet rings on the lanes):
     64 sampled envs, 50 steps, against reference processes with the same seeds."""
     ref_env = _need_oracle(oracle_available)
     from procgen2_b200.engine import BatchedEnv
@@ -91,7 +91,7 @@ def test_bossfight_16384_sampled_oracle(oracle_available):
     rs = np.random.RandomState(8)
     acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
     env = BatchedEnv("bossfight", n, seed=seed)
-    assert env.step_epw == 2
+    assert env.step_epw == 1      # lane-aware since round 2: a whole warp per environment, bullets on the lanes
     idx = np.sort(rs.choice(n, 64, replace=False))
     idx[:4] = [0, 1, n - 2, n - 1]
     idx = np.unique(idx)
