@@ -5,7 +5,11 @@
 #include <memory>
 extern std::shared_ptr<System_Tilemap> tilemap;
 extern std::shared_ptr<System_Agent> agent;
+extern System_Tilemap::Config tilemap_config;   /* games/maze/maze.cpp: the generator's compile-time Config, a global */
 extern "C" {
+/* A probe that WRITES: selects a distribution mode the reference only offers at compile time (tilemap.h Config::mode) —
+ * call before cenv_make. */
+void pg2o_set_mode(int mode) { tilemap_config.mode = (Distribution_Mode)mode; }
 void pg2o_tile_dims(int* wh) { wh[0] = tilemap->get_width(); wh[1] = tilemap->get_height(); }
 /* out[x * h + y] = tile id at map position (x, y) — the reference's own column-major order */
 void pg2o_tiles(int32_t* out) {

@@ -74,7 +74,7 @@ class RefEnv:
     """One reference environment (one private copy of lib<Game>.so)."""
     _count = 0
 
-    def __init__(self, game, seed, width=None, height=None, easy_mode=None):
+    def __init__(self, game, seed, width=None, height=None, easy_mode=None, mode=None):
         d = _prepare()
         RefEnv._count += 1
         self.game = game
@@ -86,6 +86,8 @@ class RefEnv:
         self.lib.cenv_step.argtypes = [ctypes.POINTER(KeyValue), ctypes.c_int32]
         if easy_mode is not None:   # compile-time Config::easy_mode of the generator (coinrun, climber), set through the probe
             self.probe("pg2o_set_easy_mode", None, [ctypes.c_int])(1 if easy_mode else 0)
+        if mode is not None:        # compile-time Config::mode (maze, chaser, jumper, caveflyer): 0 easy, 1 hard, 2 memory / extreme
+            self.probe("pg2o_set_mode", None, [ctypes.c_int])(int(mode))
         opts = [(b"seed", int(seed))] + ([(b"width", int(width))] if width else []) + ([(b"height", int(height))] if height else [])
         arr = (Option * len(opts))()
         for i, (k, v) in enumerate(opts):

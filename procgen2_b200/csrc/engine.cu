@@ -67,9 +67,10 @@ __global__ void k_seed(CommonState c, int N, uint32_t base_seed, const int32_t* 
 }
 
 // Level prefetch (G::PREFETCH_LEVELS): the NEXT level of every env is generated one episode ahead into a shadow copy of the
-// state (k_reset on the shadow state, asynchronous, second stream). When an env finishes, the warp that stepped it copies the
-// shadow's reset-written fields over the live ones right in k_step's tail (swap_env) and the env goes onto the generator's
-// list, which prepares the level after that. Field table: one entry per copied SoA field.
+// state (k_reset on the shadow state, asynchronous, second stream). When an env finishes, k_step makes sure that level exists
+// (swap_wait) and flags the env in `pending`; the render CTA that draws the env copies the shadow's reset-written fields over
+// the live ones first (swap_copy), and the env goes onto the generator's list, which prepares the level after that. Field
+// table: one entry per copied SoA field.
 struct SwapField { char* live; const char* shadow; int esz, per_env, env_major; };
 constexpr int MAX_SWAP_FIELDS = 64;
 struct SwapTable { SwapField f[MAX_SWAP_FIELDS]; int n; };
@@ -80,82 +81,79 @@ struct SwapArgs {
     int* used;                // [N] levels taken
 };
 
-// One warp, one finished env: wait until the generator has delivered the level this env is about to take (ready <=>
-// gen_done >= used; almost always true on arrival — the generator had a whole episode; the poll is bounded so that a logic
-// error can never hang the GPU: fault bit 4 instead), then copy the fields.
-__device__ __noinline__ void swap_env(const SwapArgs& a, const CommonState& live_c, int env, int N, int lane) {
-    if (lane == 0) {
-        const int need = a.used[env];
-        const volatile int* g = a.gen_done + env;
-        int spins = 0;
-        while (*g < need && spins < (1 << 18)) { __nanosleep(200); spins++; }
-        if (*g < need) live_c.fault[env] |= 4;
-        __threadfence();
-    }
-    __syncwarp();
-    // Loads are issued in batches before their stores (the compiler cannot prove that a store does not alias the next load,
-    // which would serialise one memory round trip per element): env-major fields (tile map, MT19937 words) 8 elements per
-    // lane at a time, slot-major fields (<= 32 elements each, usually 1) four fields at a time.
-    for (int i = 0; i < a.table.n; i++) {
-        const SwapField f = a.table.f[i];
-        if (!f.env_major) continue;
-        const size_t off = (size_t)env * f.per_env * f.esz;
-        const int bytes = f.per_env * f.esz;
-        if (((off | (size_t)bytes) & 3) == 0) {
-            uint32_t* dst = (uint32_t*)(f.live + off);
-            const uint32_t* src = (const uint32_t*)(f.shadow + off);
-            for (int b0 = 0; b0 < bytes / 4; b0 += 256) {
-                uint32_t v[8];
+// k_step, lane 0 of the warp / lane group that finished an env: wait until the generator has delivered the level this env is
+// about to take (ready <=> gen_done >= used; almost always true on arrival — the generator had a whole episode; the poll is
+// bounded so that a logic error can never hang the GPU: fault bit 4 instead). The wait sits in k_step, whose CTAs come and
+// go, never in the persistent render CTAs, which would keep the generator off the SMs.
+__device__ __forceinline__ void swap_wait(const SwapArgs& a, const CommonState& live_c, int env) {
+    const int need = a.used[env];
+    const volatile int* g = a.gen_done + env;
+    int spins = 0;
+    while (*g < need && spins < (1 << 18)) { __nanosleep(200); spins++; }
+    if (*g < need) live_c.fault[env] |= 4;
+    __threadfence();
+}
+
+// k_render, the whole CTA that is about to draw a finished env: copy the reset-written fields shadow -> live. Loads are issued
+// in batches before their stores (the compiler cannot prove that a store does not alias the next load, which would
+// serialise one memory round trip per element): short fields (<= blockDim elements per env) eight fields per round, one
+// element per thread; long ones (tile map, MT19937 words, particle pools) eight elements per thread per round.
+__device__ __noinline__ void swap_copy(const SwapArgs& a, const CommonState& live_c, int env, int N) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    __threadfence();
+    auto elem_off = [&](const SwapField& f, int j) { return f.env_major ? ((size_t)env * f.per_env + j) * f.esz : ((size_t)j * N + env) * f.esz; };
+    for (int i0 = 0; i0 < a.table.n; i0 += 8) {
+        uint32_t v[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) { const int idx = b0 + k * 32 + lane; v[k] = idx < bytes / 4 ? src[idx] : 0u; }
-#pragma unroll
-                for (int k = 0; k < 8; k++) { const int idx = b0 + k * 32 + lane; if (idx < bytes / 4) dst[idx] = v[k]; }
-            }
-        } else {
-            for (int b0 = 0; b0 < bytes; b0 += 256) {
-                uint8_t v[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) { const int idx = b0 + k * 32 + lane; v[k] = idx < bytes ? (uint8_t)f.shadow[off + idx] : (uint8_t)0; }
-#pragma unroll
-                for (int k = 0; k < 8; k++) { const int idx = b0 + k * 32 + lane; if (idx < bytes) f.live[off + idx] = (char)v[k]; }
-            }
-        }
-    }
-    for (int i0 = 0; i0 < a.table.n; i0 += 4) {
-        uint32_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 8; k++) {
             v[k] = 0u;
             if (i0 + k >= a.table.n) continue;
             const SwapField f = a.table.f[i0 + k];
-            if (f.env_major || lane >= f.per_env || f.per_env > 32) continue;
-            const size_t off = ((size_t)lane * N + env) * f.esz;
-            v[k] = f.esz == 4 ? *(const uint32_t*)(f.shadow + off) : f.esz == 1 ? (uint32_t)(uint8_t)f.shadow[off] : 0u;
+            if (f.per_env > nthr || tid >= f.per_env || (f.esz != 4 && f.esz != 1)) continue;
+            const size_t off = elem_off(f, tid);
+            v[k] = f.esz == 4 ? *(const uint32_t*)(f.shadow + off) : (uint32_t)(uint8_t)f.shadow[off];
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 8; k++) {
             if (i0 + k >= a.table.n) continue;
             const SwapField f = a.table.f[i0 + k];
-            if (f.env_major) continue;
-            if (f.per_env <= 32 && (f.esz == 4 || f.esz == 1)) {
-                if (lane < f.per_env) {
-                    const size_t off = ((size_t)lane * N + env) * f.esz;
-                    if (f.esz == 4) *(uint32_t*)(f.live + off) = v[k]; else f.live[off] = (char)v[k];
-                }
-            } else {   // long pools / odd element sizes: element j at [j * N + env]
-                for (int j = lane; j < f.per_env; j += 32) {
-                    const size_t off = ((size_t)j * N + env) * f.esz;
-                    for (int bb = 0; bb < f.esz; bb++) f.live[off + bb] = f.shadow[off + bb];
-                }
+            if (f.per_env > nthr || tid >= f.per_env || (f.esz != 4 && f.esz != 1)) continue;
+            const size_t off = elem_off(f, tid);
+            if (f.esz == 4) *(uint32_t*)(f.live + off) = v[k]; else f.live[off] = (char)v[k];
+        }
+    }
+    for (int i = 0; i < a.table.n; i++) {
+        const SwapField f = a.table.f[i];
+        if (f.per_env <= nthr && (f.esz == 4 || f.esz == 1)) continue;
+        if (f.esz != 4 && f.esz != 1) {   // odd element sizes (none today)
+            for (int j = tid; j < f.per_env; j += nthr) { const size_t off = elem_off(f, j); for (int bb = 0; bb < f.esz; bb++) f.live[off + bb] = f.shadow[off + bb]; }
+            continue;
+        }
+        // an env-major byte field whose per-env block is word-aligned is copied as words
+        const bool as_words = f.env_major && f.esz == 1 && ((((size_t)env * f.per_env) | (size_t)f.per_env | (size_t)(uintptr_t)f.live | (size_t)(uintptr_t)f.shadow) & 3) == 0;
+        const int count = as_words ? f.per_env / 4 : f.per_env, esz = as_words ? 4 : f.esz;
+        for (int j0 = 0; j0 < count; j0 += 8 * nthr) {
+            uint32_t u[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int j = j0 + q * nthr + tid;
+                const size_t off = f.env_major ? ((size_t)env * f.per_env * f.esz + (size_t)j * esz) : ((size_t)j * N + env) * esz;
+                u[q] = j >= count ? 0u : esz == 4 ? *(const uint32_t*)(f.shadow + off) : (uint32_t)(uint8_t)f.shadow[off];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int j = j0 + q * nthr + tid;
+                const size_t off = f.env_major ? ((size_t)env * f.per_env * f.esz + (size_t)j * esz) : ((size_t)j * N + env) * esz;
+                if (j < count) { if (esz == 4) *(uint32_t*)(f.live + off) = u[q]; else f.live[off] = (char)u[q]; }
             }
         }
     }
-    __syncwarp();
-    if (lane == 0) {   // what reset_body does besides the level
-        a.used[env] += 1;   // read by this env's next swap only
+    if (tid == 0) {   // what reset_body does besides the level
+        a.used[env] += 1;   // read by this env's next wait only
         live_c.ep_steps[env] = 0; live_c.view_valid[env] = 0;
         live_c.fault[env] |= a.shadow_c.fault[env];
     }
+    __syncthreads();   // the CTA reads what it just wrote
 }
 
 // Finished envs are appended to `list` (ballot + one atomic per warp on *count) and flagged in `pending` (an overlapped
@@ -204,10 +202,7 @@ __global__ void __launch_bounds__(128) k_step(typename G::State s, CommonState c
         if (lane == 0) base = atomicAdd(count, __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (done) list[base + __popc(m & ((1u << lane) - 1u))] = env;
-        if (swap.table.n > 0) {   // level prefetch: the finished envs take their next level now
-            __syncwarp();
-            for (unsigned mm = m; mm; mm &= mm - 1u) swap_env(swap, c, __shfl_sync(0xffffffffu, env, __ffs(mm) - 1), N, lane);
-        }
+        if (swap.table.n > 0 && done) swap_wait(swap, c, env);   // level prefetch: the env's next level exists (k_render copies it in)
     }
 }
 
@@ -226,7 +221,7 @@ __global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::
     for (int w = blockIdx.x * RESET_WARPS_PER_CTA + warp_in_cta; w < count; w += total_warps) {
         int env = reset_list ? reset_list[w] : w;
         reset_body<G>(s, c, env, mt, arena, lane);
-        if (gen_done != nullptr) {   // level prefetch: publish "the next level of env exists" (swap_env polls it)
+        if (gen_done != nullptr) {   // level prefetch: publish "the next level of env exists" (swap_wait polls it)
             __threadfence();
             __syncwarp();
             if (lane == 0) atomicAdd(&gen_done[env], 1);
@@ -245,29 +240,40 @@ __global__ void __launch_bounds__(RENDER_THREADS, PG2_RENDER_MIN_CTAS) k_render(
                                                            const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs,
                                                            int* __restrict__ ticket, int mode, const int* __restrict__ list,
                                                            const int* __restrict__ list_count, const uint8_t* __restrict__ pending, int N,
-                                                           uint8_t* __restrict__ view_cache) {
+                                                           uint8_t* __restrict__ view_cache, const __grid_constant__ SwapArgs swap) {
     __shared__ FrameOf<G> f;
     __shared__ int s_env;
     const int count = mode == 2 ? *list_count : N;
     frame_init_tiletex<G>(f, tex);
+    // thread 0: the next frame's env (-1: none left) and whether its cached base image is valid — both fetched one frame
+    // ahead, so that their memory round trips overlap the current frame's work (an env's view_valid only changes when the
+    // env itself is rendered, or in earlier kernels)
+    __shared__ int s_swap;
+    int next_env = -1;
+    bool next_reuse = false, next_swap = false;
+    // level prefetch: the envs that finished in this step (the list k_step appended them to) come first — their CTAs copy the
+    // next level in before drawing, which must not land in the kernel's tail — then every env that is not on the list
+    const int nfirst = (swap.table.n > 0 && mode == 0) ? *list_count : 0;
     auto take_ticket = [&]() {
         int t = atomicAdd(ticket, 1);
+        if (nfirst > 0) {
+            if (t < nfirst) { next_env = list[t]; next_swap = true; next_reuse = false; return; }
+            t -= nfirst;
+            while (t < count && pending[t]) t = atomicAdd(ticket, 1) - nfirst;
+        }
         if (mode == 1) while (t < count && pending[t]) t = atomicAdd(ticket, 1);
-        return t;
+        next_env = t < count ? (mode == 2 ? list[t] : t) : -1;
+        next_swap = false;
+        next_reuse = G::STATIC_VIEW && view_cache != nullptr && next_env >= 0 && !next_swap && c.view_valid[next_env] != 0;
     };
-    int next = 0;
-    if (threadIdx.x == 0) next = take_ticket();
+    if (threadIdx.x == 0) take_ticket();
     for (;;) {
 #ifdef PG2_PHASE_TIMERS
         long long phase_t__ = clock64();
 #endif
         __syncthreads();   // every warp is done with the previous frame (bands are stored per warp, without a CTA barrier)
-        bool reuse = false;
-        if (threadIdx.x == 0) {
-            s_env = next < count ? (mode == 2 ? list[next] : next) : -1;
-            reuse = G::STATIC_VIEW && view_cache != nullptr && s_env >= 0 && c.view_valid[s_env] != 0;
-        }
-        frame_begin(f, reuse);
+        if (threadIdx.x == 0) { s_env = next_env; s_swap = next_swap ? 1 : 0; }
+        frame_begin(f, next_reuse);
         __syncthreads();
         const int env = s_env;
         if (env < 0) break;
@@ -276,7 +282,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, PG2_RENDER_MIN_CTAS) k_render(
         if (threadIdx.x == 0) atomicAdd(&g_phase[0], 1ull);
 #endif
         // the next frame's ticket is taken now: the atomic's round trip overlaps this frame's work
-        if (threadIdx.x == 0) next = take_ticket();
+        const bool do_swap = s_swap != 0;
+        if (threadIdx.x == 0) take_ticket();
+        if (do_swap) swap_copy(swap, c, env, N);
         render_body<G>(s, c, env, f, tex, atlas, obs, view_cache, false);
     }
     if ((threadIdx.x & 31) == 0) frame_store_wait();   // every warp issued bulk stores of its own
@@ -376,7 +384,7 @@ struct EngineBase {
     int* prep_list = nullptr;        // [PREP_SLOTS][N]: private copy of a step's reset list for the asynchronous generator
     int* prep_count = nullptr;       // [PREP_SLOTS]
     int* gen_done = nullptr;         // [N] levels delivered by the generator (beyond the first)
-    int* gen_used = nullptr;         // [N] levels taken (swap_env)
+    int* gen_used = nullptr;         // [N] levels taken (swap_copy)
     int prep_slot = 0;
     cudaStream_t prep_streams[4] = { nullptr, nullptr, nullptr, nullptr };   // one per slot: the launches overlap
     cudaEvent_t ev_prepared[PREP_SLOTS] = { nullptr, nullptr, nullptr, nullptr };
@@ -553,7 +561,7 @@ struct Engine : EngineBase {
         return 0;
     }
 
-    // Fields swap_env copies from the shadow state: every field of the game state and mt / mti / sprites_valid (+ the camera
+    // Fields swap_copy copies from the shadow state: every field of the game state and mt / mti / sprites_valid (+ the camera
     // where reset() sets it), except the ones the game lists as persisting across reset() (G::reset_keeps()).
     int build_swap_table() {
         swap_table.n = 0;
@@ -619,7 +627,10 @@ struct Engine : EngineBase {
     void launch_render(int mode, int* ticket, cudaStream_t on) {
         const int per_sm = render_ctas_per_sm;
         int grid = N < num_sms * per_sm ? N : num_sms * per_sm;
-        k_render<G><<<grid, RENDER_THREADS, 0, on>>>(st, common, texinfo, atlas, obs, ticket, mode, reset_list, reset_count + parity, pending, N, view_cache);
+        // (level prefetch: the list / counter k_step appended this step's finished envs to)
+        const int* lst = prefetch && ka_list ? ka_list : reset_list;
+        const int* cnt = prefetch && ka_count ? ka_count : reset_count + parity;
+        k_render<G><<<grid, RENDER_THREADS, 0, on>>>(st, common, texinfo, atlas, obs, ticket, mode, lst, cnt, pending, N, view_cache, swap_args);
         launches++;
     }
 
@@ -635,6 +646,8 @@ struct Engine : EngineBase {
         launch_reset_all();
         if (init_shadow()) return 1;
         PG2_CUDA(cudaMemsetAsync(reset_count + 2, 0, 2 * sizeof(int), stream));
+        PG2_CUDA(cudaMemsetAsync(pending, 0, N, stream));   // no env of the last step is waiting for its level swap any more
+        ka_list = nullptr; ka_count = nullptr;              // ... and the render below has no swap list (reset_count[0..1] stay zero for these games)
         launch_render(0, reset_count + 2, stream);
         PG2_CUDA(cudaMemsetAsync(reward, 0, sizeof(float) * N, stream));
         PG2_CUDA(cudaMemsetAsync(terminated, 0, N, stream));
@@ -645,7 +658,7 @@ struct Engine : EngineBase {
 
     // ---- one step -------------------------------------------------------------------------------------------------
     // k_step -> k_reset (finished envs) -> k_render on the main stream. Level-prefetch games have no k_reset on that
-    // path: finished envs take their pre-generated level inside k_step (swap_env), and the level after that is generated on
+    // path: finished envs take their pre-generated level in the render CTA that draws them (swap_copy; k_step waits for it to exist), and the level after that is generated on
     // a second stream while the following steps run — up to PREP_SLOTS generator launches in flight, each with a private
     // list (k_step appends to the slot's list directly); an env that finishes again before its next level exists
     // (episodes shorter than a generation) is waited for individually.
@@ -828,6 +841,11 @@ int32_t pg2_create(const pg2_config* cfg, pg2_engine** out) {
     std::unique_ptr<EngineBase> impl;
     int rc = 1;
     PG2_ON_DEVICE(cfg->device);
+    // a distribution mode with its own world size is its own instantiation; the others are run-time parameters of the base one
+#define PG2_TRY_GAME_MODE(NAME, MODE, TYPE) \
+    if (!impl && g == NAME && cfg->distribution_mode == MODE) { auto* e = new Engine<TYPE>(); impl.reset(e); rc = e->init(cfg); }
+    PG2_FOR_EACH_GAME_MODE(PG2_TRY_GAME_MODE)
+#undef PG2_TRY_GAME_MODE
 #define PG2_TRY_GAME(NAME, TYPE) \
     if (!impl && g == NAME) { auto* e = new Engine<TYPE>(); impl.reset(e); rc = e->init(cfg); }
     PG2_FOR_EACH_GAME(PG2_TRY_GAME)

@@ -16,3 +16,9 @@
     X("chaser", pg2::Chaser)       \
     X("caveflyer", pg2::CaveFlyer) \
     X("jumper", pg2::Jumper)
+
+// Distribution modes that change the world size are separate instantiations (no cost for the default mode):
+// PG2_FOR_EACH_GAME_MODE(X) expands X(name, mode, Type) for every non-default (game, mode) pair that is built.
+#define PG2_FOR_EACH_GAME_MODE(X) \
+    X("maze", 0, pg2::MazeT<0>)    \
+    X("maze", 2, pg2::MazeT<2>)

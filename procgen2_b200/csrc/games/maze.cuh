@@ -4,7 +4,8 @@
 //                reset()                       maze.cpp:416-438
 //   frame        render_game                   maze.cpp:386-414, tilemap.cpp:111-131,
 //                sprite / agent render         common_systems.cpp:41-63, 138-151
-// hard_mode only (compile-time default of the reference): 25x25 world, all visible.
+// All three distribution modes of tilemap.cpp:35-47 as MazeT<MODE> (0 easy: 15x15 world; 1 hard, the reference's compiled-in
+// default: 25x25; 2 memory: 31x31 world, an 8x8-tile view that follows the agent).
 #pragma once
 #include "../pg2_common.cuh"
 #include "../pg2_mazegen.cuh"
@@ -15,7 +16,7 @@
 namespace pg2 {
 
 #define PG2_MAZE_FIELDS(F)                                              \
-    F(uint8_t, tiles, 640)   /* env-major, [y + x*25], 0 empty 1 wall */ \
+    F(uint8_t, tiles, 1024)  /* env-major, [y + x*WORLD] (WORLD <= 31), 0 empty 1 wall */ \
     F(float, agent_x, 1)                                                \
     F(float, agent_y, 1)                                                \
     F(uint8_t, face_forward, 1)                                         \
@@ -27,26 +28,29 @@ namespace pg2 {
 
 PG2_DEFINE_STATE(MazeState, PG2_MAZE_FIELDS)
 
-struct Maze {
+template <int MODE>
+struct MazeT {
     using State = MazeState;
-    static constexpr int WORLD = 25;          // world_dim (tilemap.cpp:36)
+    static constexpr int WORLD = MODE == 1 ? 25 : MODE == 2 ? 31 : 15;     // world_dim (tilemap.cpp:35-47)
+    static constexpr int VISIBLE = MODE == 1 ? 25 : MODE == 2 ? 8 : 15;    // visibility: the zoom's denominator (maze.cpp:397)
+    static constexpr bool CENTER_AGENT = MODE == 2;                        // memory mode: the camera follows the agent from its first update on
     static constexpr int TIMEOUT = 500;       // maze.cpp:49
     static constexpr bool LANE_AWARE = false;   // step() is written for one thread per environment
     static constexpr int STEP_LANES = 32;       // (lane-aware games only) lanes per environment in k_step
     static constexpr int MAX_POST = 4;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
-    static constexpr int RESET_ARENA = 10 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
+    static constexpr int RESET_ARENA = 13 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE; 31x31 mazes)
     static constexpr bool PREFETCH_LEVELS = true;    // the RNG is only drawn inside reset(): the next level is generated one episode ahead
     static const char* reset_keeps() { return "  "; }   // fields reset() does not write (they persist across episodes)
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 28;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
     static constexpr int BLIT_UNROLL = 1;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
-    static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
-    static bool mode_supported(int mode) { return mode == 1; }
+    static constexpr int DEFAULT_MODE = MODE;    // this instantiation's distribution mode (the reference compiles in 1 = hard; tilemap.h Config)
+    static bool mode_supported(int mode) { return mode == MODE; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
-    static constexpr bool STATIC_VIEW = true;    // fixed camera and tile map within an episode: the base image (background + tiles) is cached per env
-    static constexpr int TILE_STRIDE = 640;
+    static constexpr bool STATIC_VIEW = !CENTER_AGENT;   // fixed camera and tile map within an episode: the base image (background + tiles) is cached per env
+    static constexpr int TILE_STRIDE = 1024;
     enum Tex { T_WALL = 0, T_CHEESE = 1, T_MOUSE = 2, T_BG0 = 3, NUM_BG = 9, NUM_TEX = 12 };
 
     static const char* const* texture_names(int* count) {
@@ -94,6 +98,10 @@ struct Maze {
         if (movement_x > 0) s.face_forward[env] = 1;
         else if (movement_x < 0) s.face_forward[env] = 0;
         s.agent_x[env] = px; s.agent_y[env] = py;
+        if (CENTER_AGENT) {                       // camera follows the agent (common_systems.cpp:119-123: tilemap->center_agent())
+            c.cam_x[env] = __fmul_rn(px, UNIT_TO_PIXELS);
+            c.cam_y[env] = __fmul_rn(py, UNIT_TO_PIXELS);
+        }
         c.sprites_valid[env] = 1;                 // sprite_render->update(dt)
         *reward = reached ? 10.0f : 0.0f;
         bool terminated = reached;
@@ -167,7 +175,7 @@ struct Maze {
     template <class F>
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
         const int tid = threadIdx.x;
-        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(f.view_w, __fmul_rn(UNIT_TO_PIXELS, (float)WORLD)), f.view_w, f.view_h };   // maze.cpp:403: zoom from the width
+        Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(f.view_w, __fmul_rn(UNIT_TO_PIXELS, (float)VISIBLE)), f.view_w, f.view_h };   // maze.cpp:403: zoom from the width
         int lx, ly, ux, uy;
         tile_window(cam, &lx, &ly, &ux, &uy);
         int ncol = min(ux - lx + 1, MAX_WIN), nrow = min(uy - ly + 1, MAX_WIN);
@@ -196,5 +204,7 @@ struct Maze {
         });
     }
 };
+
+using Maze = MazeT<1>;   // the reference's compiled-in mode
 
 }  // namespace pg2

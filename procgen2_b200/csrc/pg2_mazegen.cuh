@@ -10,7 +10,7 @@
 
 namespace pg2 {
 
-constexpr int MAZE_MAX_DIM = 25;                                   // maze_dim <= 25 (maze hard mode)
+constexpr int MAZE_MAX_DIM = 31;                                   // maze_dim <= 31 (maze memory mode)
 constexpr int MAZE_MAX_ARR = (MAZE_MAX_DIM + 2) * (MAZE_MAX_DIM + 2);
 
 struct MazeGrid {
@@ -29,16 +29,18 @@ PG2_DEV_NOINLINE MazeGrid kruskal_maze(WarpCtx& w, int mw, int mh) {
     MazeGrid m;
     m.mw = mw; m.mh = mh; m.aw = mw + 2; m.ah = mh + 2;
     const int ah = m.ah;
-    m.grid = w.alloc<uint8_t>(MAZE_MAX_ARR);
-    m.free_cells = w.alloc<int16_t>(MAZE_MAX_ARR);
-    int16_t* set_idx = w.alloc<int16_t>(MAZE_MAX_ARR);
-    uint8_t* set_rank = w.alloc<uint8_t>(MAZE_MAX_ARR);
-    uint8_t* is_free = w.alloc<uint8_t>(MAZE_MAX_DIM * MAZE_MAX_DIM);
-    uint32_t* walls = w.alloc<uint32_t>(320);                       // x1 | y1<<8 | x2<<16 | y2<<24
+    // scratch sized by THIS maze (11x11 chaser ... 31x31 maze memory mode), so every game's arena only pays for its own
+    const int arr = m.aw * m.ah, cells = mw * mh;
+    m.grid = w.alloc<uint8_t>(arr);
+    m.free_cells = w.alloc<int16_t>(arr);
+    int16_t* set_idx = w.alloc<int16_t>(arr);
+    uint8_t* set_rank = w.alloc<uint8_t>(arr);
+    uint8_t* is_free = w.alloc<uint8_t>(cells);
+    uint32_t* walls = w.alloc<uint32_t>(cells / 2 + 4);             // x1 | y1<<8 | x2<<16 | y2<<24 (31x31: 480 walls)
     uint8_t* grid = m.grid;
     int16_t* free_cells = m.free_cells;
     w.fill<uint8_t>(grid, m.aw * m.ah, 1);
-    w.fill<uint8_t>(is_free, MAZE_MAX_DIM * MAZE_MAX_DIM, 0);
+    w.fill<uint8_t>(is_free, cells, 0);
     for (int i = lane; i < mw * mh; i += WARP_LANES) { set_idx[i] = (int16_t)i; set_rank[i] = 0; }
     __syncwarp();
     grid[1 + ah * 1] = 0;                                          // corner

@@ -33,7 +33,7 @@ for r in rows:
             if ln <= line: name = fn
             else: break
         key = "%s:%s" % (os.path.basename(cur or "?"), name)
-        agg[key] += n; smp[key] += int(r[s] or 0)
+        agg[key] += n; smp[key] += int(r[s]) if r[s].strip().isdigit() else 0
 tot = sum(agg.values()); stot = max(sum(smp.values()), 1)
 print("total warp instructions", tot, ("= %.0f per frame" % (tot / frames)) if frames else "", "samples", stot)
 for k, v in agg.most_common(40):

@@ -12,7 +12,7 @@ for r in rows:
         i = h.index("Instructions Executed"); s = h.index("# Samples")
         try: n = int(r[i])
         except ValueError: continue
-        if n > 0: out.append((n, int(r[s] or 0), sect, int(r[0]), r[1].strip()[:120]))
+        if n > 0: out.append((n, int(r[s]) if r[s].strip().isdigit() else 0, sect, int(r[0]), r[1].strip()[:120]))
 tot = sum(o[0] for o in out); smp = sum(o[1] for o in out)
 print("total warp instructions", tot, "samples", smp)
 out.sort(reverse=True)

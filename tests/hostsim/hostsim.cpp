@@ -103,8 +103,12 @@ void* hs_create_mode(const char* game, int n, int seed, int max_ep, const char* 
     if (g_sort_table.empty()) { g_sort_table = build_sort_perm(SORT_MAXN); g_sort_perm = g_sort_table.data(); }
     SimBase* out = nullptr;
     bool ok = false;
+#define PG2_TRY_GAME_MODE(NAME, MODE, TYPE) \
+    if (!out && g == NAME && mode == MODE) { auto* s = new Sim<TYPE>(); out = s; ok = s->init(n, (uint32_t)seed, max_ep, assets, &g_err, mode); }
+    PG2_FOR_EACH_GAME_MODE(PG2_TRY_GAME_MODE)
+#undef PG2_TRY_GAME_MODE
 #define PG2_TRY_GAME(NAME, TYPE) \
-    if (g == NAME) { auto* s = new Sim<TYPE>(); out = s; ok = s->init(n, (uint32_t)seed, max_ep, assets, &g_err, mode); }
+    if (!out && g == NAME) { auto* s = new Sim<TYPE>(); out = s; ok = s->init(n, (uint32_t)seed, max_ep, assets, &g_err, mode); }
     PG2_FOR_EACH_GAME(PG2_TRY_GAME)
 #undef PG2_TRY_GAME
     if (!out) { g_err = "unknown game " + g; return nullptr; }

@@ -193,3 +193,39 @@ def test_easy_distribution_mode_live_oracle(game, oracle_available):
     if game == "climber":   # the mode does change climber's levels (fewer enemies): easy and hard runs part ways
         easy, hard = SimAdapter(game, n, seed, distribution_mode=0), SimAdapter(game, n, seed, distribution_mode=1)
         assert any(not np.array_equal(easy.reset(), hard.reset()) for _ in range(6))
+
+
+@pytest.mark.parametrize("game,mode", [("maze", 0), ("maze", 2)])
+def test_world_size_modes_live_oracle(game, mode, oracle_available):
+    """Distribution modes that change the world size (own instantiations, G = <Game>T<MODE>) against the reference with its
+    compile-time Config::mode set through the probe: levels (tile map + RNG state), pixels, rewards, dones, truncation."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_env
+    n, seed, T = 5, 8300 + mode, 150
+    rs = np.random.RandomState(mode)
+    acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
+    sim = SimAdapter(game, n, seed, max_episode_steps=40, distribution_mode=mode)
+    refs = [ref_env.RefEnv(game, seed + i, mode=mode) for i in range(n)]
+    f = sim.fields()
+    for i, r in enumerate(refs):   # level #1 (cenv_make)
+        rt = r.tiles()
+        w, h = rt.shape
+        np.testing.assert_array_equal((f["tiles"][i, :w * h] & 15).reshape(w, h), rt, err_msg="tile map after make, env %d" % i)
+    np.testing.assert_array_equal(sim.reset(), np.stack([r.reset() for r in refs]))
+    age = np.zeros(n, np.int64)
+    for t in range(T):
+        o, rw, d = sim.step(acts[t])
+        for i, r in enumerate(refs):
+            oo, w, dd = r.step(acts[t, i])
+            age[i] += 1
+            if dd or age[i] >= 40:
+                oo = r.reset(); age[i] = 0
+            assert w == rw[i] and dd == d[i], (t, i)
+            np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))
+    f = sim.fields()
+    for i, r in enumerate(refs):
+        st, pos = r.rng_state()
+        assert pos == f["mti"][i]
+        np.testing.assert_array_equal(st, f["mt"][i])
+        r.close()
