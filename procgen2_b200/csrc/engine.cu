@@ -501,7 +501,7 @@ struct Engine : EngineBase {
         PG2_CUDA(cudaMemsetAsync(reset_count, 0, 4 * sizeof(int), stream));
         PG2_CUDA(cudaMalloc(&pending, N));
         PG2_CUDA(cudaMemsetAsync(pending, 0, N, stream));
-        prefetch = G::PREFETCH_LEVELS && auto_reset;
+        prefetch = G::PREFETCH_LEVELS && auto_reset && !(max_episode_steps > 0 && max_episode_steps < G::PREFETCH_MIN_EPISODE);
         if (const char* o = getenv("PG2_PREFETCH")) prefetch = atoi(o) != 0 && G::PREFETCH_LEVELS && auto_reset;
         if (prefetch) {
             PG2_CUDA(cudaMalloc(&shadow_state_mem, G::State::bytes(N)));

@@ -53,6 +53,7 @@ struct BossFight {
     static constexpr bool SLOW_RESET = false;   // level generation is long: run it concurrently with the render of the other envs
     static constexpr int RESET_ARENA = 2 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
     static constexpr bool PREFETCH_LEVELS = false;   // step() draws from the RNG: the next level is not known ahead of time
+    static constexpr int PREFETCH_MIN_EPISODE = 0;   // level prefetch whatever max_episode_steps is
     static const char* reset_keeps() { return ""; }
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 1;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)

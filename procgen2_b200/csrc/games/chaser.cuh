@@ -49,6 +49,7 @@ struct Chaser {
     static constexpr bool SLOW_RESET = true;    // level generation (Kruskal + set orders, ~0.1 ms) runs concurrently with the render of the other envs: +22 % at 4096 envs
     static constexpr int RESET_ARENA = 10 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
     static constexpr bool PREFETCH_LEVELS = false;   // step() draws from the RNG: the next level is not known ahead of time
+    static constexpr int PREFETCH_MIN_EPISODE = 0;   // level prefetch whatever max_episode_steps is
     static const char* reset_keeps() { return ""; }
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 14;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)

@@ -51,7 +51,7 @@ PG2_DEV int sort_perm(int n, int k) { return (n <= 16 || n > SORT_MAXN) ? k : g_
 
 struct BlitRot {
     double s, c;       // sin/cos of the blit angle (deterministic, see sincos_deg)
-    int ex, ey;        // half extents (pixels, rounded up + 2) of the rotated rect's axis-aligned bounding box
+    int16_t x_lo, x_hi, y_lo, y_hi;   // pixel bounds (inclusive) of the rotated rect's axis-aligned bounding box (rotated_bounds)
 };
 
 // Per-pixel form of a blit (what the frame keeps): coverage test = two unsigned compares, sampling = one
@@ -271,22 +271,24 @@ PG2_DEV FastBlit make_fast(const Blit& b) {
     return fb;
 }
 
-// Half extents of the axis-aligned bounding box of a rotated destination rect: a pixel centre passes the inverse-mapping
-// test of rotated_texel_coords only if |x - cx| <= hw |c| + hh |s| and |y - cy| <= hw |s| + hh |c|; + 2 px of slack for
-// the integer centre and rounding (a bound only has to be conservative, it never changes which pixels are drawn).
-PG2_DEV void rotated_extents(const FastBlit& fb, BlitRot* rot) {
+// Pixel bounds of the axis-aligned bounding box of a rotated destination rect. A pixel centre (X + 0.5, Y + 0.5) passes the
+// inverse-mapping test of rotated_texel_coords only if |u| <= hw and |v| <= hh, hence |X + 0.5 - cx| <= hw |c| + hh |s| (and
+// the same with s, c swapped in y), cx = x0 + hw the real centre. The bounds are rounded OUTWARDS after widening by 1e-3 for
+// the rounding of the test's own arithmetic: a bound only has to be conservative, it never changes which pixels are drawn
+// (bullets a few pixels long got 9-11 px boxes from the integer centre +- (ceil + 2) of round 1: three times the patches).
+PG2_DEV void rotated_bounds(const FastBlit& fb, BlitRot* rot) {
     const double hw = 0.5 * (double)fb.w, hh = 0.5 * (double)fb.h, ac = fabs(rot->c), as = fabs(rot->s);
-    rot->ex = (int)ceil(hw * ac + hh * as) + 2;
-    rot->ey = (int)ceil(hw * as + hh * ac) + 2;
+    const double ex = hw * ac + hh * as + 1e-3, ey = hw * as + hh * ac + 1e-3;
+    const double cx = (double)fb.x0 + hw - 0.5, cy = (double)fb.y0 + hh - 0.5;   // pixel index X = centre coordinate - 0.5
+    const double lo_x = floor(cx - ex), hi_x = ceil(cx + ex), lo_y = floor(cy - ey), hi_y = ceil(cy + ey);
+    rot->x_lo = (int16_t)fmax(lo_x, -30000.0); rot->x_hi = (int16_t)fmin(hi_x, 30000.0);
+    rot->y_lo = (int16_t)fmax(lo_y, -30000.0); rot->y_hi = (int16_t)fmin(hi_y, 30000.0);
 }
 
 // Bands (8 rows each) a blit can touch.
 PG2_DEV uint32_t blit_bands(const FastBlit& fb, const BlitRot& rot) {
     int y0 = fb.y0, y1 = fb.y0 + fb.h - 1;
-    if (fb.flags & 2u) {
-        const int cy = fb.y0 + fb.h / 2;
-        y0 = cy - rot.ey; y1 = cy + rot.ey;
-    }
+    if (fb.flags & 2u) { y0 = rot.y_lo; y1 = rot.y_hi; }
     if (y1 < 0 || y0 >= OBS_H) return 0u;
     int b0 = max(y0, 0) / BAND_ROWS, b1 = min(y1, OBS_H - 1) / BAND_ROWS;
     return ((2u << b1) - 1u) & ~((1u << b0) - 1u);
@@ -325,7 +327,7 @@ PG2_DEV void emit_post_blits(F& f, const TexInfo* tex, int ncand, MakeFn make) {
     for (int base = 0; base < ncand; base += blockDim.x, round ^= 1) {
         int k = base + tid;
         BlitReq req; BlitRot rot;
-        req.mode = 0; rot.s = 0.0; rot.c = 1.0; rot.ex = 0; rot.ey = 0;
+        req.mode = 0; rot.s = 0.0; rot.c = 1.0; rot.x_lo = rot.x_hi = rot.y_lo = rot.y_hi = 0;
         if (k < ncand) make(k, req, rot);
         Blit b;
         b.ax.visible = 0;
@@ -343,7 +345,7 @@ PG2_DEV void emit_post_blits(F& f, const TexInfo* tex, int ncand, MakeFn make) {
         if (vis) {
             int idx = n + before + __popc(m & ((1u << lane) - 1u));
             if (idx < F::MAX_POST) {
-                if (F::ROTATES && (fb.flags & 2u)) rotated_extents(fb, &rot);
+                if (F::ROTATES && (fb.flags & 2u)) rotated_bounds(fb, &rot);
                 f.fpost[idx] = fb;
                 f.bandmask[idx] = (uint8_t)blit_bands(fb, rot);
                 if (F::ROTATES) f.post_rot[idx] = rot;
@@ -728,7 +730,7 @@ PG2_DEV_COLD uint32_t shade_base_ordered(const F& f, const uint32_t* __restrict_
     uint32_t color = 0u, texel;   // SDL_RenderClear(0,0,0,255)
     for (int k = 0; k < f.npre; k++) {
         const FastBlit fb = f.fpre[k];
-        BlitRot rot{ 0.0, 1.0, 0, 0 };
+        BlitRot rot{ 0.0, 1.0, 0, 0, 0, 0 };
         if (!(fb.flags & 4u) && fast_texel<false>(fb, &rot, atlas, X, Y, &texel)) color = blend_packed(color, texel, fb.flags & 1u, fb.alpha_mod);
     }
     if (!f.wide) {
@@ -920,10 +922,7 @@ PG2_DEV void draw_blit_band(F& f, const uint32_t* __restrict__ atlas, int k, int
     const FastBlit fb = f.fpost[k];
     const BlitRot* rot = &f.post_rot[F::ROTATES ? k : 0];
     int x0 = fb.x0, y0 = fb.y0, x1 = fb.x0 + fb.w - 1, y1 = fb.y0 + fb.h - 1;
-    if (F::ROTATES && (fb.flags & 2u)) {   // bounding box of the rotated rect (rotated_extents)
-        const int cx = fb.x0 + fb.w / 2, cy = fb.y0 + fb.h / 2;
-        x0 = cx - rot->ex; x1 = cx + rot->ex; y0 = cy - rot->ey; y1 = cy + rot->ey;
-    }
+    if (F::ROTATES && (fb.flags & 2u)) { x0 = rot->x_lo; x1 = rot->x_hi; y0 = rot->y_lo; y1 = rot->y_hi; }   // bounding box of the rotated rect
     x0 = max(x0, 0); x1 = min(x1, OBS_W - 1); y0 = max(y0, Y0); y1 = min(y1, Y0 + BAND_ROWS - 1);
     const uint32_t blend = fb.flags & 1u, alpha_mod = fb.alpha_mod;
     if (!(F::ROTATES && (fb.flags & 2u))) {
