@@ -229,14 +229,11 @@ __global__ void __launch_bounds__(32 * RESET_WARPS_PER_CTA) k_reset(typename G::
     }
 }
 
-#ifndef PG2_RENDER_MIN_CTAS
-#define PG2_RENDER_MIN_CTAS 8   // CTAs per SM the register allocation of k_render aims at
-#endif
 // Persistent CTAs; frames are handed out through a ticket counter, so a CTA that drew cheap frames simply takes
 // more of them. mode 0: every env; mode 1: every env that is NOT being reset this step (k_reset runs concurrently
 // on a second stream); mode 2: exactly the envs of the reset list (after k_reset).
 template <class G>
-__global__ void __launch_bounds__(RENDER_THREADS, PG2_RENDER_MIN_CTAS) k_render(typename G::State s, CommonState c, const TexInfo* __restrict__ tex,
+__global__ void __launch_bounds__(RENDER_THREADS, G::RENDER_MIN_CTAS) k_render(typename G::State s, CommonState c, const TexInfo* __restrict__ tex,
                                                            const uint32_t* __restrict__ atlas, uint8_t* __restrict__ obs,
                                                            int* __restrict__ ticket, int mode, const int* __restrict__ list,
                                                            const int* __restrict__ list_count, const uint8_t* __restrict__ pending, int N,

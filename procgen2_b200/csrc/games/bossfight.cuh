@@ -58,6 +58,7 @@ struct BossFight {
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 1;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
     static constexpr int BLIT_UNROLL = 2;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
+    static constexpr int RENDER_MIN_CTAS = 10;   // CTAs per SM the register allocation of k_render aims at (small frame tables: 10 frames per SM measured +5 % over 8)
     static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
     static bool mode_supported(int mode) { return mode == 1; }
     static constexpr bool HAS_TILES = false;     // the frame has a tile layer

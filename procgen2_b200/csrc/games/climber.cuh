@@ -52,6 +52,7 @@ struct Climber {
     static constexpr int TILE_CLASSES = 2;   // wall_mid textures are 64x64, one wall_top texture is 64x53
     static constexpr int WIN_ROWS = 23;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
     static constexpr int BLIT_UNROLL = 1;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
+    static constexpr int RENDER_MIN_CTAS = 8;   // CTAs per SM the register allocation of k_render aims at
     static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
     static bool mode_supported(int mode) { return mode == 0 || mode == 1; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer

@@ -35,7 +35,10 @@ constexpr int MAX_PRE = 2;
 #endif
 constexpr int RENDER_THREADS = PG2_RENDER_THREADS;
 constexpr uint8_t NO_TILE = 0xff;
-constexpr int BAND_ROWS = 8, NUM_BANDS = OBS_H / BAND_ROWS, BAND_BYTES = BAND_ROWS * OBS_W * 3, BAND_PX = BAND_ROWS * OBS_W;
+#ifndef PG2_BAND_ROWS
+#define PG2_BAND_ROWS 8
+#endif
+constexpr int BAND_ROWS = PG2_BAND_ROWS, NUM_BANDS = OBS_H / BAND_ROWS, BAND_BYTES = BAND_ROWS * OBS_W * 3, BAND_PX = BAND_ROWS * OBS_W;
 
 // std::sort permutation table. System_Sprite_Render::update sorts (z, entity) pairs
 // by z with std::sort (common_systems.cpp:36-38); every sprite of a game has the same z, so the
@@ -347,7 +350,7 @@ PG2_DEV void emit_post_blits(F& f, const TexInfo* tex, int ncand, MakeFn make) {
             if (idx < F::MAX_POST) {
                 if (F::ROTATES && (fb.flags & 2u)) rotated_bounds(fb, &rot);
                 f.fpost[idx] = fb;
-                f.bandmask[idx] = (uint8_t)blit_bands(fb, rot);
+                f.bandmask[idx] = (uint16_t)blit_bands(fb, rot);
                 if (F::ROTATES) f.post_rot[idx] = rot;
             }
         }

@@ -166,7 +166,7 @@ def test_distribution_mode_option(oracle_available):
     a (game, mode) pair that is not built is refused loudly."""
     from procgen2_b200.engine import BatchedEnv
     with pytest.raises(RuntimeError, match="distribution_mode"):
-        BatchedEnv("maze", 4, distribution_mode=2)
+        BatchedEnv("chaser", 4, distribution_mode=2)      # chaser extreme: not built
     if not oracle_available:
         pytest.skip("oracle/_ref did not travel")
     from oracle import ref_env
@@ -190,4 +190,45 @@ def test_distribution_mode_option(oracle_available):
             np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))
     for r in refs:
         r.close()
+    env.close()
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_maze_world_size_modes(mode, oracle_available):
+    """maze easy (15x15) / memory (31x31, agent-centred 8x8 view) = the MazeT<MODE> instantiations, against the reference with
+    its compile-time Config::mode set: tile maps + RNG after make, pixels / rewards / dones over truncated episodes."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref did not travel")
+    from oracle import ref_env
+    from procgen2_b200.engine import BatchedEnv
+    n, seed, T = 48, 8300 + mode, 150
+    rs = np.random.RandomState(mode)
+    acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
+    env = BatchedEnv("maze", n, seed=seed, max_episode_steps=40, distribution_mode=mode)
+    refs = [ref_env.RefEnv("maze", seed + i, mode=mode) for i in range(n)]
+    tb, _, pe = env.read_field("tiles")
+    tiles = tb.reshape(n, pe)
+    for i, r in enumerate(refs):
+        rt = r.tiles()
+        w, h = rt.shape
+        assert w == (15 if mode == 0 else 31)
+        np.testing.assert_array_equal(tiles[i, :w * h].reshape(w, h), rt, err_msg="tile map after make, env %d" % i)
+    env.reset()
+    np.testing.assert_array_equal(env.fetch()[0], np.stack([r.reset() for r in refs]))
+    age = np.zeros(n, np.int64)
+    for t in range(T):
+        env.step(acts[t])
+        o, rw, d, _ = env.fetch()
+        for i, r in enumerate(refs):
+            oo, w, dd = r.step(acts[t, i])
+            age[i] += 1
+            if dd or age[i] >= 40:
+                oo = r.reset(); age[i] = 0
+            assert w == rw[i] and dd == d[i], (t, i)
+            np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))
+    mt = env.read_field("mt")[0].view(np.uint32).reshape(n, 624)
+    for i, r in enumerate(refs):
+        np.testing.assert_array_equal(r.rng_state()[0], mt[i])
+        r.close()
+    assert not env.read_field("fault")[0].view(np.int32).any()
     env.close()
