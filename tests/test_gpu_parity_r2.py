@@ -256,3 +256,28 @@ def test_step_graph_equals_eager(game, monkeypatch):
         np.testing.assert_array_equal(a.read_field(name)[0], b.read_field(name)[0])
     _assert_no_fault(b)
     a.close(); b.close()
+
+
+# ---- (f) level prefetch under the worst case ----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("game,n,max_ep", [("maze", 32768, 1), ("jumper", 8192, 1), ("climber", 16384, 2)])
+def test_prefetch_when_every_env_finishes_every_step(game, n, max_ep, monkeypatch):
+    """Large batch, one- / two-step episodes: every env finishes (again) before its next level can exist, so every stepping
+    warp waits for the asynchronous generator while the GPU is full of them. No fault flag (= no bounded wait expired, no
+    deadlock) and the same results as the inline-reset path."""
+    from procgen2_b200.engine import BatchedEnv
+    T = 16
+    acts = np.random.RandomState(1).randint(0, 15, size=(T, n)).astype(np.int32)
+    outs = []
+    for pf in ("1", "0"):
+        monkeypatch.setenv("PG2_PREFETCH", pf)
+        env = BatchedEnv(game, n, seed=3, max_episode_steps=max_ep)
+        env.reset()
+        for t in range(T):
+            env.step(acts[t])
+        o, r, d, tr = env.fetch(truncated=True)
+        _assert_no_fault(env)
+        outs.append((o, r, d, tr, env.read_field("mti")[0].copy(), env.read_field("mt")[0].copy()))
+        env.close()
+    for a, b in zip(*outs):
+        np.testing.assert_array_equal(a, b)
