@@ -99,7 +99,7 @@ __device__ __forceinline__ void swap_wait(const SwapArgs& a, const CommonState& 
 // serialise one memory round trip per element): short fields (<= blockDim elements per env) eight fields per round, one
 // element per thread; long ones (tile map, MT19937 words, particle pools) eight elements per thread per round.
 __device__ __noinline__ void swap_copy(const SwapArgs& a, const CommonState& live_c, int env, int N) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x, nthr = CTA_THREADS;   // called by the render CTA
     __threadfence();
     auto elem_off = [&](const SwapField& f, int j) { return f.env_major ? ((size_t)env * f.per_env + j) * f.esz : ((size_t)j * N + env) * f.esz; };
     for (int i0 = 0; i0 < a.table.n; i0 += 8) {

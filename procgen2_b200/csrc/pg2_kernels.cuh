@@ -115,7 +115,7 @@ PG2_DEV void render_human_body(const typename G::State& s, const CommonState& c,
     G::build_frame(s, c, env, f, tex);
     __syncthreads();
     frame_finalize<G>(f);
-    for (int p = first + (int)threadIdx.x; p < last; p += (int)blockDim.x) {
+    for (int p = first + (int)threadIdx.x; p < last; p += CTA_THREADS) {
         const uint32_t color = shade_human_pixel<G>(f, atlas, p % width, p / width);
         out[3 * (size_t)p] = (uint8_t)color; out[3 * (size_t)p + 1] = (uint8_t)(color >> 8); out[3 * (size_t)p + 2] = (uint8_t)(color >> 16);
     }

@@ -34,6 +34,9 @@ constexpr int MAX_PRE = 2;
 #define PG2_RENDER_THREADS 128
 #endif
 constexpr int RENDER_THREADS = PG2_RENDER_THREADS;
+// Threads of a render CTA as a compile-time constant (every render kernel is launched with RENDER_THREADS; the host-sim
+// harness runs one "thread"): strided loops get constant trip counts instead of a division by blockDim.x.
+constexpr int CTA_THREADS = WARP_LANES == 32 ? RENDER_THREADS : 1;
 constexpr uint8_t NO_TILE = 0xff;
 #ifndef PG2_BAND_ROWS
 #define PG2_BAND_ROWS 8
@@ -192,7 +195,7 @@ PG2_DEV_CALL void sincos_deg(double deg, double* s, double* c) {
 // ---- blit construction helpers (called by the per-game frame builders) --------------------
 
 // Work item k of a frame builder runs on the first lane of warp k (any thread when simulated).
-PG2_DEV bool is_role(int k) { return (int)threadIdx.x == (k * 32) % (int)blockDim.x; }
+PG2_DEV bool is_role(int k) { return (int)threadIdx.x == (k * 32) % CTA_THREADS; }
 
 // gr.camera_position / gr.camera_scale / gr.camera_size (renderer.h:18-20). The size is 64x64 for observations and the
 // window size for the human-mode frame of cenv_render (render_game(false), coinrun.cpp:451-455).
@@ -325,9 +328,9 @@ struct BlitReq {
 template <class F, class MakeFn>
 PG2_DEV void emit_post_blits(F& f, const TexInfo* tex, int ncand, MakeFn make) {
     const int tid = threadIdx.x, lane = tid % WARP_LANES, warp = tid / WARP_LANES;
-    const int nwarps = ((int)blockDim.x + WARP_LANES - 1) / WARP_LANES;
+    const int nwarps = (CTA_THREADS + WARP_LANES - 1) / WARP_LANES;
     int n = 0, round = 0;
-    for (int base = 0; base < ncand; base += blockDim.x, round ^= 1) {
+    for (int base = 0; base < ncand; base += CTA_THREADS, round ^= 1) {
         int k = base + tid;
         BlitReq req; BlitRot rot;
         req.mode = 0; rot.s = 0.0; rot.c = 1.0; rot.x_lo = rot.x_hi = rot.y_lo = rot.y_hi = 0;
@@ -409,7 +412,7 @@ PG2_DEV void frame_begin(F& f, bool reuse = false) {   // `reuse` is only looked
         if (!reuse) { f.npre = 0; f.wide = 0; f.pre_blend = 0; }
     }
     // cslot and rslot are adjacent: one run of 16-byte words
-    for (int k = tid; k < (int)(sizeof(f.cslot) + sizeof(f.rslot)) / 16; k += blockDim.x) ((Word16*)f.cslot)[k] = Word16{ 0u, 0u, 0u, 0u };
+    for (int k = tid; k < (int)(sizeof(f.cslot) + sizeof(f.rslot)) / 16; k += CTA_THREADS) ((Word16*)f.cslot)[k] = Word16{ 0u, 0u, 0u, 0u };
 }
 
 // One band of the base image: cache -> band buffer as ONE 2 048-byte TMA bulk load (async proxy, completion on the
@@ -455,12 +458,23 @@ template <class F, class ClassTex, class TileAt>
 PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int nclass, int lx, int ly, int ncol, int nrow,
                               ClassTex class_tex, TileAt tile_at, int bg_tex, float bg_x, float bg_y, float bg_scale) {
     const int tid = threadIdx.x, lane = tid % WARP_LANES, warp = tid / WARP_LANES;
-    const int nwarps = ((int)blockDim.x + WARP_LANES - 1) / WARP_LANES;
+    const int nwarps = (CTA_THREADS + WARP_LANES - 1) / WARP_LANES;
     if (f.reuse) return;   // the base image comes from the env's cache: no descriptors, cells or background needed
     if (nrow > F::WINR) { nrow = F::WINR; if (tid == 0) f.overflow = 1; }
     const int per = ncol + nrow, njobs = 2 + nclass * per;
     if (tid == 0) { f.tx0 = lx; f.ty0 = ly; f.ncol = ncol; f.nrow = nrow; f.nclass = nclass; f.npre = 1; }
-    for (int job = (int)blockDim.x - 1 - tid; job < njobs; job += blockDim.x) {
+    // window cells: lanes = tile columns, two tile rows per warp pass when the window is at most 16 columns wide
+    // (cells right of the window stay unwritten: nothing valid ever points at them). The tile loads of the first two
+    // passes are issued here, so that their latency runs under the axis jobs below.
+    const int cpr = ncol <= 16 ? 16 : 32, rpp = 32 / cpr;
+    constexpr int CELL_AHEAD = WARP_LANES == 32 ? 2 : 0;
+    uint32_t ahead[CELL_AHEAD > 0 ? CELL_AHEAD : 1];
+#pragma unroll
+    for (int q = 0; q < CELL_AHEAD; q++) {
+        const int ry = (warp + q * nwarps) * rpp + lane / cpr, cx = lane % cpr;
+        ahead[q] = (ry < nrow && cx < ncol) ? (uint32_t)tile_at(lx + cx, ly + ry) : (uint32_t)NO_TILE;
+    }
+    for (int job = CTA_THREADS - 1 - tid; job < njobs; job += CTA_THREADS) {
         const bool bg = job < 2;
         const int t = job - 2, cls = (!bg && t >= per) ? 1 : 0, u = bg ? 0 : t - cls * per;
         const bool is_row = bg ? job == 1 : u >= ncol;
@@ -497,11 +511,13 @@ PG2_DEV void build_tile_layer(F& f, const Camera& cam, const TexInfo* tex, int n
             if (bad) f.wide = 1;
         }
     }
-    for (int cls = tid; cls < nclass; cls += blockDim.x) f.class_w[cls] = tex[class_tex(cls)].w;
-    // window cells: lanes = tile columns, two tile rows per warp pass when the window is at most 16 columns wide
-    // (cells right of the window stay unwritten: nothing valid ever points at them)
-    const int cpr = ncol <= 16 ? 16 : 32, rpp = 32 / cpr;
-    for (int ry0 = warp * rpp; ry0 < nrow; ry0 += nwarps * rpp)
+    for (int cls = tid; cls < nclass; cls += CTA_THREADS) f.class_w[cls] = tex[class_tex(cls)].w;
+#pragma unroll
+    for (int q = 0; q < CELL_AHEAD; q++) {
+        const int ry = (warp + q * nwarps) * rpp + lane / cpr, cx = lane % cpr;
+        if (ry < nrow) f.cell[ry * MAX_WIN + cx] = ahead[q] != NO_TILE ? f.tileword[ahead[q] & (MAX_TILE_TEX - 1)] : 0u;
+    }
+    for (int ry0 = (warp + CELL_AHEAD * nwarps) * rpp; ry0 < nrow; ry0 += nwarps * rpp)
         for (int l = lane; l < 32; l += WARP_LANES) {
             const int ry = ry0 + l / cpr, cx = l % cpr;
             if (ry < nrow) {
@@ -528,7 +544,7 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
         if (!pre_ok) f.wide = 1;
         f.pre_blend = npre >= 1 ? f.pre[npre - 1].blend : 0;
     }
-    for (int k = tid; k < npre; k += blockDim.x) {
+    for (int k = tid; k < npre; k += CTA_THREADS) {
         Blit b = f.pre[k];
         if (!b.ay.visible) b.ax.visible = 0;   // make_blit's rule (the two axes were built by different threads)
         f.fpre[k] = make_fast(b);
@@ -538,7 +554,7 @@ PG2_DEV_NOINLINE void frame_finalize(F& f) {
         __syncthreads();
         return;
     }
-    for (int k = tid; k < 2 * OBS_W; k += blockDim.x) {
+    for (int k = tid; k < 2 * OBS_W; k += CTA_THREADS) {
         const bool is_row = k >= OBS_W;
         const int p = k & (OBS_W - 1);
         // the column's candidates (always needed: both jobs of a column build rowcell entries)
@@ -1041,7 +1057,7 @@ PG2_DEV_NOINLINE void frame_rasterise(F& f, const uint32_t* __restrict__ atlas, 
 // Per-CTA table of the game's tile textures (ids < MAX_TILE_TEX) as window cell words, filled once before the first frame.
 template <class G, class F>
 PG2_DEV void frame_init_tiletex(F& f, const TexInfo* __restrict__ tex) {
-    for (int t = threadIdx.x; t < MAX_TILE_TEX; t += blockDim.x) {
+    for (int t = threadIdx.x; t < MAX_TILE_TEX; t += CTA_THREADS) {
         uint32_t w = 0u;
         if (t < G::NUM_TEX) {
             const TexInfo ti = tex[t];
@@ -1050,8 +1066,8 @@ PG2_DEV void frame_init_tiletex(F& f, const TexInfo* __restrict__ tex) {
         }
         f.tileword[t] = w;
     }
-    for (int k = threadIdx.x; k < OBS_W; k += blockDim.x) f.rowcell[F::WINR * OBS_W + k] = 0u;
-    for (int w = threadIdx.x; w < RENDER_THREADS / 32; w += blockDim.x) {
+    for (int k = threadIdx.x; k < OBS_W; k += CTA_THREADS) f.rowcell[F::WINR * OBS_W + k] = 0u;
+    for (int w = threadIdx.x; w < RENDER_THREADS / 32; w += CTA_THREADS) {
         f.mbar_phase[w] = 0u;
 #ifndef PG2_HOSTSIM
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&f.mbar[w])) : "memory");
