@@ -86,13 +86,16 @@ class RefEnv:
         self.lib.cenv_step.argtypes = [ctypes.POINTER(KeyValue), ctypes.c_int32]
         if easy_mode is not None:   # compile-time Config::easy_mode of the generator (coinrun, climber), set through the probe
             self.probe("pg2o_set_easy_mode", None, [ctypes.c_int])(1 if easy_mode else 0)
-        if mode is not None:        # compile-time Config::mode (maze, chaser, jumper, caveflyer): 0 easy, 1 hard, 2 memory / extreme
+        late_mode = mode is not None and game == "bossfight"   # its Config lives in a system cenv_make creates; only update() reads it
+        if mode is not None and not late_mode:   # compile-time Config::mode (maze, chaser, jumper, caveflyer): 0 easy, 1 hard, 2 memory / extreme
             self.probe("pg2o_set_mode", None, [ctypes.c_int])(int(mode))
         opts = [(b"seed", int(seed))] + ([(b"width", int(width))] if width else []) + ([(b"height", int(height))] if height else [])
         arr = (Option * len(opts))()
         for i, (k, v) in enumerate(opts):
             arr[i].name, arr[i].value_type, arr[i].value = k, 0, _Value(i=v)
         assert self.lib.cenv_make(b"", arr, len(opts)) == 0
+        if late_mode:
+            self.probe("pg2o_set_mode", None, [ctypes.c_int])(int(mode))
         self.render_data = RenderData.in_dll(self.lib, "render_data")
         self.step_data = StepData.in_dll(self.lib, "step_data")
         self.reset_data = ResetData.in_dll(self.lib, "reset_data")

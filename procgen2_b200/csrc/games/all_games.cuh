@@ -21,4 +21,8 @@
 // PG2_FOR_EACH_GAME_MODE(X) expands X(name, mode, Type) for every non-default (game, mode) pair that is built.
 #define PG2_FOR_EACH_GAME_MODE(X) \
     X("maze", 0, pg2::MazeT<0>)    \
-    X("maze", 2, pg2::MazeT<2>)
+    X("maze", 2, pg2::MazeT<2>)    \
+    X("chaser", 1, pg2::ChaserT<1>) \
+    X("chaser", 2, pg2::ChaserT<2>) \
+    X("jumper", 0, pg2::JumperT<0>)   \
+    X("caveflyer", 0, pg2::CaveFlyerT<0>)

@@ -5,7 +5,7 @@
 //   level gen   System_Tilemap::regenerate tilemap.cpp:118-278 (spawn helpers :35-116), Room_Generator
 //               room_generator.cpp, reset() caveflyer.cpp:442-462
 //   frame       render_game caveflyer.cpp:413-440; tilemap.cpp:280-303; common_systems.cpp:26-48, 291-326, 374-398
-// hard_mode (compile-time default): 40 x 40 world. Entity ids per episode: 0 goal, 1 agent,
+// hard_mode (compile-time default): 40 x 40 world; easy_mode (20 x 20) is the <Game>T<0> instantiation. Entity ids per episode: 0 goal, 1 agent,
 // 2.. objects (obstacles, then targets, then enemies). The four post-prune automaton passes never feed back
 // into the tile map and are skipped.
 #pragma once
@@ -38,9 +38,12 @@ namespace pg2 {
 
 PG2_DEFINE_STATE(CaveFlyerState, PG2_CAVEFLYER_FIELDS)
 
-struct CaveFlyer {
+template <int MODE>
+struct CaveFlyerT {
     using State = CaveFlyerState;
-    static constexpr int W = 40, H = 40, MAX_OBJ = 64, NB = 32, NPART = 10;
+    static constexpr int W = MODE == 0 ? 20 : 40, H = W;   // world_dim (tilemap.cpp regenerate: easy 20, hard 40)
+    static constexpr int TILE_STRIDE = 1600;   // per-env extent of State::tiles (the field's size, whatever the world size)
+    static constexpr int MAX_OBJ = 64, NB = 32, NPART = 10;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = false;   // step() supports warp-per-env (ctx) but measures faster thread-per-env (r01j)
     static constexpr int STEP_LANES = 32;       // (lane-aware games only) lanes per environment in k_step
@@ -55,8 +58,8 @@ struct CaveFlyer {
     static constexpr int WIN_ROWS = 11;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
     static constexpr int BLIT_UNROLL = 1;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
     static constexpr int RENDER_MIN_CTAS = 8;   // CTAs per SM the register allocation of k_render aims at
-    static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
-    static bool mode_supported(int mode) { return mode == 1; }
+    static constexpr int DEFAULT_MODE = MODE;    // this instantiation's distribution mode (the reference compiles in 1 = hard; tilemap.h Config)
+    static bool mode_supported(int mode) { return mode == MODE; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = false;   // the camera follows the agent: the base image changes every frame (a camera-keyed cache measured slower)
     enum Obj { O_NONE = 0, O_OBSTACLE, O_TARGET, O_ENEMY };
@@ -91,7 +94,7 @@ struct CaveFlyer {
     // ---------------------------------------------------------------------------------------
     static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward, const StepCtx& ctx) {
         const int N = s.N;
-        const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
+        const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
         const float dt = 1.0f / SUB_STEPS;
         const double PI = 3.14159265358979323846;
         const int nobj = s.num_obj[env];
@@ -339,7 +342,7 @@ struct CaveFlyer {
         __syncwarp();
         for (int k = lane; k < nsp; k += WARP_LANES) s.sprite_order[k * N + env] = (uint8_t)(order[k] == 0 ? 0 : order[k] - 1);
 
-        uint8_t* gt = s.tiles + (size_t)env * (W * H);
+        uint8_t* gt = s.tiles + (size_t)env * TILE_STRIDE;
         for (int i = lane; i < W * H; i += WARP_LANES) gt[i] = tiles[i] == 1 ? 1 : 0;   // markers cleared
         for (int k = lane; k < num_objects; k += WARP_LANES) {
             s.obj_type[k * N + env] = otype[k];
@@ -369,7 +372,7 @@ struct CaveFlyer {
 
     template <class F>
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
-        const int tid = threadIdx.x, N = s.N;
+        const int N = s.N;
         const double PI = 3.14159265358979323846;
         Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(0.5f, f.view_w), 64.0f), f.view_w, f.view_h };
         int lx, ly, ux, uy;
@@ -388,7 +391,7 @@ struct CaveFlyer {
             return sprite_alive(sp) ? sp : -1; });
         const int num_bullets = s.num_bullets[env], next_bullet = s.next_bullet[env];
         const int o_spr = NPART, o_bul = o_spr + nlive, o_ship = o_bul + num_bullets;
-        const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
+        const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
         build_tile_layer(f, cam, tex, 1, lx, ly, ncol, nrow, [](int) { return (int)T_WALL; },
                          [&](int x, int y) { return get(tiles, x, H - 1 - y) == 1 ? (int)T_WALL : (int)NO_TILE; }, bg, bg_x, 0.0f, bg_scale);
         emit_post_blits(f, tex, o_ship + 1, [&](int k, BlitReq& b, BlitRot& rot) {
@@ -438,5 +441,6 @@ struct CaveFlyer {
         });
     }
 };
+using CaveFlyer = CaveFlyerT<1>;
 
 }  // namespace pg2

@@ -5,8 +5,11 @@
 //   level gen   System_Tilemap::regenerate tilemap.cpp:80-243 (spawn helpers :30-78),
 //               Maze_Generator::generate_maze maze_generator.cpp:47-130, reset() chaser.cpp:420-447
 //   frame       render_game chaser.cpp:390-418; tilemap.cpp:245-267; common_systems.cpp:42-64, 446-462
-// easy_mode (compile-time default, tilemap.h:40): 11 x 11 world, 3 enemies, 4 orbs.
-// Entity ids per episode: 0-3 orbs, 4-6 eggs, 7-69 points, 70 agent.
+// All three distribution modes of tilemap.cpp:85-99 as ChaserT<MODE>: 0 easy (the reference's compiled-in default,
+// tilemap.h:40): 11 x 11 world, 3 enemies, 4 orbs; 1 hard: 13 x 13, 3 enemies, 3 orbs (one quadrant has none);
+// 2 extreme: 19 x 19, 5 enemies, 5 orbs (one quadrant has two).
+// Entity ids per episode, easy: 0-3 orbs, 4-6 eggs, 7-69 points, 70 agent (orbs, eggs, points, agent in
+// creation order in every mode).
 // abs() on floats is the float overload.
 #pragma once
 #include "../pg2_common.cuh"
@@ -19,47 +22,66 @@
 
 namespace pg2 {
 
-#define PG2_CHASER_FIELDS(F)                                                                    \
-    F(uint8_t, tiles, 128)      /* env-major [y + x*11]: 0 empty, 1 wall */                       \
-    F(uint8_t, free_cells, 64)  /* env-major: System_Tilemap::free_cells after regenerate (the point cells) */ \
+// CELL: type of a cell index y + x*H (19 x 19 needs 16 bits); NT / NF / NE / NM: capacities of the tile map, the point
+// cells, the sprite entities and the mobs
+#define PG2_CHASER_FIELDS_(F, CELL, NT, NF, NE, NM)                                                \
+    F(uint8_t, tiles, NT)       /* env-major [y + x*H]: 0 empty, 1 wall */                         \
+    F(CELL, free_cells, NF)     /* env-major: System_Tilemap::free_cells after regenerate (the point cells) */ \
     F(int32_t, num_free, 1)                                                                       \
     F(int32_t, num_ents, 1)     /* sprite entities: orbs, eggs, points */                         \
-    F(uint8_t, ent_kind, 72)    /* slot-major: 1 orb, 2 egg/mob, 3 point, 0 destroyed */          \
-    F(uint8_t, ent_cell, 72)    /* spawn cell index (y + x*11, map space) of orbs and points */   \
-    F(uint8_t, sprite_order, 72) /* iteration order of System_Sprite_Render::entities at reset */ \
-    F(uint8_t, mob_order, 4)    /* iteration order of System_Mob_AI::entities (mob slots 0..2) */ \
+    F(uint8_t, ent_kind, NE)    /* slot-major: 1 orb, 2 egg/mob, 3 point, 0 destroyed */          \
+    F(CELL, ent_cell, NE)       /* spawn cell index (y + x*H, map space) of orbs and points */    \
+    F(uint8_t, sprite_order, NE) /* iteration order of System_Sprite_Render::entities at reset */ \
+    F(uint8_t, mob_order, NM + 1) /* iteration order of System_Mob_AI::entities (mob slots 0..NM-1) */ \
     F(int32_t, nb_sprite, 1) F(int32_t, nb_mob, 1)   /* persisted bucket counts (Q25) */           \
-    F(float, mob_x, 3) F(float, mob_y, 3) F(float, mob_vx, 3) F(float, mob_vy, 3)                  \
-    F(float, mob_hatch, 3) F(uint8_t, mob_tex, 3)                                                  \
+    F(float, mob_x, NM) F(float, mob_y, NM) F(float, mob_vx, NM) F(float, mob_vy, NM)              \
+    F(float, mob_hatch, NM) F(uint8_t, mob_tex, NM)                                                \
     F(float, anim_timer, 1) F(int32_t, anim_index, 1) F(float, eat_timer, 1)                       \
     F(float, ax, 1) F(float, ay, 1) F(float, avx, 1) F(float, avy, 1)                              \
     F(float, next_vx, 1) F(float, next_vy, 1) F(float, input_timer, 1)                             \
     F(int32_t, bg_index, 1) F(float, bg_offset, 1)
+#define PG2_CHASER_FIELDS(F) PG2_CHASER_FIELDS_(F, uint8_t, 128, 64, 72, 3)
+#define PG2_CHASER_FIELDS_HARD(F) PG2_CHASER_FIELDS_(F, uint8_t, 256, 128, 104, 3)
+#define PG2_CHASER_FIELDS_EXTREME(F) PG2_CHASER_FIELDS_(F, uint16_t, 384, 256, 208, 5)
 
 PG2_DEFINE_STATE(ChaserState, PG2_CHASER_FIELDS)
+PG2_DEFINE_STATE(ChaserStateHard, PG2_CHASER_FIELDS_HARD)
+PG2_DEFINE_STATE(ChaserStateExtreme, PG2_CHASER_FIELDS_EXTREME)
+template <int MODE> struct ChaserStateOf { using type = ChaserState; using cell_t = uint8_t; };
+template <> struct ChaserStateOf<1> { using type = ChaserStateHard; using cell_t = uint8_t; };
+template <> struct ChaserStateOf<2> { using type = ChaserStateExtreme; using cell_t = uint16_t; };
 
-struct Chaser {
-    using State = ChaserState;
-    static constexpr int W = 11, H = 11, MAX_ENTS = 72, NMOB = 3;
+template <int MODE>
+struct ChaserT {
+    using State = typename ChaserStateOf<MODE>::type;
+    using cell_t = typename ChaserStateOf<MODE>::cell_t;
+    static constexpr int W = MODE == 1 ? 13 : MODE == 2 ? 19 : 11, H = W;   // world_dim (tilemap.cpp:85-99)
+    static constexpr int NMOB = MODE == 2 ? 5 : 3;                          // total_enemies
+    static constexpr int ORB_SIGN = MODE == 1 ? -1 : MODE == 2 ? 1 : 0;     // extra_orb_sign: orbs of the one "extra" quadrant
+    static constexpr int NORB = 4 + ORB_SIGN;                               // orbs = the first entity ids, the eggs follow
+    static constexpr int MAX_ENTS = MODE == 1 ? 104 : MODE == 2 ? 208 : 72; // orbs + eggs + points (70 / 96 / 198 in every level seen)
+    static constexpr int QUAD_CAP = MODE == 2 ? 128 : 64;                   // free cells of one quadrant
+    static constexpr int FC_CAP = MODE == 2 ? 256 : 128;                    // free cells of the world
+    using Set = USet<(MODE == 2 ? 256 : 128), (MODE == 2 ? 264 : 128)>;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = true;    // step(): the point loop is strided over ctx's lanes, the rest is uniform
     static constexpr int STEP_LANES = 32;       // lanes per environment in k_step
-    static constexpr int MAX_POST = 80;        // capacity of the frame's post-blit list
+    static constexpr int MAX_POST = MODE == 1 ? 104 : MODE == 2 ? 208 : 80;   // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;    // level generation (Kruskal + set orders, ~0.1 ms) runs concurrently with the render of the other envs: +22 % at 4096 envs
-    static constexpr int RESET_ARENA = 10 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
+    static constexpr int RESET_ARENA = (MODE == 1 ? 14 : MODE == 2 ? 28 : 10) * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
     static constexpr bool PREFETCH_LEVELS = false;   // step() draws from the RNG: the next level is not known ahead of time
     static constexpr int PREFETCH_MIN_EPISODE = 0;   // level prefetch whatever max_episode_steps is
     static const char* reset_keeps() { return ""; }
     static constexpr int TILE_CLASSES = 1;
-    static constexpr int WIN_ROWS = 14;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
+    static constexpr int WIN_ROWS = MODE == 1 ? 16 : MODE == 2 ? 22 : 14;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
     static constexpr int BLIT_UNROLL = 1;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
     static constexpr int RENDER_MIN_CTAS = 8;   // CTAs per SM the register allocation of k_render aims at
-    static constexpr int DEFAULT_MODE = 0;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
-    static bool mode_supported(int mode) { return mode == 0; }
+    static constexpr int DEFAULT_MODE = MODE;    // this instantiation's distribution mode (the reference compiles in 0 = easy; tilemap.h Config)
+    static bool mode_supported(int mode) { return mode == MODE; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = true;    // fixed camera and tile map within an episode: the base image (background + tiles) is cached per env
-    static constexpr int TILE_STRIDE = 128, FREE_STRIDE = 64;
+    static constexpr int TILE_STRIDE = MODE == 1 ? 256 : MODE == 2 ? 384 : 128, FREE_STRIDE = MODE == 1 ? 128 : MODE == 2 ? 256 : 64;
     enum Kind { K_NONE = 0, K_ORB, K_MOB, K_POINT };
     enum Tex { T_WALL = 0, T_CRYSTAL, T_EGG, T_POINT, T_FLY0, T_FLY1, T_FLY2, T_WALK, T_AGENT, T_BG0, NUM_BG = 9, NUM_TEX = 18 };
 
@@ -255,15 +277,15 @@ struct Chaser {
         const int N = s.N, lane = w.lane;
         uint8_t* tiles = w.alloc<uint8_t>(TILE_STRIDE);   // 0 empty, 1 wall, 2 marker
         uint8_t* kinds = w.alloc<uint8_t>(MAX_ENTS);
-        uint8_t* cells = w.alloc<uint8_t>(MAX_ENTS);
-        uint8_t* quad = w.alloc<uint8_t>(4 * 64);
-        uint8_t* fc = w.alloc<uint8_t>(128);
+        cell_t* cells = w.alloc<cell_t>(MAX_ENTS);
+        cell_t* quad = w.alloc<cell_t>(4 * QUAD_CAP);
+        cell_t* fc = w.alloc<cell_t>(FC_CAP);
         uint8_t* order = w.alloc<uint8_t>(MAX_ENTS);
-        USet<128, 128>* us = w.alloc<USet<128, 128>>(1);
+        Set* us = w.alloc<Set>(1);
         int nents = 0;
 
         MazeGrid mg = kruskal_maze(w, W, H);
-        w.rng.uniform_int(0, 3);   // extra_quad: extra_orb_sign == 0 in easy mode, the draw is still consumed
+        const int extra_quad = w.rng.uniform_int(0, 3);   // drawn in every mode (extra_orb_sign == 0 in easy mode)
 
         int nq[4] = { 0, 0, 0, 0 };
         for (int x = 0; x < W; x++)
@@ -272,21 +294,34 @@ struct Chaser {
                 tiles[y + x * H] = obj == 1 ? 1 : 0;
                 if (obj == 0) {
                     int qi = (x >= W / 2) * 2 + (y >= H / 2);
-                    quad[qi * 64 + nq[qi]] = (uint8_t)(y + x * H);
+                    if (nq[qi] < QUAD_CAP) quad[qi * QUAD_CAP + nq[qi]] = (cell_t)(y + x * H);
                     nq[qi]++;
                 }
             }
         __syncwarp();
+        bool quad_overflow = false;
         for (int i = 0; i < 4; i++) {
-            // one orb per quadrant: selected_indices = { pos }
-            int pos = w.rng.uniform_int(0, nq[i] - 1);
-            int cell = quad[i * 64 + pos];
-            kinds[nents] = K_ORB; cells[nents] = (uint8_t)cell; nents++;
-            tiles[cell] = 2;
+            // 1 + (i == extra_quad ? extra_orb_sign : 0) orbs per quadrant, distinct positions, spawned in the
+            // iteration order of the local unordered_set (tilemap.cpp:146-170)
+            if (nq[i] > QUAD_CAP) { quad_overflow = true; nq[i] = QUAD_CAP; }
+            const int num_orbs = 1 + (i == extra_quad ? ORB_SIGN : 0);
+            us->init(1);
+            for (int j = 0; j < num_orbs; j++) {
+                int pos = w.rng.uniform_int(0, nq[i] - 1);
+                while (us->count > 0 && us->contains(pos)) pos = (pos + 1) % nq[i];
+                us->insert(pos);
+            }
+            const int nsel = us->order(order);
+            __syncwarp();
+            for (int j = 0; j < nsel; j++) {
+                int cell = quad[i * QUAD_CAP + order[j]];
+                kinds[nents] = K_ORB; cells[nents] = (cell_t)cell; nents++;
+                tiles[cell] = 2;
+            }
             __syncwarp();
         }
         int nfree = 0;
-        for (int i = 0; i < W * H; i++) if (tiles[i] == 0) fc[nfree++] = (uint8_t)i;
+        for (int i = 0; i < W * H; i++) if (tiles[i] == 0) { if (nfree < FC_CAP) fc[nfree] = (cell_t)i; nfree++; }
         __syncwarp();
         // agent + 3 eggs: distinct positions into free_cells, walked in unordered_set order (Q4)
         us->init(1);
@@ -303,20 +338,20 @@ struct Chaser {
         tiles[start] = 2;
         for (int i = 0; i < NMOB; i++) {
             egg_cell[i] = fc[order[1 + i]];
-            kinds[nents] = K_MOB; cells[nents] = (uint8_t)egg_cell[i]; nents++;
+            kinds[nents] = K_MOB; cells[nents] = (cell_t)egg_cell[i]; nents++;
             tiles[egg_cell[i]] = 2;
         }
         __syncwarp();
         nfree = 0;
-        for (int i = 0; i < W * H; i++) if (tiles[i] == 0) fc[nfree++] = (uint8_t)i;
-        for (int i = 0; i < nfree; i++) { kinds[nents] = K_POINT; cells[nents] = fc[i]; nents++; }
+        for (int i = 0; i < W * H; i++) if (tiles[i] == 0) { if (nfree < FC_CAP) fc[nfree] = (cell_t)i; nfree++; }
+        for (int i = 0; i < nfree && nents < MAX_ENTS; i++) { kinds[nents] = K_POINT; cells[nents] = fc[i]; nents++; }
         __syncwarp();
 
         // ---- reset() tail (chaser.cpp:425-446)
         int bg_index = w.rng.uniform_int(0, NUM_BG - 1);
         float bg_offset = w.rng.uniform_real(0.0f, 1.0f);
 
-        // ---- ECS set orders: sprite_render = every entity above (ids ascending), mob_ai = eggs (ids 4..6)
+        // ---- ECS set orders: sprite_render = every entity above (ids ascending), mob_ai = eggs (ids NORB ..)
         us->init(s.nb_sprite[env]);
         for (int e = 0; e < nents; e++) us->insert(e);
         int n_sprite = us->order(order);
@@ -325,15 +360,15 @@ struct Chaser {
         for (int k = lane; k < n_sprite; k += WARP_LANES) s.sprite_order[k * N + env] = order[k];
         __syncwarp();
         us->init(s.nb_mob[env]);
-        for (int i = 0; i < NMOB; i++) us->insert(4 + i);
+        for (int i = 0; i < NMOB; i++) us->insert(NORB + i);
         us->order(order);
         int nb_mob = us->nb;
         __syncwarp();
-        for (int k = lane; k < NMOB; k += WARP_LANES) s.mob_order[k * N + env] = (uint8_t)(order[k] - 4);
+        for (int k = lane; k < NMOB; k += WARP_LANES) s.mob_order[k * N + env] = (uint8_t)(order[k] - NORB);
 
         uint8_t* gt = s.tiles + (size_t)env * TILE_STRIDE;
         for (int i = lane; i < W * H; i += WARP_LANES) gt[i] = tiles[i] == 1 ? 1 : 0;   // markers cleared
-        uint8_t* gf = s.free_cells + (size_t)env * FREE_STRIDE;
+        cell_t* gf = s.free_cells + (size_t)env * FREE_STRIDE;
         for (int i = lane; i < nfree && i < FREE_STRIDE; i += WARP_LANES) gf[i] = fc[i];
         for (int e = lane; e < nents; e += WARP_LANES) { s.ent_kind[e * N + env] = kinds[e]; s.ent_cell[e * N + env] = cells[e]; }
         for (int i = lane; i < NMOB; i += WARP_LANES) {
@@ -354,7 +389,7 @@ struct Chaser {
             c.cam_x[env] = __fmul_rn(__fmul_rn((float)W, 0.5f), UNIT_TO_PIXELS);
             c.cam_y[env] = __fmul_rn(__fmul_rn((float)H, 0.5f), UNIT_TO_PIXELS);
             c.sprites_valid[env] = 0;
-            if (nfree > FREE_STRIDE || nents > MAX_ENTS) c.fault[env] |= 1;
+            if (nfree > FREE_STRIDE || nfree + NORB + NMOB > MAX_ENTS || quad_overflow) c.fault[env] |= 1;
         }
     }
 
@@ -363,7 +398,7 @@ struct Chaser {
 
     template <class F>
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
-        const int tid = threadIdx.x, N = s.N;
+        const int N = s.N;
         // game_zoom = width * pixels_to_unit / map_width (chaser.cpp:401)
         Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(f.view_w, PIXELS_TO_UNIT), (float)W), f.view_w, f.view_h };
         int lx, ly, ux, uy;
@@ -388,7 +423,7 @@ struct Chaser {
                 int kind = s.ent_kind[e * N + env];
                 int t; float x, y;
                 if (kind == K_MOB) {
-                    int m = e - 4;
+                    int m = e - NORB;
                     t = s.mob_tex[m * N + env]; x = s.mob_x[m * N + env]; y = s.mob_y[m * N + env];
                 } else {
                     int cell = s.ent_cell[e * N + env];
@@ -407,5 +442,6 @@ struct Chaser {
         });
     }
 };
+using Chaser = ChaserT<0>;
 
 }  // namespace pg2

@@ -316,7 +316,7 @@ struct Climber {
 
     template <class F>
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
-        const int tid = threadIdx.x, N = s.N;
+        const int N = s.N;
         Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(0.2f, f.view_w), 64.0f), f.view_w, f.view_h };
         int lx, ly, ux, uy;
         tile_window(cam, &lx, &ly, &ux, &uy);

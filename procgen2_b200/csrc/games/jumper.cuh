@@ -5,7 +5,7 @@
 //               maze_generator.cpp:47-173, Room_Generator room_generator.cpp, reset() jumper.cpp:512-535
 //   frame       render_game incl. compass HUD jumper.cpp:445-510; tilemap.cpp:255-278;
 //               common_systems.cpp:26-48, 204-244, 281-303
-// hard_mode (compile-time default): 40 x 40 world. Entity ids: 0 goal, 1 agent, 2.. spikes.
+// hard_mode (compile-time default): 40 x 40 world; easy_mode (20 x 20) is the <Game>T<0> instantiation. Entity ids: 0 goal, 1 agent, 2.. spikes.
 #pragma once
 #include "../pg2_common.cuh"
 #include "../pg2_libm.cuh"
@@ -36,9 +36,12 @@ namespace pg2 {
 
 PG2_DEFINE_STATE(JumperState, PG2_JUMPER_FIELDS)
 
-struct Jumper {
+template <int MODE>
+struct JumperT {
     using State = JumperState;
-    static constexpr int W = 40, H = 40, MAX_SPIKES = 64, NPART = 10;
+    static constexpr int W = MODE == 0 ? 20 : 40, H = W;   // world_dim (tilemap.cpp regenerate: easy 20, hard 40)
+    static constexpr int TILE_STRIDE = 1600;   // per-env extent of State::tiles (the field's size, whatever the world size)
+    static constexpr int MAX_SPIKES = 64, NPART = 10;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = false;   // step() supports warp-per-env (ctx) but measures faster thread-per-env (r01j)
     static constexpr int STEP_LANES = 32;       // (lane-aware games only) lanes per environment in k_step
@@ -53,8 +56,8 @@ struct Jumper {
     static constexpr int WIN_ROWS = 16;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
     static constexpr int BLIT_UNROLL = 1;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
     static constexpr int RENDER_MIN_CTAS = 8;   // CTAs per SM the register allocation of k_render aims at
-    static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
-    static bool mode_supported(int mode) { return mode == 1; }
+    static constexpr int DEFAULT_MODE = MODE;    // this instantiation's distribution mode (the reference compiles in 1 = hard; tilemap.h Config)
+    static bool mode_supported(int mode) { return mode == MODE; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = false;   // the camera follows the agent: the base image changes every frame (a camera-keyed cache measured slower)
     enum Tile { EMPTY = 0, WALL_TOP, WALL_MID, SPIKE };
@@ -89,7 +92,7 @@ struct Jumper {
     // ---------------------------------------------------------------------------------------
     static PG2_DEV_NOINLINE bool step(const State& s, const CommonState& c, int env, int action, float* reward, const StepCtx& ctx) {
         const int N = s.N;
-        const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
+        const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
         const float dt = 1.0f / SUB_STEPS;
         const int nspikes = s.num_spikes[env];
         auto tile_at = [&](int x, int y) { return get(tiles, x, H - 1 - y); };
@@ -345,7 +348,7 @@ struct Jumper {
         __syncwarp();
         for (int k = lane; k < nsp; k += WARP_LANES) s.sprite_order[k * N + env] = (uint8_t)(order[k] == 0 ? 0 : order[k] - 1);
 
-        uint8_t* gt = s.tiles + (size_t)env * (W * H);
+        uint8_t* gt = s.tiles + (size_t)env * TILE_STRIDE;
         for (int i = lane; i < W * H / 4; i += WARP_LANES) ((uint32_t*)gt)[i] = ((const uint32_t*)tiles)[i];
         for (int k = lane; k < nspikes; k += WARP_LANES) s.spike_cell[k * N + env] = spikes[k];
         for (int k = lane; k < NPART; k += WARP_LANES) { s.p_x[k * N + env] = 0.0f; s.p_y[k * N + env] = 0.0f; s.p_life[k * N + env] = 0.0f; }
@@ -368,7 +371,7 @@ struct Jumper {
 
     template <class F>
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
-        const int tid = threadIdx.x, N = s.N;
+        const int N = s.N;
         const float zoom = 0.3f;
         Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(__fmul_rn(zoom, f.view_w), 64.0f), f.view_w, f.view_h };
         int lx, ly, ux, uy;
@@ -384,7 +387,7 @@ struct Jumper {
         const float bg_scale = __fdiv_rn(__fmul_rn(64.0f, UNIT_TO_PIXELS), (float)bt.h);
         const int o_spr = NPART, o_agent = o_spr + nspr, o_hud = o_agent + 1;
         // tile layer: class 0 = wall_mid texture of the theme, class 1 = wall_top texture
-        const uint8_t* tiles = s.tiles + (size_t)env * (W * H);
+        const uint8_t* tiles = s.tiles + (size_t)env * TILE_STRIDE;
         build_tile_layer(f, cam, tex, 2, lx, ly, ncol, nrow, [&](int cls) { return (cls ? T_WALL_TOP0 : T_WALL_MID0) + theme; }, [&](int x, int y) {
             const int id = get(tiles, x, H - 1 - y);
             return id == WALL_MID ? T_WALL_MID0 + theme : id == WALL_TOP ? T_WALL_TOP0 + theme : (int)NO_TILE;
@@ -454,5 +457,6 @@ struct Jumper {
         });
     }
 };
+using Jumper = JumperT<1>;
 
 }  // namespace pg2

@@ -176,7 +176,6 @@ struct MazeT {
 
     template <class F>
     static PG2_DEV_NOINLINE void build_frame(const State& s, const CommonState& c, int env, F& f, const TexInfo* tex) {
-        const int tid = threadIdx.x;
         Camera cam{ c.cam_x[env], c.cam_y[env], __fdiv_rn(f.view_w, __fmul_rn(UNIT_TO_PIXELS, (float)VISIBLE)), f.view_w, f.view_h };   // maze.cpp:403: zoom from the width
         int lx, ly, ux, uy;
         tile_window(cam, &lx, &ly, &ux, &uy);

@@ -47,7 +47,7 @@ constexpr int BAND_ROWS = PG2_BAND_ROWS, NUM_BANDS = OBS_H / BAND_ROWS, BAND_BYT
 // by z with std::sort (common_systems.cpp:36-38); every sprite of a game has the same z, so the
 // comparator is always false and the resulting permutation depends on n only. It is computed on
 // the host with the real std::sort (sort_perm.h) and uploaded: sorted[k] = input[perm[n][k]].
-constexpr int SORT_MAXN = 128;
+constexpr int SORT_MAXN = 256;   // chaser extreme draws 198 sprites (f.live holds 256 ids)
 #ifdef PG2_HOSTSIM
 static const uint8_t* g_sort_perm = nullptr;
 #else

@@ -161,20 +161,22 @@ def test_cenv_render_matches_oracle(game, oracle_available):
         env.close(); ref.close()
 
 
-def test_distribution_mode_option(oracle_available):
-    """cenv make-option "distribution_mode": climber easy (0) on the GPU against the reference with Config::easy_mode set;
-    a (game, mode) pair that is not built is refused loudly."""
+@pytest.mark.parametrize("game", ["climber", "bossfight"])
+def test_distribution_mode_option(game, oracle_available):
+    """cenv make-option "distribution_mode" = 0 (easy) on the GPU against the reference with its compile-time mode flipped
+    through the probe (climber: Config::easy_mode; bossfight: System_Mob_AI::Config::mode); a (game, mode) pair that is
+    not built is refused loudly."""
     from procgen2_b200.engine import BatchedEnv
     with pytest.raises(RuntimeError, match="distribution_mode"):
-        BatchedEnv("chaser", 4, distribution_mode=2)      # chaser extreme: not built
+        BatchedEnv("jumper", 4, distribution_mode=2)      # jumper memory: not built
     if not oracle_available:
         pytest.skip("oracle/_ref did not travel")
     from oracle import ref_env
-    n, seed, T = 32, 9100, 90
+    n, seed, T, ep = (32, 9100, 90, 30) if game == "climber" else (12, 9100, 500, 250)
     rs = np.random.RandomState(12)
     acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
-    env = BatchedEnv("climber", n, seed=seed, max_episode_steps=30, distribution_mode=0)
-    refs = [ref_env.RefEnv("climber", seed + i, easy_mode=True) for i in range(n)]
+    env = BatchedEnv(game, n, seed=seed, max_episode_steps=ep, distribution_mode=0)
+    refs = [ref_env.RefEnv(game, seed + i, **(dict(easy_mode=True) if game == "climber" else dict(mode=0))) for i in range(n)]
     env.reset()
     np.testing.assert_array_equal(env.fetch()[0], np.stack([r.reset() for r in refs]))
     age = np.zeros(n, np.int64)
@@ -184,7 +186,7 @@ def test_distribution_mode_option(oracle_available):
         for i, r in enumerate(refs):
             oo, w, dd = r.step(acts[t, i])
             age[i] += 1
-            if dd or age[i] >= 30:
+            if dd or age[i] >= ep:
                 oo = r.reset(); age[i] = 0
             assert w == rw[i] and dd == d[i]
             np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))
@@ -193,25 +195,28 @@ def test_distribution_mode_option(oracle_available):
     env.close()
 
 
-@pytest.mark.parametrize("mode", [0, 2])
-def test_maze_world_size_modes(mode, oracle_available):
-    """maze easy (15x15) / memory (31x31, agent-centred 8x8 view) = the MazeT<MODE> instantiations, against the reference with
-    its compile-time Config::mode set: tile maps + RNG after make, pixels / rewards / dones over truncated episodes."""
+@pytest.mark.parametrize("game,mode,dim,max_ep,T", [("maze", 0, 15, 40, 150), ("maze", 2, 31, 40, 150),
+                                                    ("chaser", 1, 13, 120, 300), ("chaser", 2, 19, 120, 300),
+                                                    ("jumper", 0, 20, 100, 250), ("caveflyer", 0, 20, 100, 250)])
+def test_world_size_modes(game, mode, dim, max_ep, T, oracle_available):
+    """Distribution modes with their own world size = own instantiations (maze easy 15x15 / memory 31x31 with an agent-centred
+    8x8 view: MazeT<MODE>; chaser hard 13x13 / extreme 19x19 with 5 enemies and 5 orbs: ChaserT<MODE>; jumper / caveflyer easy 20x20), against the reference
+    with its compile-time Config::mode set: tile maps + RNG after make, pixels / rewards / dones over truncated episodes."""
     if not oracle_available:
         pytest.skip("oracle/_ref did not travel")
     from oracle import ref_env
     from procgen2_b200.engine import BatchedEnv
-    n, seed, T = 48, 8300 + mode, 150
+    n, seed = 48, 8300 + mode
     rs = np.random.RandomState(mode)
     acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
-    env = BatchedEnv("maze", n, seed=seed, max_episode_steps=40, distribution_mode=mode)
-    refs = [ref_env.RefEnv("maze", seed + i, mode=mode) for i in range(n)]
+    env = BatchedEnv(game, n, seed=seed, max_episode_steps=max_ep, distribution_mode=mode)
+    refs = [ref_env.RefEnv(game, seed + i, mode=mode) for i in range(n)]
     tb, _, pe = env.read_field("tiles")
     tiles = tb.reshape(n, pe)
     for i, r in enumerate(refs):
         rt = r.tiles()
         w, h = rt.shape
-        assert w == (15 if mode == 0 else 31)
+        assert w == dim
         np.testing.assert_array_equal(tiles[i, :w * h].reshape(w, h), rt, err_msg="tile map after make, env %d" % i)
     env.reset()
     np.testing.assert_array_equal(env.fetch()[0], np.stack([r.reset() for r in refs]))
@@ -222,7 +227,7 @@ def test_maze_world_size_modes(mode, oracle_available):
         for i, r in enumerate(refs):
             oo, w, dd = r.step(acts[t, i])
             age[i] += 1
-            if dd or age[i] >= 40:
+            if dd or age[i] >= max_ep:
                 oo = r.reset(); age[i] = 0
             assert w == rw[i] and dd == d[i], (t, i)
             np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))

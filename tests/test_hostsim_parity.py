@@ -160,19 +160,20 @@ def test_human_render_live_oracle(game, oracle_available):
             r.close()
 
 
-@pytest.mark.parametrize("game", ["climber", "coinrun"])
+@pytest.mark.parametrize("game", ["climber", "coinrun", "bossfight"])
 def test_easy_distribution_mode_live_oracle(game, oracle_available):
     """Make-option distribution_mode = 0 (easy) against the reference with its compile-time Config::easy_mode flipped
     (climber: enemy probability .2 instead of .5, tilemap.cpp:118; coinrun: the flag only feeds a variable nothing reads,
-    tilemap.cpp:148 — same levels as hard)."""
+    tilemap.cpp:148 — same levels as hard; bossfight: System_Mob_AI::Config::mode, boss bullets at half speed and shielded
+    phases of 180 + 30 u instead of 180 + 80 u steps, common_systems.cpp:104, 202)."""
     if not oracle_available:
         pytest.skip("oracle/_ref not built")
     from oracle import ref_env
-    n, seed, T = 6, 9100, 120
+    n, seed, T, ep = (6, 9100, 120, 30) if game != "bossfight" else (4, 9100, 700, 350)
     rs = np.random.RandomState(12)
     acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
-    sim = SimAdapter(game, n, seed, max_episode_steps=30, distribution_mode=0)
-    refs = [ref_env.RefEnv(game, seed + i, easy_mode=True) for i in range(n)]
+    sim = SimAdapter(game, n, seed, max_episode_steps=ep, distribution_mode=0)
+    refs = [ref_env.RefEnv(game, seed + i, **(dict(mode=0) if game == "bossfight" else dict(easy_mode=True))) for i in range(n)]
     np.testing.assert_array_equal(sim.reset(), np.stack([r.reset() for r in refs]))
     age = np.zeros(n, np.int64)
     for t in range(T):
@@ -180,7 +181,7 @@ def test_easy_distribution_mode_live_oracle(game, oracle_available):
         for i, r in enumerate(refs):
             oo, w, dd = r.step(acts[t, i])
             age[i] += 1
-            if dd or age[i] >= 30:
+            if dd or age[i] >= ep:
                 oo = r.reset(); age[i] = 0
             assert w == rw[i] and dd == d[i]
             np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))
@@ -193,9 +194,13 @@ def test_easy_distribution_mode_live_oracle(game, oracle_available):
     if game == "climber":   # the mode does change climber's levels (fewer enemies): easy and hard runs part ways
         easy, hard = SimAdapter(game, n, seed, distribution_mode=0), SimAdapter(game, n, seed, distribution_mode=1)
         assert any(not np.array_equal(easy.reset(), hard.reset()) for _ in range(6))
+    if game == "bossfight":   # ... and bossfight's frames once the boss has fired
+        easy, hard = SimAdapter(game, n, seed, distribution_mode=0), SimAdapter(game, n, seed, distribution_mode=1)
+        easy.reset(); hard.reset()
+        assert any(not np.array_equal(easy.step(acts[t])[0], hard.step(acts[t])[0]) for t in range(200))
 
 
-@pytest.mark.parametrize("game,mode", [("maze", 0), ("maze", 2)])
+@pytest.mark.parametrize("game,mode", [("maze", 0), ("maze", 2), ("chaser", 1), ("chaser", 2), ("jumper", 0), ("caveflyer", 0)])
 def test_world_size_modes_live_oracle(game, mode, oracle_available):
     """Distribution modes that change the world size (own instantiations, G = <Game>T<MODE>) against the reference with its
     compile-time Config::mode set through the probe: levels (tile map + RNG state), pixels, rewards, dones, truncation."""
