@@ -25,4 +25,6 @@
     X("chaser", 1, pg2::ChaserT<1>) \
     X("chaser", 2, pg2::ChaserT<2>) \
     X("jumper", 0, pg2::JumperT<0>)   \
-    X("caveflyer", 0, pg2::CaveFlyerT<0>)
+    X("jumper", 2, pg2::JumperT<2>)   \
+    X("caveflyer", 0, pg2::CaveFlyerT<0>) \
+    X("caveflyer", 2, pg2::CaveFlyerT<2>)

@@ -5,10 +5,11 @@
 //   level gen   System_Tilemap::regenerate tilemap.cpp:118-278 (spawn helpers :35-116), Room_Generator
 //               room_generator.cpp, reset() caveflyer.cpp:442-462
 //   frame       render_game caveflyer.cpp:413-440; tilemap.cpp:280-303; common_systems.cpp:26-48, 291-326, 374-398
-// hard_mode (compile-time default): 40 x 40 world; easy_mode (20 x 20) is the <Game>T<0> instantiation. Entity ids per episode: 0 goal, 1 agent,
+// hard_mode (compile-time default): 40 x 40 world; easy_mode (20 x 20) and memory_mode (45 x 45, unpruned caves) are the CaveFlyerT<0> / CaveFlyerT<2> instantiations. Entity ids per episode: 0 goal, 1 agent,
 // 2.. objects (obstacles, then targets, then enemies). The four post-prune automaton passes never feed back
 // into the tile map and are skipped.
 #pragma once
+#include <type_traits>
 #include "../pg2_common.cuh"
 #include "../pg2_libm.cuh"
 #include "../pg2_render.cuh"
@@ -20,8 +21,8 @@
 
 namespace pg2 {
 
-#define PG2_CAVEFLYER_FIELDS(F)                                                                  \
-    F(uint8_t, tiles, 1600)     /* env-major [y + x*40]: 0 empty, 1 wall */                        \
+#define PG2_CAVEFLYER_FIELDS_(F, NT)                                                                \
+    F(uint8_t, tiles, NT)       /* env-major [y + x*H]: 0 empty, 1 wall */                         \
     F(int32_t, num_obj, 1)                                                                         \
     F(uint8_t, obj_type, 64)    /* slot-major; 1 obstacle, 2 target, 3 enemy, 0 destroyed */       \
     F(float, obj_x, 64) F(float, obj_y, 64) F(float, obj_vx, 64) F(float, obj_vy, 64)              \
@@ -36,13 +37,17 @@ namespace pg2 {
     F(float, p_timer, 1) F(uint8_t, p_enabled, 1)                                                  \
     F(int32_t, bg_index, 1) F(float, bg_offset, 1)
 
+#define PG2_CAVEFLYER_FIELDS(F) PG2_CAVEFLYER_FIELDS_(F, 1600)
+#define PG2_CAVEFLYER_FIELDS_MEMORY(F) PG2_CAVEFLYER_FIELDS_(F, 2048)
 PG2_DEFINE_STATE(CaveFlyerState, PG2_CAVEFLYER_FIELDS)
+PG2_DEFINE_STATE(CaveFlyerStateMemory, PG2_CAVEFLYER_FIELDS_MEMORY)
 
 template <int MODE>
 struct CaveFlyerT {
-    using State = CaveFlyerState;
-    static constexpr int W = MODE == 0 ? 20 : 40, H = W;   // world_dim (tilemap.cpp regenerate: easy 20, hard 40)
-    static constexpr int TILE_STRIDE = 1600;   // per-env extent of State::tiles (the field's size, whatever the world size)
+    using State = typename std::conditional<MODE == 2, CaveFlyerStateMemory, CaveFlyerState>::type;
+    static constexpr int W = MODE == 0 ? 20 : MODE == 2 ? 45 : 40, H = W;   // world_dim (tilemap.cpp:121-126: easy 20, hard 40, memory 45)
+    static constexpr int TILE_STRIDE = MODE == 2 ? 2048 : 1600;   // per-env extent of State::tiles (the field's size, whatever the world size)
+    static constexpr bool PRUNE = MODE != 2;                      // should_prune (tilemap.cpp:203): memory mode keeps every cave of the automaton
     static constexpr int MAX_OBJ = 64, NB = 32, NPART = 10;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = false;   // step() supports warp-per-env (ctx) but measures faster thread-per-env (r01j)
@@ -50,7 +55,7 @@ struct CaveFlyerT {
     static constexpr int MAX_POST = 112;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
-    static constexpr int RESET_ARENA = 52 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
+    static constexpr int RESET_ARENA = (MODE == 2 ? 56 : 52) * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
     static constexpr bool PREFETCH_LEVELS = true;    // the RNG is only drawn inside reset(): the next level is generated one episode ahead
     static constexpr int PREFETCH_MIN_EPISODE = 0;   // level prefetch whatever max_episode_steps is
     static const char* reset_keeps() { return " cam_x cam_y "; }   // fields reset() does not write (they persist across episodes)
@@ -285,8 +290,12 @@ struct CaveFlyerT {
         const float agent_x = __fadd_rn((float)(agent_cell / H), 0.5f), agent_y = (float)(H - 1 - (agent_cell % H));
 
         int plen = rg.find_path(w, agent_cell, goal_cell);
-        rg.expand(w, rg.path, plen, 4, rg.mark);
-        for (int i = lane; i < W * H; i += WARP_LANES) tiles[i] = rg.mark[i] ? 0 : 1;
+        if (PRUNE) {   // only wide_path = goal_path dilated 4 times stays open
+            rg.expand(w, rg.path, plen, 4, rg.mark);
+            for (int i = lane; i < W * H; i += WARP_LANES) tiles[i] = rg.mark[i] ? 0 : 1;
+        } else {       // the automaton's grid as it is (tilemap.cpp:152-160; best_room's cells are spaces of it already)
+            for (int i = lane; i < W * H; i += WARP_LANES) tiles[i] = rg.grid[i] == 1 ? 1 : 0;
+        }
         __syncwarp();
         for (int i = lane; i < plen; i += WARP_LANES) tiles[rg.path[i]] = 2;
         __syncwarp();

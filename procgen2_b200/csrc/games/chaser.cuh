@@ -69,7 +69,7 @@ struct ChaserT {
     static constexpr int MAX_POST = MODE == 1 ? 104 : MODE == 2 ? 208 : 80;   // capacity of the frame's post-blit list
     static constexpr bool ROTATES = false;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;    // level generation (Kruskal + set orders, ~0.1 ms) runs concurrently with the render of the other envs: +22 % at 4096 envs
-    static constexpr int RESET_ARENA = (MODE == 1 ? 14 : MODE == 2 ? 28 : 10) * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
+    static constexpr int RESET_ARENA = (MODE == 1 ? 6 : MODE == 2 ? 10 : 4) * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
     static constexpr bool PREFETCH_LEVELS = false;   // step() draws from the RNG: the next level is not known ahead of time
     static constexpr int PREFETCH_MIN_EPISODE = 0;   // level prefetch whatever max_episode_steps is
     static const char* reset_keeps() { return ""; }

@@ -5,8 +5,9 @@
 //               maze_generator.cpp:47-173, Room_Generator room_generator.cpp, reset() jumper.cpp:512-535
 //   frame       render_game incl. compass HUD jumper.cpp:445-510; tilemap.cpp:255-278;
 //               common_systems.cpp:26-48, 204-244, 281-303
-// hard_mode (compile-time default): 40 x 40 world; easy_mode (20 x 20) is the <Game>T<0> instantiation. Entity ids: 0 goal, 1 agent, 2.. spikes.
+// hard_mode (compile-time default): 40 x 40 world; easy_mode (20 x 20) and memory_mode (45 x 45, unpruned cave, no spikes) are the JumperT<0> / JumperT<2> instantiations. Entity ids: 0 goal, 1 agent, 2.. spikes.
 #pragma once
+#include <type_traits>
 #include "../pg2_common.cuh"
 #include "../pg2_libm.cuh"
 #include "../pg2_mazegen.cuh"
@@ -20,8 +21,8 @@
 
 namespace pg2 {
 
-#define PG2_JUMPER_FIELDS(F)                                                                     \
-    F(uint8_t, tiles, 1600)     /* env-major [y + x*40]: 0 empty, 1 wall_top, 2 wall_mid */        \
+#define PG2_JUMPER_FIELDS_(F, NT)                                                                   \
+    F(uint8_t, tiles, NT)       /* env-major [y + x*H]: 0 empty, 1 wall_top, 2 wall_mid */         \
     F(int32_t, num_spikes, 1)                                                                      \
     F(uint16_t, spike_cell, 64) /* slot-major */                                                   \
     F(uint8_t, sprite_order, 72) /* iteration order of System_Sprite_Render::entities: 0 goal, k+1 spike k */ \
@@ -34,13 +35,18 @@ namespace pg2 {
     F(float, p_x, 10) F(float, p_y, 10) F(float, p_life, 10) F(float, p_timer, 1) F(uint8_t, p_enabled, 1) \
     F(int32_t, bg_index, 1) F(float, bg_offset, 1) F(int32_t, map_theme, 1)
 
+#define PG2_JUMPER_FIELDS(F) PG2_JUMPER_FIELDS_(F, 1600)
+#define PG2_JUMPER_FIELDS_MEMORY(F) PG2_JUMPER_FIELDS_(F, 2048)
 PG2_DEFINE_STATE(JumperState, PG2_JUMPER_FIELDS)
+PG2_DEFINE_STATE(JumperStateMemory, PG2_JUMPER_FIELDS_MEMORY)
 
 template <int MODE>
 struct JumperT {
-    using State = JumperState;
-    static constexpr int W = MODE == 0 ? 20 : 40, H = W;   // world_dim (tilemap.cpp regenerate: easy 20, hard 40)
-    static constexpr int TILE_STRIDE = 1600;   // per-env extent of State::tiles (the field's size, whatever the world size)
+    using State = typename std::conditional<MODE == 2, JumperStateMemory, JumperState>::type;
+    static constexpr int W = MODE == 0 ? 20 : MODE == 2 ? 45 : 40, H = W;   // world_dim (tilemap.cpp:82-87: easy 20, hard 40, memory 45)
+    static constexpr int TILE_STRIDE = MODE == 2 ? 2048 : 1600;   // per-env extent of State::tiles (the field's size, whatever the world size)
+    static constexpr bool PRUNE = MODE != 2;                      // should_prune (tilemap.cpp:176): memory mode keeps the whole cave
+    static constexpr float SPIKE_PROB = MODE == 2 ? 0.0f : 0.2f;  // tilemap.cpp:205 (the draw happens either way)
     static constexpr int MAX_SPIKES = 64, NPART = 10;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = false;   // step() supports warp-per-env (ctx) but measures faster thread-per-env (r01j)
@@ -48,7 +54,7 @@ struct JumperT {
     static constexpr int MAX_POST = 80;        // capacity of the frame's post-blit list
     static constexpr bool ROTATES = true;     // some blits are rotated
     static constexpr bool SLOW_RESET = true;   // level generation is long: run it concurrently with the render of the other envs
-    static constexpr int RESET_ARENA = 52 * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
+    static constexpr int RESET_ARENA = (MODE == 2 ? 64 : 52) * 1024;   // per-warp level-generation scratch (high water measured with PG2_ARENA_TRACE)
     static constexpr bool PREFETCH_LEVELS = true;    // the RNG is only drawn inside reset(): the next level is generated one episode ahead
     static constexpr int PREFETCH_MIN_EPISODE = 0;   // level prefetch whatever max_episode_steps is
     static const char* reset_keeps() { return " cam_x cam_y to_goal_x to_goal_y "; }   // fields reset() does not write (they persist across episodes)
@@ -245,7 +251,7 @@ struct JumperT {
         }
         RoomGen rg;
         rg.init(w, W, H);
-        uint8_t* tiles = w.alloc<uint8_t>(W * H);
+        uint8_t* tiles = w.alloc<uint8_t>((W * H + 3) & ~3);
         uint16_t* cand = rg.parents;                   // agent_candidates (before find_path reuses the buffer)
         uint16_t* spikes = w.alloc<uint16_t>(MAX_SPIKES);
         uint8_t* order = w.alloc<uint8_t>(MAX_SPIKES + 8);
@@ -275,10 +281,12 @@ struct JumperT {
         const int agent_cell = cand[w.rng.uniform_int(0, ncand - 1)];
         __syncwarp();
 
-        int plen = rg.find_path(w, agent_cell, goal_cell);
-        rg.expand(w, rg.path, plen, 4, rg.mark);
-        for (int i = lane; i < W * H; i += WARP_LANES) tiles[i] = rg.mark[i] ? EMPTY : WALL_MID;
-        __syncwarp();
+        if (PRUNE) {   // only wide_path = goal_path dilated 4 times stays open (find_path draws nothing: skipped otherwise)
+            int plen = rg.find_path(w, agent_cell, goal_cell);
+            rg.expand(w, rg.path, plen, 4, rg.mark);
+            for (int i = lane; i < W * H; i += WARP_LANES) tiles[i] = rg.mark[i] ? EMPTY : WALL_MID;
+            __syncwarp();
+        }
 
         const float goal_x = __fadd_rn((float)(goal_cell / H), 0.5f), goal_y = __fadd_rn((float)(H - 1 - goal_cell % H), 0.5f);
 
@@ -292,7 +300,7 @@ struct JumperT {
             for (int k = 0; k < nsc; k++) {
                 int x = sc[k] / H, y = sc[k] % H;
                 if (map.space_on_ground(x, y) && map.space_on_ground(x - 1, y) && map.space_on_ground(x + 1, y)) {
-                    bool put = w.rng.uniform_real(0.0f, 1.0f) < 0.2f;
+                    bool put = w.rng.uniform_real(0.0f, 1.0f) < SPIKE_PROB;
                     __syncwarp();
                     if (put) map.set(x, y, SPIKE);
                     __syncwarp();
@@ -349,7 +357,7 @@ struct JumperT {
         for (int k = lane; k < nsp; k += WARP_LANES) s.sprite_order[k * N + env] = (uint8_t)(order[k] == 0 ? 0 : order[k] - 1);
 
         uint8_t* gt = s.tiles + (size_t)env * TILE_STRIDE;
-        for (int i = lane; i < W * H / 4; i += WARP_LANES) ((uint32_t*)gt)[i] = ((const uint32_t*)tiles)[i];
+        for (int i = lane; i < (W * H + 3) / 4; i += WARP_LANES) ((uint32_t*)gt)[i] = ((const uint32_t*)tiles)[i];   // (the scratch map is padded to a word)
         for (int k = lane; k < nspikes; k += WARP_LANES) s.spike_cell[k * N + env] = spikes[k];
         for (int k = lane; k < NPART; k += WARP_LANES) { s.p_x[k * N + env] = 0.0f; s.p_y[k * N + env] = 0.0f; s.p_life[k * N + env] = 0.0f; }
         if (lane == 0) {

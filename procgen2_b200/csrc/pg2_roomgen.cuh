@@ -15,8 +15,8 @@
 
 namespace pg2 {
 
-constexpr int ROOM_DIM = 40, ROOM_CELLS = ROOM_DIM * ROOM_DIM;
-constexpr int ROOM_MAX_BUCKETS = 2400;   // bucket count of a fresh unordered_set<int> holding <= 1600 keys: <= 2357
+constexpr int ROOM_MAX_DIM = 45;         // world_dim: 20 easy, 40 hard, 45 memory (bit rows: <= 64)
+constexpr int ROOM_MAX_BUCKETS = 2400;   // bucket count of a fresh unordered_set<int> holding <= 2025 keys: <= 2357; also >= 45 * 45 cell claims
 
 // Atomically claim a byte flag (0 -> 1); true for the one thread that claimed it.
 PG2_DEV bool claim_cell(uint8_t* p) {
@@ -149,38 +149,48 @@ struct RoomGen {
 
     PG2_DEV_NOINLINE void init(WarpCtx& w, int width, int height) {
         W = width; H = height;
-        grid = w.alloc<uint8_t>(ROOM_CELLS);
-        tmp = w.alloc<uint8_t>(ROOM_CELLS);
-        mark = w.alloc<uint8_t>(ROOM_CELLS);
-        queue = w.alloc<uint16_t>(ROOM_CELLS + 64);
-        parents = w.alloc<uint16_t>(ROOM_CELLS + 64);
-        order = w.alloc<uint16_t>(ROOM_CELLS + 64);
-        path = w.alloc<uint16_t>(ROOM_CELLS + 64);
-        seq = w.alloc<uint16_t>(ROOM_CELLS + 64);
+        const int cells = (W * H + 3) & ~3;          // scratch sized by THIS world (20 x 20 ... 45 x 45)
+        grid = w.alloc<uint8_t>(cells);
+        tmp = w.alloc<uint8_t>(cells);
+        mark = w.alloc<uint8_t>(cells);
+        queue = w.alloc<uint16_t>(cells + 64);
+        parents = w.alloc<uint16_t>(cells + 64);
+        order = w.alloc<uint16_t>(cells + 64);
+        path = w.alloc<uint16_t>(cells + 64);
+        seq = w.alloc<uint16_t>(cells + 64);
         res = w.alloc<int>(4);
-        claim = w.alloc<int>(ROOM_MAX_BUCKETS);     // ROOM_CELLS claims during a BFS, bucket table afterwards
+        claim = w.alloc<int>(ROOM_MAX_BUCKETS);     // W * H claims during a BFS, bucket table afterwards
         scratch = w.alloc<int>(ROOM_MAX_BUCKETS);
-        rows_a = w.alloc<uint64_t>(ROOM_DIM); rows_b = w.alloc<uint64_t>(ROOM_DIM); rows_c = w.alloc<uint64_t>(ROOM_DIM);
+        rows_a = w.alloc<uint64_t>(W); rows_b = w.alloc<uint64_t>(W); rows_c = w.alloc<uint64_t>(W);
     }
 
     PG2_DEV int get(int x, int y) const { return (x < 0 || y < 0 || x >= W || y >= H) ? 1 : grid[y + H * x]; }
 
-    // ---- bit rows: rows[x] bit y = bytes[y + H * x] (0 / 1 bytes; H a multiple of 4, <= 64: four cells per 32-bit word)
+    // ---- bit rows: rows[x] bit y = bytes[y + H * x] (0 / 1 bytes; H <= 64). H a multiple of 4 (20, 40): four cells per
+    // 32-bit word; otherwise (45) byte by byte.
     PG2_DEV void bytes_to_rows(WarpCtx& w, const uint8_t* bytes, uint64_t* rows) {
         for (int x = w.lane; x < W; x += WARP_LANES) {
-            const uint32_t* p = (const uint32_t*)(bytes + H * x);
             uint64_t m = 0;
-            for (int k = 0; k < H / 4; k++)   // bytes b0..b3 of a word -> bits 21..24 of word * 0x204081
-                m |= (uint64_t)(((p[k] & 0x01010101u) * 0x00204081u >> 21) & 15u) << (4 * k);
+            if (H % 4 == 0) {
+                const uint32_t* p = (const uint32_t*)(bytes + H * x);
+                for (int k = 0; k < H / 4; k++)   // bytes b0..b3 of a word -> bits 21..24 of word * 0x204081
+                    m |= (uint64_t)(((p[k] & 0x01010101u) * 0x00204081u >> 21) & 15u) << (4 * k);
+            } else {
+                for (int y = 0; y < H; y++) m |= (uint64_t)(bytes[y + H * x] & 1u) << y;
+            }
             rows[x] = m;
         }
         __syncwarp();
     }
     PG2_DEV void rows_to_bytes(WarpCtx& w, const uint64_t* rows, uint8_t* bytes) {
         for (int x = w.lane; x < W; x += WARP_LANES) {
-            uint32_t* p = (uint32_t*)(bytes + H * x);
             const uint64_t m = rows[x];
-            for (int k = 0; k < H / 4; k++) p[k] = ((uint32_t)(m >> (4 * k)) & 15u) * 0x00204081u & 0x01010101u;
+            if (H % 4 == 0) {
+                uint32_t* p = (uint32_t*)(bytes + H * x);
+                for (int k = 0; k < H / 4; k++) p[k] = ((uint32_t)(m >> (4 * k)) & 15u) * 0x00204081u & 0x01010101u;
+            } else {
+                for (int y = 0; y < H; y++) bytes[y + H * x] = (uint8_t)(m >> y & 1ull);
+            }
         }
         __syncwarp();
     }

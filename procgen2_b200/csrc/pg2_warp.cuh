@@ -15,7 +15,7 @@
 namespace pg2 {
 
 constexpr int RESET_WARPS_PER_CTA = 2;
-constexpr int RESET_ARENA_BYTES = 52 * 1024;   // largest per-warp scratch of any game (G::RESET_ARENA is what a game gets)
+constexpr int RESET_ARENA_BYTES = 64 * 1024;   // largest per-warp scratch of any game (G::RESET_ARENA is what a game gets)
 
 struct WarpCtx {
     WarpMt rng;

@@ -168,7 +168,7 @@ def test_distribution_mode_option(game, oracle_available):
     not built is refused loudly."""
     from procgen2_b200.engine import BatchedEnv
     with pytest.raises(RuntimeError, match="distribution_mode"):
-        BatchedEnv("jumper", 4, distribution_mode=2)      # jumper memory: not built
+        BatchedEnv("climber", 4, distribution_mode=2)     # climber has no third mode
     if not oracle_available:
         pytest.skip("oracle/_ref did not travel")
     from oracle import ref_env
@@ -197,10 +197,11 @@ def test_distribution_mode_option(game, oracle_available):
 
 @pytest.mark.parametrize("game,mode,dim,max_ep,T", [("maze", 0, 15, 40, 150), ("maze", 2, 31, 40, 150),
                                                     ("chaser", 1, 13, 120, 300), ("chaser", 2, 19, 120, 300),
-                                                    ("jumper", 0, 20, 100, 250), ("caveflyer", 0, 20, 100, 250)])
+                                                    ("jumper", 0, 20, 100, 250), ("caveflyer", 0, 20, 100, 250),
+                                                    ("jumper", 2, 45, 100, 250), ("caveflyer", 2, 45, 100, 250)])
 def test_world_size_modes(game, mode, dim, max_ep, T, oracle_available):
     """Distribution modes with their own world size = own instantiations (maze easy 15x15 / memory 31x31 with an agent-centred
-    8x8 view: MazeT<MODE>; chaser hard 13x13 / extreme 19x19 with 5 enemies and 5 orbs: ChaserT<MODE>; jumper / caveflyer easy 20x20), against the reference
+    8x8 view: MazeT<MODE>; chaser hard 13x13 / extreme 19x19 with 5 enemies and 5 orbs: ChaserT<MODE>; jumper / caveflyer easy 20x20 and memory 45x45 with the unpruned cave), against the reference
     with its compile-time Config::mode set: tile maps + RNG after make, pixels / rewards / dones over truncated episodes."""
     if not oracle_available:
         pytest.skip("oracle/_ref did not travel")

@@ -200,7 +200,7 @@ def test_easy_distribution_mode_live_oracle(game, oracle_available):
         assert any(not np.array_equal(easy.step(acts[t])[0], hard.step(acts[t])[0]) for t in range(200))
 
 
-@pytest.mark.parametrize("game,mode", [("maze", 0), ("maze", 2), ("chaser", 1), ("chaser", 2), ("jumper", 0), ("caveflyer", 0)])
+@pytest.mark.parametrize("game,mode", [("maze", 0), ("maze", 2), ("chaser", 1), ("chaser", 2), ("jumper", 0), ("caveflyer", 0), ("jumper", 2), ("caveflyer", 2)])
 def test_world_size_modes_live_oracle(game, mode, oracle_available):
     """Distribution modes that change the world size (own instantiations, G = <Game>T<MODE>) against the reference with its
     compile-time Config::mode set through the probe: levels (tile map + RNG state), pixels, rewards, dones, truncation."""
