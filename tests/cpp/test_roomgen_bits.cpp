@@ -12,8 +12,9 @@ int main() {
     std::mt19937 rng(7);
     std::vector<char> arena(RESET_ARENA_BYTES);
     static uint32_t mt[MT_N];
-    const int W = ROOM_DIM, H = ROOM_DIM;
-    for (int trial = 0; trial < 300; trial++) {
+    const int dims[3] = { 40, 20, 45 };   // hard, easy, memory (45: rows that are not a multiple of 4 cells)
+    for (int trial = 0; trial < 450; trial++) {
+        const int W = dims[trial % 3], H = W;
         WarpCtx w;
         w.rng.mt = mt; w.rng.idx = 0; w.rng.lane = 0;
         w.lane = 0; w.arena = arena.data(); w.arena_off = 0; w.arena_cap = RESET_ARENA_BYTES;

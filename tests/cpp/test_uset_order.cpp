@@ -11,13 +11,15 @@
 
 using namespace pg2;
 
+constexpr int ROOM_CELLS = ROOM_MAX_DIM * ROOM_MAX_DIM;   // 45 x 45: the largest cave (jumper / caveflyer memory mode)
+
 int main() {
     std::mt19937 rng(2024);
     std::vector<char> arena(RESET_ARENA_BYTES);
     static uint32_t mt[MT_N];
     int checks = 0;
     for (int trial = 0; trial < 700; trial++) {
-        int n = trial < 120 ? trial : (int)(rng() % 1601);   // every small size (incl. 0, the rehash edges 13/14, 29/30 ...) + random
+        int n = trial < 120 ? trial : (int)(rng() % (ROOM_CELLS + 1));   // every small size (incl. 0, the rehash edges 13/14, 29/30 ...) + random
         std::vector<int> all(ROOM_CELLS);
         for (int i = 0; i < ROOM_CELLS; i++) all[i] = i;
         std::shuffle(all.begin(), all.end(), rng);
