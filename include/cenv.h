@@ -17,7 +17,8 @@
  *                 "max_episode_steps" (INT, default 0 = never truncate),
  *                 "auto_reset" (INT, default 1 when num_envs > 1, else 0),
  *                 "distribution_mode" (INT, default -1 = the mode the reference compiles in; 0 easy, 1 hard, 2 memory /
- *                 extreme — games/<g>/tilemap.h Config; built: the defaults, + easy for coinrun and climber),
+ *                 extreme — games/<g>/tilemap.h Config, bossfight common_systems.h:44-65; every mode a game has is built,
+ *                 one it does not have makes cenv_make fail),
  *                 "host_copy" (INT, default 1; 0: observations stay device-resident — cenv_step / cenv_reset return
  *                 when the kernels have finished, without the device -> host copy of "screen"; rewards and flags are
  *                 still copied)

@@ -47,8 +47,8 @@ typedef struct {
                                     reset frame); 0: reference behaviour, the caller calls pg2_reset */
     int32_t distribution_mode;   /* level-generator mode of the game's tilemap Config (games/<g>/tilemap.h: compile-time in
                                     the reference): -1 = the reference's default, 0 easy, 1 hard, 2 memory / extreme.
-                                    Built: every game's default, + easy for coinrun (a no-op there, tilemap.cpp:148) and
-                                    climber (tilemap.cpp:118); anything else makes pg2_create fail */
+                                    Every mode of a game's enum is built (maze / chaser / jumper / caveflyer 0-2, coinrun /
+                                    climber / bossfight 0-1); a mode the game does not have makes pg2_create fail */
 } pg2_config;
 
 PG2_API int32_t pg2_create(const pg2_config* cfg, pg2_engine** out);
