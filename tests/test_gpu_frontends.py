@@ -132,18 +132,20 @@ def test_vector_env_matches_oracle(game, oracle_available):
     env.close()
 
 
-@pytest.mark.parametrize("game", ["coinrun", "bossfight", "jumper", "maze"])
-def test_cenv_render_matches_oracle(game, oracle_available):
+@pytest.mark.parametrize("game,mode", [("coinrun", None), ("bossfight", None), ("jumper", None), ("maze", None),
+                                       ("chaser", 2), ("caveflyer", 2)])
+def test_cenv_render_matches_oracle(game, mode, oracle_available):
     """cenv_render of the drop-in library = the reference's human-mode frame (512x512 default window and a custom size),
-    rendered on the device."""
+    rendered on the device; with the make-option "distribution_mode" passed through the cenv options for two of the
+    instantiations that have their own world size."""
     if not oracle_available:
         pytest.skip("oracle/_ref did not travel")
     from oracle import ref_env
     from procgen2_b200.build import game_lib_path
     from procgen2_b200.cenv import CEnv
     for opts in ({}, {"width": 200, "height": 200}):
-        env = CEnv(game_lib_path(game), options=dict(seed=515, **opts))
-        ref = ref_env.RefEnv(game, 515, **opts)
+        env = CEnv(game_lib_path(game), options=dict(seed=515, **opts, **({} if mode is None else {"distribution_mode": mode})))
+        ref = ref_env.RefEnv(game, 515, mode=mode, **opts)
         obs, _ = env.reset()
         np.testing.assert_array_equal(obs["screen"].reshape(64, 64, 3), ref.reset())
         rs = np.random.RandomState(1)

@@ -160,6 +160,30 @@ def test_human_render_live_oracle(game, oracle_available):
             r.close()
 
 
+@pytest.mark.parametrize("game,mode", [("maze", 2), ("chaser", 2), ("jumper", 2), ("caveflyer", 0)])
+def test_human_render_in_other_modes_live_oracle(game, mode, oracle_available):
+    """cenv_render of the instantiations with their own world size (zoom, sprite count and tile window differ)."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_env
+    n, seed, W, H = 2, 91, 128, 128
+    sim = SimAdapter(game, n, seed, distribution_mode=mode)
+    refs = [ref_env.RefEnv(game, seed + i, width=W, height=H, mode=mode) for i in range(n)]
+    np.testing.assert_array_equal(sim.reset(), np.stack([r.reset() for r in refs]))
+    rs = np.random.RandomState(4)
+    for t in range(60):
+        a = rs.randint(0, 15, size=n).astype(np.int32)
+        o, _, _ = sim.step(a)
+        for i, r in enumerate(refs):
+            oo, w, d = r.step(a[i])
+            np.testing.assert_array_equal(o[i], r.reset() if d else oo)
+        if t % 20 == 19:
+            for i, r in enumerate(refs):
+                np.testing.assert_array_equal(sim.sim.render_human(i, W, H), r.render(), err_msg="%s mode %d step %d env %d" % (game, mode, t, i))
+    for r in refs:
+        r.close()
+
+
 @pytest.mark.parametrize("game", ["climber", "coinrun", "bossfight"])
 def test_easy_distribution_mode_live_oracle(game, oracle_available):
     """Make-option distribution_mode = 0 (easy) against the reference with its compile-time Config::easy_mode flipped
