@@ -62,7 +62,7 @@ struct CaveFlyerT {
     static constexpr int TILE_CLASSES = 1;
     static constexpr int WIN_ROWS = 11;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
     static constexpr int BLIT_UNROLL = 1;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
-    static constexpr int RENDER_MIN_CTAS = 8;   // CTAs per SM the register allocation of k_render aims at
+    static constexpr int RENDER_MIN_CTAS = 7;   // CTAs per SM the register allocation of k_render aims at
     static constexpr int DEFAULT_MODE = MODE;    // this instantiation's distribution mode (the reference compiles in 1 = hard; tilemap.h Config)
     static bool mode_supported(int mode) { return mode == MODE; }
     static constexpr bool HAS_TILES = true;     // the frame has a tile layer
