@@ -27,4 +27,5 @@
     X("jumper", 0, pg2::JumperT<0>)   \
     X("jumper", 2, pg2::JumperT<2>)   \
     X("caveflyer", 0, pg2::CaveFlyerT<0>) \
-    X("caveflyer", 2, pg2::CaveFlyerT<2>)
+    X("caveflyer", 2, pg2::CaveFlyerT<2>) \
+    X("bossfight", 0, pg2::BossFightT<0>)

@@ -4,7 +4,7 @@
 //   level gen   reset() bossfight.cpp:426-504; System_Agent::reset :723-737; System_Mob_AI::reset :452-469
 //   frame       render_game bossfight.cpp:401-424; System_Mob_AI::render :392-450; System_Agent::render :685-721;
 //               System_Sprite_Render::render :25-49
-// hard_mode (compile-time default, common_systems.h:61); easy_mode is the run-time c.mode == 0. World = the 64x64 px observation at
+// hard_mode (compile-time default, common_systems.h:61); easy_mode is the BossFightT<0> instantiation. World = the 64x64 px observation at
 // camera scale 1 => screen rectangle {-2,-2,4,4} units (obs-only rendering).
 // Entity ids per episode: 0 player, 1 boss, 2.. accepted barriers.
 #pragma once
@@ -43,7 +43,8 @@ namespace pg2 {
 
 PG2_DEFINE_STATE(BossFightState, PG2_BOSSFIGHT_FIELDS)
 
-struct BossFight {
+template <int MODE>
+struct BossFightT {
     using State = BossFightState;
     static constexpr int SUB_STEPS = 4;
     static constexpr bool LANE_AWARE = true;    // step(): the bullet rings are walked lane-parallel, the rest is uniform (leader stores)
@@ -59,8 +60,12 @@ struct BossFight {
     static constexpr int WIN_ROWS = 1;        // most tile rows the camera window can span (zoom-dependent; frame table sizing)
     static constexpr int BLIT_UNROLL = 2;     // post-blit patches fetched together (pg2_render.cuh draw_blit_band)
     static constexpr int RENDER_MIN_CTAS = 10;   // CTAs per SM the register allocation of k_render aims at (small frame tables: 10 frames per SM measured +5 % over 8)
-    static constexpr int DEFAULT_MODE = 1;    // distribution mode the reference compiles in (tilemap.h Config): 0 easy, 1 hard, 2 memory / extreme
-    static bool mode_supported(int mode) { return mode == 0 || mode == 1; }   // easy: slower boss bullets, shorter shielded phases (run-time, c.mode)
+    static constexpr int DEFAULT_MODE = MODE;    // this instantiation's distribution mode (the reference compiles in 1 = hard; common_systems.h:61-65)
+    static bool mode_supported(int mode) { return mode == MODE; }
+    // System_Mob_AI::Config::mode: easy = boss bullets at half speed, shorter shielded phases. Compile-time: as run-time
+    // selects the two constants cost k_step 38 registers (118 -> 156) and with them a quarter of its occupancy.
+    static constexpr float BULLET_SPEED = MODE == 0 ? 0.05f : 0.1f;     // common_systems.cpp:104
+    static constexpr float SHIELD_JITTER = MODE == 0 ? 30.0f : 80.0f;   // common_systems.cpp:202
     static constexpr bool HAS_TILES = false;     // the frame has a tile layer
     static constexpr bool STATIC_VIEW = true;    // fixed camera, no tile layer: the background image is cached per env
     static constexpr int MB = 64, NEX = 8, AB = 32, MAX_BAR = 4;
@@ -152,7 +157,6 @@ struct BossFight {
         const int N = s.N;
         const float dt = 1.0f / SUB_STEPS;
         const double PI = 3.14159265358979323846;
-        const bool easy = c.mode == 0;   // System_Mob_AI::Config::mode (common_systems.h:61-65); -1 / 1 = hard_mode, the reference's default
         Mt rng; rng.mt = c.mt + (size_t)env * MT_N; rng.idx = c.mti[env];
         rng.collective = ctx.nlanes != 1; rng.writer = ctx.leader(); rng.sync_mask = ctx.mask;
         const Rect screen{ -2.0f, -2.0f, 4.0f, 4.0f };
@@ -320,14 +324,14 @@ struct BossFight {
             // ================= System_Mob_AI::update =================
             {
                 boss_alive = true;
-                const float shielded_phase_time = __fadd_rn(180.0f, __fmul_rn(rng.canonical(), easy ? 30.0f : 80.0f));   // common_systems.cpp:202
+                const float shielded_phase_time = __fadd_rn(180.0f, __fmul_rn(rng.canonical(), SHIELD_JITTER));
                 const Rect agent_rect{ __fadd_rn(px, -0.15f), __fadd_rn(py, -0.1f), 0.3f, 0.2f };
                 if (phase_timer == 0.0f) {
                     weapon_index = rng.uniform_int(0, 3);
                     attack_timer = 0.0f;
                     hp = 3;
                 }
-                const float bullet_speed = easy ? 0.05f : 0.1f;   // common_systems.cpp:104
+                const float bullet_speed = BULLET_SPEED;
                 auto fire_pattern = [&](int pattern) {
                     switch (pattern) {
                     case -1:
@@ -651,5 +655,6 @@ struct BossFight {
         });
     }
 };
+using BossFight = BossFightT<1>;
 
 }  // namespace pg2
