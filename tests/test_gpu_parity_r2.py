@@ -182,14 +182,18 @@ def test_maze_timeout_live_oracle(oracle_available):
 
 # ---- (d) level generation, many seeds ---------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("game", IMPLEMENTED)
-def test_gpu_level_generation_many_seeds(game, oracle_available):
+OTHER_MODES = [("maze", 0), ("maze", 2), ("chaser", 1), ("chaser", 2), ("jumper", 0), ("jumper", 2), ("caveflyer", 0), ("caveflyer", 2)]
+
+
+@pytest.mark.parametrize("game,mode", [(g, None) for g in IMPLEMENTED] + OTHER_MODES)
+def test_gpu_level_generation_many_seeds(game, mode, oracle_available):
     """The warp-parallel generators (ordered BFS with atomicMin claims, unordered_set regrouping, bit-row automaton) exist
-    only in the GPU build: 512 seeds x (make + 4 resets), tile map + complete RNG state + the reset frame every time."""
+    only in the GPU build: 512 seeds x (make + 4 resets), tile map + complete RNG state + the reset frame every time
+    (128 seeds for the distribution modes that have their own world size)."""
     ref_env = _need_oracle(oracle_available)
     from procgen2_b200.engine import BatchedEnv
-    n, seed, chunk = 512, 52000, 128
-    env = BatchedEnv(game, n, seed=seed)
+    n, seed, chunk = (512 if mode is None else 128), 52000, 128
+    env = BatchedEnv(game, n, seed=seed, distribution_mode=-1 if mode is None else mode)
     frames = []
     fields = []
     for rnd in range(5):
@@ -207,7 +211,7 @@ def test_gpu_level_generation_many_seeds(game, oracle_available):
     _assert_no_fault(env)
     env.close()
     for c0 in range(0, n, chunk):
-        refs = [ref_env.RefEnv(game, seed + i) for i in range(c0, min(n, c0 + chunk))]
+        refs = [ref_env.RefEnv(game, seed + i, mode=mode) for i in range(c0, min(n, c0 + chunk))]
         for rnd in range(5):
             mt, mti, tiles = fields[rnd]
             for k, r in enumerate(refs):

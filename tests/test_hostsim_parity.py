@@ -49,15 +49,19 @@ def test_live_oracle(game, oracle_available):
     check_against_oracle(SimAdapter(game, n, seed), refs, acts, tag=game)
 
 
-@pytest.mark.parametrize("game", IMPLEMENTED)
-def test_level_generation_many_seeds(game, oracle_available):
-    """Level layouts + the complete MT19937 state for many seeds and consecutive resets."""
+OTHER_MODES = [("maze", 0), ("maze", 2), ("chaser", 1), ("chaser", 2), ("jumper", 0), ("jumper", 2), ("caveflyer", 0), ("caveflyer", 2)]
+
+
+@pytest.mark.parametrize("game,mode", [(g, None) for g in IMPLEMENTED] + OTHER_MODES)
+def test_level_generation_many_seeds(game, mode, oracle_available):
+    """Level layouts + the complete MT19937 state for many seeds and consecutive resets — the compiled-in mode of every game
+    and every distribution mode that has its own world size."""
     if not oracle_available:
         pytest.skip("oracle/_ref not built")
     from oracle import ref_env
     n, seed = 24, 31337
-    sim = SimAdapter(game, n, seed)
-    refs = [ref_env.RefEnv(game, seed + i) for i in range(n)]
+    sim = SimAdapter(game, n, seed, distribution_mode=-1 if mode is None else mode)
+    refs = [ref_env.RefEnv(game, seed + i, mode=mode) for i in range(n)]
     for rnd in range(4):
         f = sim.fields()
         for i, r in enumerate(refs):
