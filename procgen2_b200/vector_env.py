@@ -61,10 +61,18 @@ class ProcgenVectorEnv(_VectorEnvBase):
     """`num_envs` environments of `game` on CUDA device `device`, Gymnasium-VectorEnv style, tensors in HBM."""
     metadata = {"render_modes": ["rgb_array"], "autoreset_mode": "SameStep"}
 
-    def __init__(self, game, num_envs, seed=0, device=0, max_episode_steps=0, first_env=0, copy=False):
+    DISTRIBUTION_MODES = {None: -1, "default": -1, "easy": 0, "hard": 1, "memory": 2, "extreme": 2}
+
+    def __init__(self, game, num_envs, seed=0, device=0, max_episode_steps=0, first_env=0, copy=False, distribution_mode=None):
+        """distribution_mode: None (the mode the reference compiles in), "easy" / "hard" / "memory" / "extreme" or the integer
+        of the reference's `Distribution_Mode` enum (games/<g>/tilemap.h); a mode the game does not have raises."""
         import torch
         self._torch = torch
-        self.env = BatchedEnv(game, num_envs, seed=seed, device=device, first_env=first_env, max_episode_steps=max_episode_steps)
+        mode = self.DISTRIBUTION_MODES.get(distribution_mode, distribution_mode) if not isinstance(distribution_mode, int) else distribution_mode
+        if not isinstance(mode, int):
+            raise ValueError("distribution_mode %r: expected one of %s or an integer" % (distribution_mode, sorted(k for k in self.DISTRIBUTION_MODES if k)))
+        self.env = BatchedEnv(game, num_envs, seed=seed, device=device, first_env=first_env, max_episode_steps=max_episode_steps,
+                              distribution_mode=mode)
         self.game, self.num_envs, self.copy = game, int(num_envs), bool(copy)
         self.device = torch.device("cuda", device)
         self.stream = torch.cuda.ExternalStream(self.env.stream_ptr, device=self.device)

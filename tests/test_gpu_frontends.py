@@ -82,15 +82,18 @@ def test_cenv_single_env_reports_no_infos():
     e.close()
 
 
-@pytest.mark.parametrize("game", ["coinrun", "chaser"])
-def test_vector_env_matches_oracle(game, oracle_available):
-    """ProcgenVectorEnv: zero-copy tensors, actions as CUDA tensor / numpy / list, same-step autoreset, seeds."""
+@pytest.mark.parametrize("game,mode", [("coinrun", None), ("chaser", None), ("chaser", "extreme"), ("maze", "easy")])
+def test_vector_env_matches_oracle(game, mode, oracle_available):
+    """ProcgenVectorEnv: zero-copy tensors, actions as CUDA tensor / numpy / list, same-step autoreset, seeds, and the
+    `distribution_mode` keyword by name."""
     import torch
     from procgen2_b200.vector_env import ProcgenVectorEnv
     n, T, seed = 16, 60, 4400
     rs = np.random.RandomState(6)
     acts = rs.randint(0, 15, size=(T, n)).astype(np.int32)
-    env = ProcgenVectorEnv(game, n, seed=seed, max_episode_steps=25)
+    env = ProcgenVectorEnv(game, n, seed=seed, max_episode_steps=25, distribution_mode=mode)
+    with pytest.raises(ValueError):
+        ProcgenVectorEnv(game, n, distribution_mode="nightmare")
     assert env.single_observation_space.shape == (64, 64, 3) and env.observation_space.shape == (n, 64, 64, 3)
     assert env.single_action_space.n == 15
     obs, info = env.reset()
@@ -99,7 +102,7 @@ def test_vector_env_matches_oracle(game, oracle_available):
     refs = None
     if oracle_available:
         from oracle import ref_env
-        refs = [ref_env.RefEnv(game, seed + i) for i in range(n)]
+        refs = [ref_env.RefEnv(game, seed + i, mode=ProcgenVectorEnv.DISTRIBUTION_MODES[mode] if mode else None) for i in range(n)]
         np.testing.assert_array_equal(obs.cpu().numpy(), np.stack([r.reset() for r in refs]))
     age = np.zeros(n, np.int64)
     for t in range(T):
