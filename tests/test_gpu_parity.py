@@ -204,7 +204,7 @@ def test_pipelined_stepping_equals_sequential():
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("game", ["coinrun", "bossfight", "jumper"])
+@pytest.mark.parametrize("game", IMPLEMENTED)
 def test_snapshot_restore_replays_bit_exact(game):
     """pg2_snapshot / pg2_restore: stepping after a restore reproduces the steps that followed
     the snapshot bit for bit (observations, rewards, done flags, MT19937 streams) — also into a fresh engine, and
