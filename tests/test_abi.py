@@ -56,3 +56,12 @@ def test_create_fails_loudly_without_gpu(built):
     from procgen2_b200.engine import BatchedEnv
     with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
         BatchedEnv("maze", 4)
+
+
+def test_vector_env_distribution_mode_names():
+    """The tensor front-end takes the reference's mode names; a name that is no mode fails before anything touches the GPU."""
+    from procgen2_b200.vector_env import ProcgenVectorEnv as V
+    assert (V.DISTRIBUTION_MODES[None], V.DISTRIBUTION_MODES["easy"], V.DISTRIBUTION_MODES["hard"]) == (-1, 0, 1)
+    assert V.DISTRIBUTION_MODES["memory"] == V.DISTRIBUTION_MODES["extreme"] == 2      # games/<g>/tilemap.h Distribution_Mode
+    with pytest.raises(ValueError, match="distribution_mode"):
+        V("maze", 4, distribution_mode="nightmare")
