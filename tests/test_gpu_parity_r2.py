@@ -285,3 +285,41 @@ def test_prefetch_when_every_env_finishes_every_step(game, n, max_ep, monkeypatc
         env.close()
     for a, b in zip(*outs):
         np.testing.assert_array_equal(a, b)
+
+
+# ---- bossfight past its first seconds -----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("mode", [None, 0])
+def test_bossfight_whole_fight_live_oracle(mode, oracle_available):
+    """The lane-aware k_step<bossfight> (bullet rings as visited prefixes, ballots over 8-lane groups) through whole fights:
+    a policy that dodges and fires (random actions die within ~50 steps) walks the boss through its shielded / unshielded
+    phases, every attack pattern, the shield bounces, hp and its death — pixels, rewards, dones every step, RNG at the end."""
+    ref_env = _need_oracle(oracle_available)
+    from procgen2_b200.engine import BatchedEnv
+    from tests.test_hostsim_parity import bossfight_policy
+    n, seed, T = 16, 777, 1500
+    rs = np.random.RandomState(seed)
+    env = BatchedEnv("bossfight", n, seed=seed, distribution_mode=-1 if mode is None else mode)
+    refs = [ref_env.RefEnv("bossfight", seed + i, mode=mode) for i in range(n)]
+    env.reset()
+    np.testing.assert_array_equal(env.fetch()[0], np.stack([r.reset() for r in refs]))
+    wins, longest, age = 0, 0, np.zeros(n, np.int64)
+    for t in range(T):
+        a = bossfight_policy(env.read_field, n, rs)
+        env.step(a)
+        o, rw, d, _ = env.fetch()
+        for i, r in enumerate(refs):
+            oo, w, dd = r.step(a[i])
+            age[i] += 1
+            if dd:
+                oo = r.reset()
+                wins += w > 0
+                longest, age[i] = max(longest, age[i]), 0
+            assert w == rw[i] and dd == d[i], (t, i)
+            np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))
+    _check_state(env, refs, tag="bossfight whole fight")
+    _assert_no_fault(env)
+    assert wins >= 1 and longest >= 400, (wins, longest)
+    for r in refs:
+        r.close()
+    env.close()

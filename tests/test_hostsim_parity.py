@@ -262,3 +262,65 @@ def test_world_size_modes_live_oracle(game, mode, oracle_available):
         assert pos == f["mti"][i]
         np.testing.assert_array_equal(st, f["mt"][i])
         r.close()
+
+
+def bossfight_policy(read_field, n, rs):
+    """Dodge the nearest boss bullet, otherwise line up under the boss and fire (action 9): random actions die within ~50
+    steps, this survives long enough to walk the boss through all of its phases and to win. read_field(name) -> (bytes,
+    element size, elements per env) of a state field (slot-major)."""
+    def fld(name):
+        buf, esz, pe = read_field(name)
+        return buf.view(np.float32).reshape(pe, n) if pe > 1 else buf.view(np.float32)
+    px, py, bx = fld("px"), fld("py"), fld("bx")
+    mx, my, mf = fld("mb_x"), fld("mb_y"), fld("mb_frame")
+    acts = np.zeros(n, np.int32)
+    for i in range(n):
+        live = mf[:, i] == 0.0
+        dx, dy = mx[live, i] - px[i], my[live, i] - py[i]
+        d2 = dx * dx + dy * dy
+        if d2.size and d2.min() < 0.5:
+            k = int(np.argmin(d2))
+            mxv, myv = (-1 if dx[k] > 0 else 1), (1 if dy[k] > 0 else -1)
+            if rs.rand() < 0.3:
+                myv = 0
+            acts[i] = (mxv + 1) * 3 + (myv + 1)
+        elif abs(px[i] - bx[i]) > 0.25 and rs.rand() < 0.8:
+            acts[i] = 7 if bx[i] > px[i] else 1
+        else:
+            acts[i] = 9 if rs.rand() < 0.8 else rs.randint(0, 15)
+    return acts
+
+
+@pytest.mark.parametrize("mode", [None, 0])
+def test_bossfight_whole_fight_live_oracle(mode, oracle_available):
+    """bossfight beyond the first seconds (System_Mob_AI::update common_systems.cpp:199-390: shielded / unshielded phases,
+    every attack pattern, hp, the boss's death and the win reward) with a policy that survives: pixels, rewards, dones every
+    step, RNG state at the end, hard and easy mode."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_env
+    n, seed, T = 8, 777, 1500
+    rs = np.random.RandomState(seed)
+    sim = SimAdapter("bossfight", n, seed, distribution_mode=-1 if mode is None else mode)
+    refs = [ref_env.RefEnv("bossfight", seed + i, mode=mode) for i in range(n)]
+    np.testing.assert_array_equal(sim.reset(), np.stack([r.reset() for r in refs]))
+    wins, longest, age = 0, 0, np.zeros(n, np.int64)
+    for t in range(T):
+        a = bossfight_policy(sim.sim.field, n, rs)
+        o, rw, d = sim.step(a)
+        for i, r in enumerate(refs):
+            oo, w, dd = r.step(a[i])
+            age[i] += 1
+            if dd:
+                oo = r.reset()
+                wins += w > 0
+                longest, age[i] = max(longest, age[i]), 0
+            assert w == rw[i] and dd == d[i], (t, i)
+            np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))
+    f = sim.fields()
+    for i, r in enumerate(refs):
+        st, pos = r.rng_state()
+        assert pos == f["mti"][i]
+        np.testing.assert_array_equal(st, f["mt"][i])
+        r.close()
+    assert wins >= 1 and longest >= 400, (wins, longest)
