@@ -323,3 +323,42 @@ def test_bossfight_whole_fight_live_oracle(mode, oracle_available):
     for r in refs:
         r.close()
     env.close()
+
+
+# ---- chaser with orbs and eaten mobs --------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("mode", [None, 2])
+def test_chaser_orbs_and_eaten_mobs_live_oracle(mode, oracle_available):
+    """The warp-per-env k_step<chaser> (point loop on the lanes, votes for "ate an orb") with a corridor-walking policy: the
+    agent covers the maze, eats orbs (mobs flee and slow down) and now and then a mob (respawn on a free cell drawn from the
+    RNG) — paths uniform-random actions hardly reach. Easy 11x11 and extreme 19x19."""
+    ref_env = _need_oracle(oracle_available)
+    from procgen2_b200.engine import BatchedEnv
+    n, seed, T = 16, 555, 1500
+    rs = np.random.RandomState(seed)
+    env = BatchedEnv("chaser", n, seed=seed, distribution_mode=-1 if mode is None else mode)
+    refs = [ref_env.RefEnv("chaser", seed + i, mode=mode) for i in range(n)]
+    env.reset()
+    np.testing.assert_array_equal(env.fetch()[0], np.stack([r.reset() for r in refs]))
+    cur = rs.choice([1, 7, 3, 5], size=n)
+    orbs, prev_eat = 0, np.zeros(n, np.float32)
+    for t in range(T):
+        cur = np.where(rs.rand(n) < 0.08, rs.choice([1, 7, 3, 5], size=n), cur)
+        a = cur.astype(np.int32)
+        env.step(a)
+        o, rw, d, _ = env.fetch()
+        eat = env.read_field("eat_timer")[0].view(np.float32).copy()
+        orbs += int(((eat > prev_eat) & ~d.astype(bool)).sum())
+        prev_eat = eat
+        for i, r in enumerate(refs):
+            oo, w, dd = r.step(a[i])
+            if dd:
+                oo = r.reset()
+            assert w == rw[i] and dd == d[i], (t, i)
+            np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))
+    _check_state(env, refs, tag="chaser orbs")
+    _assert_no_fault(env)
+    assert orbs >= 5, orbs
+    for r in refs:
+        r.close()
+    env.close()

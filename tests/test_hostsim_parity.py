@@ -324,3 +324,40 @@ def test_bossfight_whole_fight_live_oracle(mode, oracle_available):
         np.testing.assert_array_equal(st, f["mt"][i])
         r.close()
     assert wins >= 1 and longest >= 400, (wins, longest)
+
+
+@pytest.mark.parametrize("mode", [None, 2])
+def test_chaser_orbs_and_eaten_mobs_live_oracle(mode, oracle_available):
+    """chaser with a corridor-walking policy (hold a direction, turn now and then): the agent covers the maze, eats orbs
+    (System_Mob_AI::eat, mobs flee and slow down, common_systems.cpp:117-297) and, now and then, a mob (respawn as an egg on
+    a free cell drawn from the RNG, y not flipped: SURVEY Q17) — paths uniform-random actions hardly reach."""
+    if not oracle_available:
+        pytest.skip("oracle/_ref not built")
+    from oracle import ref_env
+    n, seed, T = 16, 555, 1500
+    rs = np.random.RandomState(seed)
+    sim = SimAdapter("chaser", n, seed, distribution_mode=-1 if mode is None else mode)
+    refs = [ref_env.RefEnv("chaser", seed + i, mode=mode) for i in range(n)]
+    np.testing.assert_array_equal(sim.reset(), np.stack([r.reset() for r in refs]))
+    cur = rs.choice([1, 7, 3, 5], size=n)
+    orbs, prev_eat = 0, np.zeros(n, np.float32)
+    for t in range(T):
+        cur = np.where(rs.rand(n) < 0.08, rs.choice([1, 7, 3, 5], size=n), cur)
+        a = cur.astype(np.int32)
+        o, rw, d = sim.step(a)
+        eat = sim.sim.field("eat_timer")[0].view(np.float32).copy()
+        orbs += int(((eat > prev_eat) & ~d).sum())
+        prev_eat = eat
+        for i, r in enumerate(refs):
+            oo, w, dd = r.step(a[i])
+            if dd:
+                oo = r.reset()
+            assert w == rw[i] and dd == d[i], (t, i)
+            np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))
+    f = sim.fields()
+    for i, r in enumerate(refs):
+        st, pos = r.rng_state()
+        assert pos == f["mti"][i]
+        np.testing.assert_array_equal(st, f["mt"][i])
+        r.close()
+    assert orbs >= 5, orbs
