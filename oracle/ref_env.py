@@ -84,6 +84,8 @@ class RefEnv:
         self.lib.cenv_make.argtypes = [ctypes.c_char_p, ctypes.POINTER(Option), ctypes.c_int32]
         self.lib.cenv_reset.argtypes = [ctypes.POINTER(Option), ctypes.c_int32]
         self.lib.cenv_step.argtypes = [ctypes.POINTER(KeyValue), ctypes.c_int32]
+        if mode is not None and game in ("coinrun", "climber"):   # their Config has a bool easy_mode instead of the enum
+            easy_mode, mode = (int(mode) == 0), None
         if easy_mode is not None:   # compile-time Config::easy_mode of the generator (coinrun, climber), set through the probe
             self.probe("pg2o_set_easy_mode", None, [ctypes.c_int])(1 if easy_mode else 0)
         late_mode = mode is not None and game == "bossfight"   # its Config lives in a system cenv_make creates; only update() reads it
