@@ -362,3 +362,40 @@ def test_chaser_orbs_and_eaten_mobs_live_oracle(mode, oracle_available):
     for r in refs:
         r.close()
     env.close()
+
+
+# ---- purposeful action streams for the warp-per-env platformers ------------------------------------------------------------
+
+@pytest.mark.parametrize("game,bias", [("coinrun", [8, 8, 7, 7, 5, 8, 6, 1, 4, 8]), ("climber", [2, 5, 8, 8, 2, 5, 1, 7, 5, 5])])
+def test_biased_actions_live_oracle(game, bias, oracle_available):
+    """Run-right-and-jump (coinrun) / jump-a-lot (climber) action streams, held for 6 steps with 15 % noise: the agents get
+    deep into their levels (crates, saws, lava, enemies, coins; 50x more rewarded steps than uniform-random actions), through
+    the warp-per-env k_step with the entity loops on the lanes."""
+    ref_env = _need_oracle(oracle_available)
+    from procgen2_b200.engine import BatchedEnv
+    n, seed, T = 32, 31415, 800
+    rs = np.random.RandomState(seed)
+    run = np.array(bias)[rs.randint(0, len(bias), size=(T // 6 + 1, n))]
+    acts = np.repeat(run, 6, axis=0)[:T]
+    acts = np.where(rs.rand(T, n) < 0.15, rs.randint(0, 15, size=(T, n)), acts).astype(np.int32)
+    env = BatchedEnv(game, n, seed=seed)
+    refs = [ref_env.RefEnv(game, seed + i) for i in range(n)]
+    env.reset()
+    np.testing.assert_array_equal(env.fetch()[0], np.stack([r.reset() for r in refs]))
+    rewarded = 0
+    for t in range(T):
+        env.step(acts[t])
+        o, rw, d, _ = env.fetch()
+        for i, r in enumerate(refs):
+            oo, w, dd = r.step(acts[t, i])
+            if dd:
+                oo = r.reset()
+            rewarded += w > 0
+            assert w == rw[i] and dd == d[i], (t, i)
+            np.testing.assert_array_equal(o[i], oo, err_msg="step %d env %d" % (t, i))
+    _check_state(env, refs, tag=game)
+    _assert_no_fault(env)
+    assert rewarded >= 3, rewarded
+    for r in refs:
+        r.close()
+    env.close()
