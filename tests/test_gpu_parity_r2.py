@@ -399,3 +399,20 @@ def test_biased_actions_live_oracle(game, bias, oracle_available):
     for r in refs:
         r.close()
     env.close()
+
+
+def test_bossfight_partial_last_warp_live_oracle(oracle_available):
+    """13 envs with 8 lanes each: the last warp of k_step<bossfight> holds ONE env and three idle lane groups."""
+    ref_env = _need_oracle(oracle_available)
+    from tests.parity_util import check_against_oracle
+    from tests.test_gpu_parity import EngineAdapter
+    n, T, seed = 13, 200, 8100
+    acts = _mixed_actions(np.random.RandomState(3), T, n)
+    a = EngineAdapter("bossfight", n, seed)
+    refs = [ref_env.RefEnv("bossfight", seed + i) for i in range(n)]
+    check_against_oracle(a, refs, acts, tag="bossfight 13 envs")
+    _check_state(a.env, refs, tag="bossfight 13 envs")
+    _assert_no_fault(a.env)
+    for r in refs:
+        r.close()
+    a.env.close()
